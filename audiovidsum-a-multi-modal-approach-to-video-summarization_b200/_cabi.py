@@ -1,0 +1,128 @@
+"""ctypes binding of ``libavsum_b200.so`` (the C ABI in ``include/avsum_b200.h``).
+
+This module is the only place Python touches the native library.  It never falls
+back to another implementation: if the library is missing or a call fails, an
+exception carrying ``avs_last_error()`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavsum_b200.so")
+
+AVS_OK, AVS_ERR_INVALID, AVS_ERR_UNSUPPORTED, AVS_ERR_CUDA, AVS_ERR_OOM = range(5)
+AVS_HOST, AVS_DEVICE = 0, 1
+AVS_ATTN_LITERAL, AVS_ATTN_TEMPORAL, AVS_ATTN_LITERAL_B1 = 0, 1, 2
+AVS_PREC_TF32, AVS_PREC_BF16, AVS_PREC_FP32_SIMT = 0, 1, 2
+
+ATTN_AXES = {"literal": AVS_ATTN_LITERAL, "temporal": AVS_ATTN_TEMPORAL, "literal_b1": AVS_ATTN_LITERAL_B1}
+PRECISIONS = {"tf32": AVS_PREC_TF32, "bf16": AVS_PREC_BF16, "fp32_simt": AVS_PREC_FP32_SIMT}
+
+# every symbol include/avsum_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "avs_last_error", "avs_version", "avs_device_ok", "avs_model_create", "avs_model_update",
+    "avs_model_destroy", "avs_forward", "avs_summarize", "avs_linear", "avs_bilstm_pair",
+    "avs_attention", "avs_temporal_f1", "avs_launch_count",
+]
+
+
+class AvsError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"avsum_b200 native call failed (status {status}): {message}")
+        self.status = status
+
+
+class AvsUnsupported(AvsError, NotImplementedError):
+    pass
+
+
+class AvsWeights(C.Structure):
+    _fields_ = [
+        ("visual_dim", C.c_int32), ("audio_dim", C.c_int32), ("hidden_dim", C.c_int32), ("num_heads", C.c_int32),
+        ("visual_fc_w", C.c_void_p), ("visual_fc_b", C.c_void_p),
+        ("audio_fc_w", C.c_void_p), ("audio_fc_b", C.c_void_p),
+        ("lstm_w_ih", C.c_void_p * 4), ("lstm_w_hh", C.c_void_p * 4),
+        ("lstm_b_ih", C.c_void_p * 4), ("lstm_b_hh", C.c_void_p * 4),
+        ("attn_in_w", C.c_void_p), ("attn_in_b", C.c_void_p),
+        ("attn_out_w", C.c_void_p), ("attn_out_b", C.c_void_p),
+        ("scorer0_w", C.c_void_p), ("scorer0_b", C.c_void_p),
+        ("scorer2_w", C.c_void_p), ("scorer2_b", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/ -> libavsum_b200.so with nvcc for sm_100a (no GPU needed)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libavsum_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load the native library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C <package>/csrc`).  avsum_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.avs_last_error.restype = C.c_char_p
+    L.avs_last_error.argtypes = []
+    L.avs_version.restype = C.c_int
+    L.avs_device_ok.restype = C.c_int
+    L.avs_launch_count.restype = i64
+    L.avs_model_create.restype = C.c_int
+    L.avs_model_create.argtypes = [C.POINTER(AvsWeights), C.c_int, C.POINTER(vp)]
+    L.avs_model_update.restype = C.c_int
+    L.avs_model_update.argtypes = [vp, C.POINTER(AvsWeights)]
+    L.avs_model_destroy.restype = None
+    L.avs_model_destroy.argtypes = [vp]
+    L.avs_forward.restype = C.c_int
+    L.avs_forward.argtypes = [vp, vp, vp, i64, i32, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.avs_summarize.restype = C.c_int
+    L.avs_summarize.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, C.c_int, vp]
+    L.avs_linear.restype = C.c_int
+    L.avs_linear.argtypes = [vp, vp, vp, i64, i32, i32, C.c_int, C.c_int, vp, vp]
+    L.avs_bilstm_pair.restype = C.c_int
+    L.avs_bilstm_pair.argtypes = [vp, vp, vp, i64, i32, vp, vp, C.c_int, vp, vp]
+    L.avs_attention.restype = C.c_int
+    L.avs_attention.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, C.c_int, vp, vp]
+    L.avs_temporal_f1.restype = C.c_int
+    L.avs_temporal_f1.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    _lib = L
+    return L
+
+
+def check(status: int) -> None:
+    if status == AVS_OK:
+        return
+    msg = lib().avs_last_error().decode("utf-8", "replace")
+    if status == AVS_ERR_UNSUPPORTED:
+        raise AvsUnsupported(status, msg)
+    if status == AVS_ERR_INVALID:
+        raise ValueError(f"avsum_b200: {msg}")
+    if status == AVS_ERR_OOM:
+        raise MemoryError(f"avsum_b200: {msg}")
+    raise AvsError(status, msg)
+
+
+def np_ptr(a):
+    """void* of a C-contiguous numpy array (host descriptor arrays)."""
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def launch_count() -> int:
+    return int(lib().avs_launch_count())

@@ -1,0 +1,749 @@
+// C ABI of libavsum_b200.so (declared in include/avsum_b200.h): model handle, weight packing,
+// workspace management and the orchestration of AVBiLSTMModel.forward
+// (/root/reference/models/av_model.py:33-46) as a short chain of sm_100a kernels.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace avs {
+
+thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+constexpr int HC = 256;  // the kernels are built for hidden_dim = 512 (SURVEY.md 8a defaults)
+constexpr int H = 512;
+constexpr int E = 1024;
+constexpr int G4 = 4 * HC;  // 1024 gate rows per direction
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0;
+    size_t off = 0;
+    avs_status reserve(size_t bytes) {
+        if (bytes <= cap) return AVS_OK;
+        if (base) AVS_CUDA(cudaFree(base));  // synchronises with outstanding work
+        base = nullptr;
+        cap = 0;
+        const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+        AVS_CUDA(cudaMalloc(&base, want));
+        cap = want;
+        return AVS_OK;
+    }
+    void reset() { off = 0; }
+    template <typename T>
+    T* take(size_t n) {
+        off = align_up(off, 256);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = off = 0;
+    }
+};
+
+// dst[p, :] = src[perm(p), :] for the LSTM gate interleave:
+//   packed row p = cta*128 + gate*32 + jj   <-   original row gate*256 + cta*32 + jj
+__global__ void permute_gate_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int cols,
+                                         int round_tf32) {
+    const int p = blockIdx.x;
+    const int cta = p >> 7, gate = (p >> 5) & 3, jj = p & 31;
+    const int o = gate * HC + cta * 32 + jj;
+    for (int k = threadIdx.x; k < cols; k += blockDim.x) {
+        const float v = src[static_cast<size_t>(o) * cols + k];
+        dst[static_cast<size_t>(p) * cols + k] = round_tf32 ? to_tf32_rn(v) : v;
+    }
+}
+__global__ void permute_gate_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                         float* __restrict__ dst) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= G4) return;
+    const int cta = p >> 7, gate = (p >> 5) & 3, jj = p & 31;
+    const int o = gate * HC + cta * 32 + jj;
+    dst[p] = b_ih[o] + b_hh[o];
+}
+
+}  // namespace
+}  // namespace avs
+
+using namespace avs;
+
+struct avs_model {
+    int device = 0;
+    int Dv = 0, Da = 0, heads = 4;
+    // packed parameters (one slab); *_x = exact fp32, *_t = tf32-rounded copies
+    char* slab = nullptr;
+    float *fc_v_w_x, *fc_v_w_t, *fc_a_w_x, *fc_a_w_t, *fc_v_b, *fc_a_b;
+    float *ih_v_x, *ih_v_t, *ih_a_x, *ih_a_t;  // [2048, 512] packed gate order, both directions
+    float *ih_v_b, *ih_a_b;                    // [2048]
+    float* whh;                                // [4][1024][256] packed gate order, exact fp32
+    float *in_w_x, *in_w_t, *in_b, *out_w_x, *out_w_t, *out_b;
+    float *sc0_w_x, *sc0_w_t, *sc0_b, *sc2_w, *sc2_b;
+    Arena ws;       // activations
+    Arena staging;  // raw weights during packing
+};
+
+namespace {
+
+avs_status check_dims(const avs_weights* w) {
+    AVS_CHECK(w != nullptr, AVS_ERR_INVALID, "weights pointer is null");
+    AVS_CHECK(w->hidden_dim == H, AVS_ERR_UNSUPPORTED,
+              "hidden_dim=%d: the sm_100a kernels are built for hidden_dim=512 (reference default)", w->hidden_dim);
+    AVS_CHECK(w->visual_dim > 0 && w->audio_dim > 0, AVS_ERR_INVALID, "feature dims must be positive");
+    AVS_CHECK(w->visual_dim % 4 == 0 && w->audio_dim % 4 == 0, AVS_ERR_UNSUPPORTED,
+              "visual_dim/audio_dim must be multiples of 4 (16-byte TMA row pitch); got %d/%d", w->visual_dim,
+              w->audio_dim);
+    AVS_CHECK(w->num_heads > 0 && E % w->num_heads == 0 && (E / w->num_heads) % 32 == 0 &&
+                  E / w->num_heads <= 256,
+              AVS_ERR_UNSUPPORTED, "num_heads=%d unsupported (head dim must be a multiple of 32, <= 256)",
+              w->num_heads);
+    const void* ptrs[] = {w->visual_fc_w, w->visual_fc_b, w->audio_fc_w, w->audio_fc_b, w->attn_in_w, w->attn_in_b,
+                          w->attn_out_w,  w->attn_out_b,  w->scorer0_w,  w->scorer0_b,  w->scorer2_w, w->scorer2_b};
+    for (const void* p : ptrs) AVS_CHECK(p != nullptr, AVS_ERR_INVALID, "a weight pointer is null");
+    for (int i = 0; i < 4; ++i)
+        AVS_CHECK(w->lstm_w_ih[i] && w->lstm_w_hh[i] && w->lstm_b_ih[i] && w->lstm_b_hh[i], AVS_ERR_INVALID,
+                  "an LSTM weight pointer is null");
+    return AVS_OK;
+}
+
+avs_status pack_weights(avs_model* m, const avs_weights* w) {
+    const int Dv = m->Dv, Da = m->Da;
+    cudaStream_t st = 0;
+    // raw copies
+    const size_t raw_elems = static_cast<size_t>(H) * (Dv + Da) + 2 * H + 4 * (static_cast<size_t>(G4) * H + G4 * HC + 2 * G4) +
+                             3ull * E * E + 3 * E + static_cast<size_t>(E) * E + E + 64ull * E + 64 + 64 + 1;
+    AVS_TRY(m->staging.reserve(raw_elems * sizeof(float) + 64 * 256));
+    m->staging.reset();
+    auto up = [&](const float* src, size_t n, float** dst) -> avs_status {
+        *dst = m->staging.take<float>(n);
+        AVS_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDefault, st));
+        return AVS_OK;
+    };
+    float *r_fcv, *r_fca, *r_ih[4], *r_hh[4], *r_bih[4], *r_bhh[4], *r_inw, *r_outw, *r_sc0;
+    AVS_TRY(up(w->visual_fc_w, static_cast<size_t>(H) * Dv, &r_fcv));
+    AVS_TRY(up(w->audio_fc_w, static_cast<size_t>(H) * Da, &r_fca));
+    for (int i = 0; i < 4; ++i) {
+        AVS_TRY(up(w->lstm_w_ih[i], static_cast<size_t>(G4) * H, &r_ih[i]));
+        AVS_TRY(up(w->lstm_w_hh[i], static_cast<size_t>(G4) * HC, &r_hh[i]));
+        AVS_TRY(up(w->lstm_b_ih[i], G4, &r_bih[i]));
+        AVS_TRY(up(w->lstm_b_hh[i], G4, &r_bhh[i]));
+    }
+    AVS_TRY(up(w->attn_in_w, 3ull * E * E, &r_inw));
+    AVS_TRY(up(w->attn_out_w, static_cast<size_t>(E) * E, &r_outw));
+    AVS_TRY(up(w->scorer0_w, 64ull * E, &r_sc0));
+    // direct (unpacked) small tensors
+    AVS_CUDA(cudaMemcpyAsync(m->fc_v_b, w->visual_fc_b, H * sizeof(float), cudaMemcpyDefault, st));
+    AVS_CUDA(cudaMemcpyAsync(m->fc_a_b, w->audio_fc_b, H * sizeof(float), cudaMemcpyDefault, st));
+    AVS_CUDA(cudaMemcpyAsync(m->in_b, w->attn_in_b, 3 * E * sizeof(float), cudaMemcpyDefault, st));
+    AVS_CUDA(cudaMemcpyAsync(m->out_b, w->attn_out_b, E * sizeof(float), cudaMemcpyDefault, st));
+    AVS_CUDA(cudaMemcpyAsync(m->sc0_b, w->scorer0_b, 64 * sizeof(float), cudaMemcpyDefault, st));
+    AVS_CUDA(cudaMemcpyAsync(m->sc2_w, w->scorer2_w, 64 * sizeof(float), cudaMemcpyDefault, st));
+    AVS_CUDA(cudaMemcpyAsync(m->sc2_b, w->scorer2_b, sizeof(float), cudaMemcpyDefault, st));
+    // exact + tf32 copies of the GEMM weights
+    auto both = [&](const float* raw, size_t n, float* exact, float* tf) -> avs_status {
+        AVS_CUDA(cudaMemcpyAsync(exact, raw, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return convert_f32(raw, tf, static_cast<int64_t>(n), DT_F32, 1, st);
+    };
+    AVS_TRY(both(r_fcv, static_cast<size_t>(H) * Dv, m->fc_v_w_x, m->fc_v_w_t));
+    AVS_TRY(both(r_fca, static_cast<size_t>(H) * Da, m->fc_a_w_x, m->fc_a_w_t));
+    AVS_TRY(both(r_inw, 3ull * E * E, m->in_w_x, m->in_w_t));
+    AVS_TRY(both(r_outw, static_cast<size_t>(E) * E, m->out_w_x, m->out_w_t));
+    AVS_TRY(both(r_sc0, 64ull * E, m->sc0_w_x, m->sc0_w_t));
+    // LSTM: gate-interleaved row order so that cluster CTA r owns 128 contiguous gate columns
+    for (int i = 0; i < 4; ++i) {
+        const int mod = i >> 1, dir = i & 1;
+        float* ih_x = (mod ? m->ih_a_x : m->ih_v_x) + static_cast<size_t>(dir) * G4 * H;
+        float* ih_t = (mod ? m->ih_a_t : m->ih_v_t) + static_cast<size_t>(dir) * G4 * H;
+        float* bias = (mod ? m->ih_a_b : m->ih_v_b) + dir * G4;
+        permute_gate_rows_kernel<<<G4, 128, 0, st>>>(r_ih[i], ih_x, H, 0);
+        AVS_LAUNCH_CHECK();
+        permute_gate_rows_kernel<<<G4, 128, 0, st>>>(r_ih[i], ih_t, H, 1);
+        AVS_LAUNCH_CHECK();
+        permute_gate_rows_kernel<<<G4, 128, 0, st>>>(r_hh[i], m->whh + static_cast<size_t>(i) * G4 * HC, HC, 0);
+        AVS_LAUNCH_CHECK();
+        permute_gate_bias_kernel<<<(G4 + 255) / 256, 256, 0, st>>>(r_bih[i], r_bhh[i], bias);
+        AVS_LAUNCH_CHECK();
+    }
+    AVS_CUDA(cudaStreamSynchronize(st));
+    return AVS_OK;
+}
+
+struct Guard {  // restore the caller's current device
+    int prev = -1;
+    explicit Guard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~Guard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+avs_status validate_videos(int64_t total_rows, int32_t n, const int32_t* row_start, const int32_t* lengths,
+                           int* max_len) {
+    AVS_CHECK(total_rows >= 0 && total_rows < (1ll << 31), AVS_ERR_INVALID, "total_rows out of range");
+    AVS_CHECK(n >= 0, AVS_ERR_INVALID, "n_videos negative");
+    AVS_CHECK(n == 0 || (row_start && lengths), AVS_ERR_INVALID, "row_start / lengths null");
+    int mx = 0;
+    for (int b = 0; b < n; ++b) {
+        AVS_CHECK(lengths[b] >= 0 && row_start[b] >= 0 &&
+                      static_cast<int64_t>(row_start[b]) + lengths[b] <= total_rows,
+                  AVS_ERR_INVALID, "video %d: rows [%d, %d) outside [0, %lld)", b, row_start[b],
+                  row_start[b] + lengths[b], static_cast<long long>(total_rows));
+        mx = std::max(mx, lengths[b]);
+    }
+    *max_len = mx;
+    return AVS_OK;
+}
+
+// Length-sorted grouping of videos into LSTM clusters.
+struct LstmPlan {
+    std::vector<int32_t> host;  // [slot_row_start | slot_len | group_maxlen]
+    int nb = 1, n_groups = 0;
+};
+LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths) {
+    std::vector<int> order;
+    for (int b = 0; b < n; ++b)
+        if (lengths[b] > 0) order.push_back(b);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lengths[a] > lengths[b]; });
+    LstmPlan p;
+    const int B = static_cast<int>(order.size());
+    if (B == 0) return p;
+    p.nb = 16;
+    for (int nb : {1, 2, 4, 8, 16}) {
+        if (((B + nb - 1) / nb) * 4 <= 16) { p.nb = nb; break; }
+    }
+    p.n_groups = (B + p.nb - 1) / p.nb;
+    const int slots = p.n_groups * p.nb;
+    p.host.assign(2 * slots + p.n_groups, 0);
+    const int base = B / p.n_groups, rem = B % p.n_groups;
+    int idx = 0;
+    for (int g = 0; g < p.n_groups; ++g) {
+        const int cnt = base + (g < rem ? 1 : 0);
+        p.host[2 * slots + g] = lengths[order[idx]];
+        for (int i = 0; i < cnt; ++i, ++idx) {
+            p.host[g * p.nb + i] = row_start[order[idx]];
+            p.host[slots + g * p.nb + i] = lengths[order[idx]];
+        }
+    }
+    return p;
+}
+
+avs_status run_gemm(int precision, const float* A, int64_t lda, const float* w_exact, const float* w_tf32, int64_t ldw,
+                    int64_t M, int N, int K, GemmEpilogue epi, cudaStream_t st) {
+    if (precision == AVS_PREC_FP32_SIMT) {
+        epi.round_tf32 = 0;
+        return gemm_simt(A, lda, w_exact, ldw, M, N, K, epi, st);
+    }
+    return gemm_tc(A, lda, w_tf32, ldw, DT_F32, M, N, K, epi, st);
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* avs_last_error(void) { return g_err; }
+int avs_version(void) { return 100; }
+int64_t avs_launch_count(void) { return g_launches.load(); }
+
+int avs_device_ok(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaDeviceProp p;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+    return p.major == 10 ? 1 : 0;
+}
+
+avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
+    AVS_CHECK(out != nullptr, AVS_ERR_INVALID, "out pointer is null");
+    *out = nullptr;
+    AVS_TRY(check_dims(w));
+    int n = 0;
+    AVS_CUDA(cudaGetDeviceCount(&n));
+    AVS_CHECK(device >= 0 && device < n, AVS_ERR_CUDA, "CUDA device %d not available (%d visible)", device, n);
+    cudaDeviceProp prop;
+    AVS_CUDA(cudaGetDeviceProperties(&prop, device));
+    AVS_CHECK(prop.major == 10, AVS_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only",
+              device, prop.major, prop.minor);
+    Guard g(device);
+    avs_model* m = new avs_model();
+    m->device = device;
+    m->Dv = w->visual_dim;
+    m->Da = w->audio_dim;
+    m->heads = w->num_heads;
+    const size_t Dv = m->Dv, Da = m->Da;
+    struct Item { float** p; size_t n; };
+    Item items[] = {
+        {&m->fc_v_w_x, H * Dv}, {&m->fc_v_w_t, H * Dv}, {&m->fc_a_w_x, H * Da}, {&m->fc_a_w_t, H * Da},
+        {&m->fc_v_b, H}, {&m->fc_a_b, H},
+        {&m->ih_v_x, 2ull * G4 * H}, {&m->ih_v_t, 2ull * G4 * H}, {&m->ih_a_x, 2ull * G4 * H}, {&m->ih_a_t, 2ull * G4 * H},
+        {&m->ih_v_b, 2 * G4}, {&m->ih_a_b, 2 * G4}, {&m->whh, 4ull * G4 * HC},
+        {&m->in_w_x, 3ull * E * E}, {&m->in_w_t, 3ull * E * E}, {&m->in_b, 3 * E},
+        {&m->out_w_x, 1ull * E * E}, {&m->out_w_t, 1ull * E * E}, {&m->out_b, E},
+        {&m->sc0_w_x, 64ull * E}, {&m->sc0_w_t, 64ull * E}, {&m->sc0_b, 64}, {&m->sc2_w, 64}, {&m->sc2_b, 64}};
+    size_t total = 0;
+    for (auto& it : items) total += align_up(it.n * sizeof(float), 256);
+    cudaError_t e = cudaMalloc(&m->slab, total);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) for packed weights failed: %s", total, cudaGetErrorString(e));
+        delete m;
+        return AVS_ERR_OOM;
+    }
+    size_t off = 0;
+    for (auto& it : items) {
+        *it.p = reinterpret_cast<float*>(m->slab + off);
+        off += align_up(it.n * sizeof(float), 256);
+    }
+    avs_status s = pack_weights(m, w);
+    if (s != AVS_OK) {
+        avs_model_destroy(m);
+        return s;
+    }
+    *out = m;
+    return AVS_OK;
+}
+
+avs_status avs_model_update(avs_model* m, const avs_weights* w) {
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_TRY(check_dims(w));
+    AVS_CHECK(w->visual_dim == m->Dv && w->audio_dim == m->Da, AVS_ERR_INVALID,
+              "avs_model_update: feature dims differ from the handle's");
+    m->heads = w->num_heads;
+    Guard g(m->device);
+    return pack_weights(m, w);
+}
+
+void avs_model_destroy(avs_model* m) {
+    if (!m) return;
+    Guard g(m->device);
+    m->ws.release();
+    m->staging.release();
+    if (m->slab) cudaFree(m->slab);
+    delete m;
+}
+
+avs_status avs_forward(avs_model* m, const float* visual, const float* audio, int64_t total_rows, int32_t n_videos,
+                       const int32_t* row_start, const int32_t* lengths, int attn_axis, int precision, float* scores,
+                       int space, void* cuda_stream) {
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
+    AVS_CHECK(precision == AVS_PREC_TF32 || precision == AVS_PREC_FP32_SIMT, AVS_ERR_UNSUPPORTED,
+              "precision %d not available in this build", precision);
+    AVS_CHECK(attn_axis == AVS_ATTN_LITERAL || attn_axis == AVS_ATTN_TEMPORAL || attn_axis == AVS_ATTN_LITERAL_B1,
+              AVS_ERR_INVALID, "bad attn_axis %d", attn_axis);
+    int max_len = 0;
+    AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
+    if (total_rows == 0 || n_videos == 0 || max_len == 0) return AVS_OK;
+    AVS_CHECK(visual && audio && scores, AVS_ERR_INVALID, "visual / audio / scores pointer is null");
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int64_t R = total_rows;
+    const int Dv = m->Dv, Da = m->Da;
+    const bool simt = precision == AVS_PREC_FP32_SIMT;
+    const int rnd = simt ? 0 : 1;
+
+    bool literal_rows = attn_axis == AVS_ATTN_LITERAL_B1 || (attn_axis == AVS_ATTN_LITERAL && n_videos == 1);
+    if (attn_axis == AVS_ATTN_LITERAL && n_videos > 1) {
+        for (int b = 0; b < n_videos; ++b)
+            AVS_CHECK(lengths[b] == lengths[0] && row_start[b] == row_start[0] + b * lengths[0], AVS_ERR_INVALID,
+                      "AVS_ATTN_LITERAL mixes the videos of a batch (av_model.py:44) and needs a dense [B, T] "
+                      "layout with equal lengths; video %d breaks it", b);
+    }
+
+    // ---- plan + workspace
+    LstmPlan plan = plan_lstm(n_videos, row_start, lengths);
+    const int n_seqs = literal_rows ? 0 : (attn_axis == AVS_ATTN_TEMPORAL ? n_videos : lengths[0]);
+    const size_t act_floats = static_cast<size_t>(R) * (Dv + Da + 2 * H + 2 * 2 * G4 + E + 3 * E + E + E + 1);
+    AVS_TRY(m->ws.reserve(act_floats * sizeof(float) + (plan.host.size() + 3 * static_cast<size_t>(n_seqs)) * 4 +
+                          64 * 256));
+    m->ws.reset();
+    float* in_v = m->ws.take<float>(R * Dv);
+    float* in_a = m->ws.take<float>(R * Da);
+    float* v_emb = m->ws.take<float>(R * H);
+    float* a_emb = m->ws.take<float>(R * H);
+    float* xg_v = m->ws.take<float>(R * 2 * G4);
+    float* xg_a = m->ws.take<float>(R * 2 * G4);
+    float* fused = m->ws.take<float>(R * E);
+    float* qkv = m->ws.take<float>(R * 3 * E);
+    float* ctx = m->ws.take<float>(R * E);
+    float* attn_out = m->ws.take<float>(R * E);
+    float* scores_dev = space == AVS_DEVICE ? scores : m->ws.take<float>(R);
+    int32_t* plan_dev = m->ws.take<int32_t>(plan.host.size());
+    int32_t* seq_dev = m->ws.take<int32_t>(3 * static_cast<size_t>(std::max(n_seqs, 1)));
+
+    // ---- inputs: H2D (host space) and tf32 rounding of the user features
+    const float* xv = visual;
+    const float* xa = audio;
+    if (space == AVS_HOST) {
+        AVS_CUDA(cudaMemcpyAsync(in_v, visual, static_cast<size_t>(R) * Dv * 4, cudaMemcpyHostToDevice, st));
+        AVS_CUDA(cudaMemcpyAsync(in_a, audio, static_cast<size_t>(R) * Da * 4, cudaMemcpyHostToDevice, st));
+        xv = in_v;
+        xa = in_a;
+    }
+    if (!simt) {
+        AVS_TRY(convert_f32(xv, in_v, R * Dv, DT_F32, 1, st));
+        AVS_TRY(convert_f32(xa, in_a, R * Da, DT_F32, 1, st));
+        xv = in_v;
+        xa = in_a;
+    }
+    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
+
+    // ---- K1: visual_fc / audio_fc (Linear + ReLU; Dropout is identity in eval)  av_model.py:35-36
+    GemmEpilogue e1;
+    e1.relu = 1;
+    e1.round_tf32 = rnd;
+    e1.ldc = H;
+    e1.bias = m->fc_v_b;
+    e1.C = v_emb;
+    AVS_TRY(run_gemm(precision, xv, Dv, m->fc_v_w_x, m->fc_v_w_t, Dv, R, H, Dv, e1, st));
+    e1.bias = m->fc_a_b;
+    e1.C = a_emb;
+    AVS_TRY(run_gemm(precision, xa, Da, m->fc_a_w_x, m->fc_a_w_t, Da, R, H, Da, e1, st));
+
+    // ---- K2a: LSTM input projections, both directions at once  av_model.py:39-40
+    GemmEpilogue e2;
+    e2.ldc = 2 * G4;
+    e2.bias = m->ih_v_b;
+    e2.C = xg_v;
+    AVS_TRY(run_gemm(precision, v_emb, H, m->ih_v_x, m->ih_v_t, H, R, 2 * G4, H, e2, st));
+    e2.bias = m->ih_a_b;
+    e2.C = xg_a;
+    AVS_TRY(run_gemm(precision, a_emb, H, m->ih_a_x, m->ih_a_t, H, R, 2 * G4, H, e2, st));
+
+    // ---- K2b: recurrences; writes [v_fwd | v_bwd | a_fwd | a_bwd] = torch.cat of av_model.py:43
+    {
+        const int slots = plan.n_groups * plan.nb;
+        LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
+        AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, rnd, nullptr, 0, st));
+    }
+
+    // ---- K3/K4: nn.MultiheadAttention  av_model.py:44
+    const float* ctx_ptr = ctx;
+    int64_t ctx_ld = E;
+    if (literal_rows) {
+        // sequence length 1: softmax weight == 1, context == value projection
+        GemmEpilogue e3;
+        e3.bias = m->in_b + 2 * E;
+        e3.C = ctx;
+        e3.ldc = E;
+        e3.round_tf32 = rnd;
+        AVS_TRY(run_gemm(precision, fused, E, m->in_w_x + 2ull * E * E, m->in_w_t + 2ull * E * E, E, R, E, E, e3, st));
+    } else {
+        GemmEpilogue e3;
+        e3.bias = m->in_b;
+        e3.C = qkv;
+        e3.ldc = 3 * E;
+        AVS_TRY(run_gemm(precision, fused, E, m->in_w_x, m->in_w_t, E, R, 3 * E, E, e3, st));
+        std::vector<int32_t> sd(3 * static_cast<size_t>(n_seqs));
+        int seq_max = 0;
+        if (attn_axis == AVS_ATTN_TEMPORAL) {
+            for (int b = 0; b < n_videos; ++b) {
+                sd[b] = row_start[b];
+                sd[n_seqs + b] = 1;
+                sd[2 * n_seqs + b] = lengths[b];
+            }
+            seq_max = max_len;
+        } else {
+            for (int t = 0; t < n_seqs; ++t) {
+                sd[t] = row_start[0] + t;
+                sd[n_seqs + t] = lengths[0];
+                sd[2 * n_seqs + t] = n_videos;
+            }
+            seq_max = n_videos;
+        }
+        AVS_CUDA(cudaMemcpyAsync(seq_dev, sd.data(), sd.size() * 4, cudaMemcpyHostToDevice, st));
+        SeqDesc seqs{seq_dev, seq_dev + n_seqs, seq_dev + 2 * n_seqs, n_seqs, seq_max};
+        AVS_TRY(attention_simt(qkv, 3 * E, E, m->heads, seqs, ctx, E, rnd, st));
+    }
+
+    // ---- K5: out_proj
+    GemmEpilogue e5;
+    e5.bias = m->out_b;
+    e5.C = attn_out;
+    e5.ldc = E;
+    e5.round_tf32 = rnd;
+    AVS_TRY(run_gemm(precision, ctx_ptr, ctx_ld, m->out_w_x, m->out_w_t, E, R, E, E, e5, st));
+
+    // ---- K6: scorer (Linear 1024->64 + ReLU + Linear 64->1 + Sigmoid fused)  av_model.py:29-31,46
+    GemmEpilogue e6;
+    e6.bias = m->sc0_b;
+    e6.relu = 1;
+    e6.score_w2 = m->sc2_w;
+    e6.score_b2 = m->sc2_b;
+    e6.scores = scores_dev;
+    AVS_TRY(run_gemm(precision, attn_out, E, m->sc0_w_x, m->sc0_w_t, E, R, 64, E, e6, st));
+
+    if (space == AVS_HOST) {
+        AVS_CUDA(cudaMemcpyAsync(scores, scores_dev, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost, st));
+        AVS_CUDA(cudaStreamSynchronize(st));
+    }
+    return AVS_OK;
+}
+
+avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* positions, int32_t n_videos,
+                         const int32_t* row_start, const int32_t* lengths, const int32_t* n_frames, const int32_t* cps,
+                         const int32_t* cps_start, int32_t prop_num, int32_t prop_den, uint8_t* picks,
+                         int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start, int space,
+                         void* cuda_stream) {
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
+    AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
+    if (n_videos == 0) return AVS_OK;
+    AVS_CHECK(scores && positions && row_start && lengths && n_frames && cps_start && picks, AVS_ERR_INVALID,
+              "a required pointer is null");
+    AVS_CHECK(prop_den > 0 && prop_num >= 0, AVS_ERR_INVALID, "bad proportion %d/%d", prop_num, prop_den);
+    AVS_CHECK(summary == nullptr || summary_start != nullptr, AVS_ERR_INVALID, "summary_start is null");
+    const int n = n_videos;
+    AVS_CHECK(cps_start[0] == 0, AVS_ERR_INVALID, "cps_start[0] must be 0");
+    const int total_S = cps_start[n];
+    AVS_CHECK(total_S == 0 || cps != nullptr, AVS_ERR_INVALID, "cps is null");
+    int64_t rows = 0;
+    std::vector<int64_t> off(2 * (static_cast<size_t>(n) + 1), 0);  // keep_start | dp_start
+    int max_cap = 0;
+    for (int v = 0; v < n; ++v) {
+        AVS_CHECK(lengths[v] >= 0 && row_start[v] >= 0 && n_frames[v] >= 0, AVS_ERR_INVALID, "video %d: bad sizes", v);
+        AVS_CHECK(cps_start[v + 1] >= cps_start[v], AVS_ERR_INVALID, "cps_start not monotone at %d", v);
+        rows = std::max<int64_t>(rows, static_cast<int64_t>(row_start[v]) + lengths[v]);
+        int prev_end = -1;
+        for (int s = cps_start[v]; s < cps_start[v + 1]; ++s) {
+            const int a = cps[2 * s], b = cps[2 * s + 1];
+            AVS_CHECK(a > prev_end && b >= a && b < n_frames[v], AVS_ERR_INVALID,
+                      "video %d shot %d = [%d, %d]: change points must be sorted, disjoint, inclusive and inside "
+                      "[0, n_frames)", v, s - cps_start[v], a, b);
+            prev_end = b;
+        }
+        const long long cap = (static_cast<long long>(n_frames[v]) * prop_num) / prop_den;
+        AVS_CHECK(cap < (1ll << 30), AVS_ERR_UNSUPPORTED, "video %d: capacity too large", v);
+        max_cap = std::max(max_cap, static_cast<int>(cap));
+        const int S = cps_start[v + 1] - cps_start[v];
+        off[v + 1] = off[v] + static_cast<int64_t>(S) * ((cap + 32) >> 5);
+        off[n + 1 + v + 1] = off[n + 1 + v] + 2 * (cap + 1);
+        if (summary) AVS_CHECK(summary_start[v + 1] - summary_start[v] >= n_frames[v], AVS_ERR_INVALID,
+                               "summary_start leaves fewer than n_frames bytes for video %d", v);
+    }
+    const int64_t keep_words = off[n];
+    const bool dp_global = 2ull * (static_cast<size_t>(max_cap) + 1) * 8 > 200 * 1024;
+    const int64_t dp_elems = dp_global ? off[2 * n + 1] : 0;
+    const int64_t sum_bytes = summary ? summary_start[n] : 0;
+
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // int32 descriptor block: row_start | lengths | n_frames | cps_start | cps
+    std::vector<int32_t> desc;
+    desc.insert(desc.end(), row_start, row_start + n);
+    desc.insert(desc.end(), lengths, lengths + n);
+    desc.insert(desc.end(), n_frames, n_frames + n);
+    desc.insert(desc.end(), cps_start, cps_start + n + 1);
+    if (desc.size() % 2) desc.push_back(0);  // keep cps 8-byte aligned for int2 loads
+    const size_t cps_off = desc.size();
+    desc.insert(desc.end(), cps, cps + 2 * static_cast<size_t>(total_S));
+    std::vector<int64_t> off64(off);
+    if (summary) off64.insert(off64.end(), summary_start, summary_start + n + 1);
+
+    size_t need = desc.size() * 4 + off64.size() * 8 + static_cast<size_t>(total_S) * (8 + 8 + 1) +
+                  static_cast<size_t>(keep_words) * 4 + static_cast<size_t>(dp_elems) * 8 + 64 * 256;
+    if (space == AVS_HOST) need += static_cast<size_t>(rows) * 8 + static_cast<size_t>(sum_bytes);
+    AVS_TRY(m->ws.reserve(need));
+    m->ws.reset();
+    int64_t* off_dev = m->ws.take<int64_t>(off64.size());
+    int32_t* desc_dev = m->ws.take<int32_t>(desc.size());
+    unsigned long long* seg_sum = m->ws.take<unsigned long long>(std::max(total_S, 1));
+    long long* seg_mean_dev = m->ws.take<long long>(std::max(total_S, 1));
+    uint32_t* keep = m->ws.take<uint32_t>(std::max<int64_t>(keep_words, 1));
+    long long* dp_ws = m->ws.take<long long>(std::max<int64_t>(dp_elems, 1));
+    const float* sc = scores;
+    const int32_t* pos = positions;
+    uint8_t* picks_dev = picks;
+    uint8_t* summary_dev = summary;
+    if (space == AVS_HOST) {
+        float* s2 = m->ws.take<float>(rows);
+        int32_t* p2 = m->ws.take<int32_t>(rows);
+        AVS_CUDA(cudaMemcpyAsync(s2, scores, rows * 4, cudaMemcpyHostToDevice, st));
+        AVS_CUDA(cudaMemcpyAsync(p2, positions, rows * 4, cudaMemcpyHostToDevice, st));
+        sc = s2;
+        pos = p2;
+        picks_dev = m->ws.take<uint8_t>(std::max(total_S, 1));
+        if (summary) summary_dev = m->ws.take<uint8_t>(sum_bytes);
+    }
+    AVS_CUDA(cudaMemcpyAsync(off_dev, off64.data(), off64.size() * 8, cudaMemcpyHostToDevice, st));
+    AVS_CUDA(cudaMemcpyAsync(desc_dev, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st));
+    AVS_CUDA(cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(std::max(total_S, 1)) * 8, st));
+
+    SummaryBatch sb;
+    sb.row_start = desc_dev;
+    sb.lengths = desc_dev + n;
+    sb.n_frames = desc_dev + 2 * n;
+    sb.cps_start = desc_dev + 3 * n;
+    sb.cps = desc_dev + cps_off;
+    sb.keep_start = off_dev;
+    sb.dp_start = off_dev + (n + 1);
+    sb.summary_start = summary ? off_dev + 2 * (n + 1) : nullptr;
+    sb.n = n;
+    sb.prop_num = prop_num;
+    sb.prop_den = prop_den;
+    sb.max_cap = max_cap;
+    AVS_TRY(shot_pool(sc, pos, sb, seg_sum, st));
+    long long* seg_mean_target = space == AVS_HOST ? (seg_mean ? seg_mean_dev : nullptr)
+                                                    : reinterpret_cast<long long*>(seg_mean);
+    AVS_TRY(knapsack_select(sb, seg_sum, seg_mean_target, picks_dev, summary_dev, keep, dp_ws, st));
+    if (space == AVS_HOST) {
+        AVS_CUDA(cudaMemcpyAsync(picks, picks_dev, total_S, cudaMemcpyDeviceToHost, st));
+        if (seg_mean) AVS_CUDA(cudaMemcpyAsync(seg_mean, seg_mean_dev, static_cast<size_t>(total_S) * 8,
+                                               cudaMemcpyDeviceToHost, st));
+        if (summary) AVS_CUDA(cudaMemcpyAsync(summary, summary_dev, sum_bytes, cudaMemcpyDeviceToHost, st));
+        AVS_CUDA(cudaStreamSynchronize(st));
+    }
+    return AVS_OK;
+}
+
+avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t M, int32_t N, int32_t K, int relu,
+                      int precision, float* C, void* cuda_stream) {
+    AVS_CHECK(A && W && C, AVS_ERR_INVALID, "avs_linear: null pointer");
+    AVS_CHECK(precision == AVS_PREC_TF32 || precision == AVS_PREC_FP32_SIMT, AVS_ERR_UNSUPPORTED,
+              "precision %d not available in this build", precision);
+    GemmEpilogue e;
+    e.bias = bias;
+    e.C = C;
+    e.ldc = N;
+    e.relu = relu;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (precision == AVS_PREC_FP32_SIMT) return gemm_simt(A, K, W, K, M, N, K, e, st);
+    return gemm_tc(A, K, W, K, DT_F32, M, N, K, e, st);
+}
+
+avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows, int32_t n_videos,
+                           const int32_t* row_start, const int32_t* lengths, int precision, float* fused,
+                           void* cuda_stream) {
+    AVS_CHECK(m && v_emb && a_emb && fused, AVS_ERR_INVALID, "avs_bilstm_pair: null pointer");
+    AVS_CHECK(precision == AVS_PREC_TF32 || precision == AVS_PREC_FP32_SIMT, AVS_ERR_UNSUPPORTED,
+              "precision %d not available in this build", precision);
+    int max_len = 0;
+    AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
+    if (total_rows == 0 || max_len == 0) return AVS_OK;
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int64_t R = total_rows;
+    LstmPlan plan = plan_lstm(n_videos, row_start, lengths);
+    AVS_TRY(m->ws.reserve(static_cast<size_t>(R) * (2 * 2 * G4 + 2 * H) * 4 + plan.host.size() * 4 + 16 * 256));
+    m->ws.reset();
+    float* xg_v = m->ws.take<float>(R * 2 * G4);
+    float* xg_a = m->ws.take<float>(R * 2 * G4);
+    int32_t* plan_dev = m->ws.take<int32_t>(plan.host.size());
+    const float* xv = v_emb;
+    const float* xa = a_emb;
+    if (precision == AVS_PREC_TF32) {
+        float* rv = m->ws.take<float>(R * H);
+        float* ra = m->ws.take<float>(R * H);
+        AVS_TRY(convert_f32(v_emb, rv, R * H, DT_F32, 1, st));
+        AVS_TRY(convert_f32(a_emb, ra, R * H, DT_F32, 1, st));
+        xv = rv;
+        xa = ra;
+    }
+    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
+    GemmEpilogue e2;
+    e2.ldc = 2 * G4;
+    e2.bias = m->ih_v_b;
+    e2.C = xg_v;
+    AVS_TRY(run_gemm(precision, xv, H, m->ih_v_x, m->ih_v_t, H, R, 2 * G4, H, e2, st));
+    e2.bias = m->ih_a_b;
+    e2.C = xg_a;
+    AVS_TRY(run_gemm(precision, xa, H, m->ih_a_x, m->ih_a_t, H, R, 2 * G4, H, e2, st));
+    const int slots = plan.n_groups * plan.nb;
+    LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
+    return lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, 0, nullptr, 0, st);
+}
+
+avs_status avs_attention(const float* qkv, int64_t rows, int32_t E_, int32_t num_heads, int32_t n_seqs,
+                         const int32_t* seq_base, const int32_t* seq_stride, const int32_t* seq_len, int precision,
+                         float* ctx, void* cuda_stream) {
+    AVS_CHECK(qkv && ctx && (n_seqs == 0 || (seq_base && seq_stride && seq_len)), AVS_ERR_INVALID,
+              "avs_attention: null pointer");
+    (void)precision;
+    if (n_seqs == 0) return AVS_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    std::vector<int32_t> sd(3 * static_cast<size_t>(n_seqs));
+    int mx = 0;
+    for (int s = 0; s < n_seqs; ++s) {
+        AVS_CHECK(seq_len[s] >= 0 && seq_base[s] >= 0 && seq_stride[s] >= 1 &&
+                      (seq_len[s] == 0 ||
+                       static_cast<int64_t>(seq_base[s]) + static_cast<int64_t>(seq_len[s] - 1) * seq_stride[s] < rows),
+                  AVS_ERR_INVALID, "avs_attention: sequence %d outside the %lld rows", s, static_cast<long long>(rows));
+        sd[s] = seq_base[s];
+        sd[n_seqs + s] = seq_stride[s];
+        sd[2 * n_seqs + s] = seq_len[s];
+        mx = std::max(mx, seq_len[s]);
+    }
+    int32_t* dev = nullptr;
+    AVS_CUDA(cudaMallocAsync(&dev, sd.size() * 4, st));
+    AVS_CUDA(cudaMemcpyAsync(dev, sd.data(), sd.size() * 4, cudaMemcpyHostToDevice, st));
+    SeqDesc seqs{dev, dev + n_seqs, dev + 2 * n_seqs, n_seqs, mx};
+    avs_status s = attention_simt(qkv, 3ll * E_, E_, num_heads, seqs, ctx, E_, 0, st);
+    cudaFreeAsync(dev, st);
+    return s;
+}
+
+avs_status avs_temporal_f1(const int32_t* pred, const int32_t* pred_start, const int32_t* gt, const int32_t* gt_start,
+                           int32_t n_videos, double* f1_host, void* cuda_stream) {
+    AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
+    if (n_videos == 0) return AVS_OK;
+    AVS_CHECK(pred_start && gt_start && f1_host, AVS_ERR_INVALID, "avs_temporal_f1: null pointer");
+    const int n = n_videos;
+    const int P = pred_start[n], G = gt_start[n];
+    AVS_CHECK(pred_start[0] == 0 && gt_start[0] == 0 && P >= 0 && G >= 0, AVS_ERR_INVALID, "bad offsets");
+    AVS_CHECK((P == 0 || pred) && (G == 0 || gt), AVS_ERR_INVALID, "avs_temporal_f1: null shot list");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // layout (8-byte aligned pieces): f1[n] | pred[2P] | gt[2G] | pred_start[n+1] | gt_start[n+1]
+    const size_t bytes = static_cast<size_t>(n) * 8 + (2ull * P + 2ull * G + 2ull * (n + 1)) * 4;
+    char* dev = nullptr;
+    AVS_CUDA(cudaMallocAsync(&dev, bytes, st));
+    double* f1_dev = reinterpret_cast<double*>(dev);
+    int32_t* pred_dev = reinterpret_cast<int32_t*>(dev + static_cast<size_t>(n) * 8);
+    int32_t* gt_dev = pred_dev + 2ull * P;
+    int32_t* ps_dev = gt_dev + 2ull * G;
+    int32_t* gs_dev = ps_dev + (n + 1);
+    if (P) AVS_CUDA(cudaMemcpyAsync(pred_dev, pred, 2ull * P * 4, cudaMemcpyHostToDevice, st));
+    if (G) AVS_CUDA(cudaMemcpyAsync(gt_dev, gt, 2ull * G * 4, cudaMemcpyHostToDevice, st));
+    AVS_CUDA(cudaMemcpyAsync(ps_dev, pred_start, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+    AVS_CUDA(cudaMemcpyAsync(gs_dev, gt_start, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+    avs_status s = temporal_f1_device(pred_dev, ps_dev, gt_dev, gs_dev, n, f1_dev, st);
+    if (s == AVS_OK) {
+        cudaError_t e = cudaMemcpyAsync(f1_host, f1_dev, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("avs_temporal_f1: %s", cudaGetErrorString(e));
+            s = AVS_ERR_CUDA;
+        }
+    }
+    cudaFreeAsync(dev, st);
+    return s;
+}
+
+}  // extern "C"

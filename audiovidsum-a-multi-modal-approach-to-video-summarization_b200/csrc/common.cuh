@@ -1,0 +1,124 @@
+// Internal declarations shared by the translation units of libavsum_b200.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include "../../include/avsum_b200.h"
+
+namespace avs {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local char g_err[512];
+void count_launch(int n = 1);
+
+#define AVS_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::avs::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return _e == cudaErrorMemoryAllocation ? AVS_ERR_OOM : AVS_ERR_CUDA;                    \
+        }                                                                                           \
+    } while (0)
+
+#define AVS_CHECK(cond, code, ...)            \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::avs::set_error(__VA_ARGS__);    \
+            return (code);                    \
+        }                                     \
+    } while (0)
+
+#define AVS_TRY(expr)                     \
+    do {                                  \
+        avs_status _s = (expr);           \
+        if (_s != AVS_OK) return _s;      \
+    } while (0)
+
+#define AVS_LAUNCH_CHECK()                \
+    do {                                  \
+        ::avs::count_launch();            \
+        AVS_CUDA(cudaGetLastError());     \
+    } while (0)
+
+// ---- element types of GEMM operands / outputs -------------------------------
+enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+static inline int dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---- GEMM: C[M,N] = act(A[M,K] * W[N,K]^T + bias) ---------------------------
+struct GemmEpilogue {
+    const float* bias = nullptr;  // [N] fp32 or null
+    void* C = nullptr;            // output, row-major, leading dimension ldc (elements)
+    int64_t ldc = 0;
+    int out_dtype = DT_F32;
+    int relu = 0;
+    int round_tf32 = 0;           // fp32 outputs rounded (RN) to tf32 for a following tf32 GEMM
+    // fused frame-score head (N must be 64): scores[m] = sigmoid(relu(acc + bias) . w2 + b2)
+    const float* score_w2 = nullptr;
+    const float* score_b2 = nullptr;   // device pointer to 1 float
+    float* scores = nullptr;
+};
+
+// tcgen05 / TMA path.  in_dtype: DT_F32 (kind::tf32), DT_F16 or DT_BF16 (kind::f16).
+avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, int64_t M, int N, int K,
+                   const GemmEpilogue& epi, cudaStream_t stream);
+// CUDA-core fp32 path (debug / exact-order aid).
+avs_status gemm_simt(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int N, int K,
+                     const GemmEpilogue& epi, cudaStream_t stream);
+
+// ---- elementwise helpers -----------------------------------------------------
+// dst = tf32_rn(src) (fp32 container) or bf16/f16 cast; n elements.
+avs_status convert_f32(const float* src, void* dst, int64_t n, int dst_dtype, int round_tf32, cudaStream_t stream);
+
+// ---- LSTM recurrence -----------------------------------------------------------
+struct LstmBatch {            // device arrays, one entry per slot (n_groups * NB slots)
+    const int32_t* slot_row_start;
+    const int32_t* slot_len;      // 0 for empty slots
+    const int32_t* group_maxlen;  // [n_groups]
+    int n_groups;
+    int nb;                       // videos per cluster (1, 2, 4, 8, 16)
+};
+// xg_v, xg_a: [rows, 2048] gate pre-activations (biases included) in the packed column order
+//   col = dir * 1024 + cta * 128 + gate * 32 + jj   (hidden unit j = cta * 32 + jj)
+// whh: [4][1024][256] fp32 in the same packed row order;  fused: [rows, 1024].
+avs_status lstm_recurrence(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
+                           float* fused, int round_tf32, void* fused_lowp, int lowp_dtype, cudaStream_t stream);
+
+// ---- attention core -------------------------------------------------------------
+struct SeqDesc {  // device arrays [n_seqs]
+    const int32_t* base;
+    const int32_t* stride;
+    const int32_t* len;
+    int n_seqs;
+    int max_len;
+};
+// CUDA-core reference implementation (fp32), any sequence layout.
+avs_status attention_simt(const float* qkv, int64_t ld_qkv, int E, int H, const SeqDesc& seqs, float* ctx,
+                          int64_t ld_ctx, int round_tf32, cudaStream_t stream);
+
+// ---- summary generation -----------------------------------------------------------
+struct SummaryBatch {   // device arrays, [n] unless noted
+    const int32_t* row_start;
+    const int32_t* lengths;
+    const int32_t* n_frames;
+    const int32_t* cps;          // [sum S, 2]
+    const int32_t* cps_start;    // [n + 1]
+    const int64_t* summary_start;// [n + 1] or null
+    const int64_t* keep_start;   // [n + 1] word offsets into keep bits workspace
+    const int64_t* dp_start;     // [n + 1] element offsets into global dp workspace (2 rows per video)
+    int n;
+    int prop_num, prop_den;
+    int max_cap;                 // max capacity over the batch
+};
+avs_status shot_pool(const float* scores, const int32_t* positions, const SummaryBatch& b, unsigned long long* seg_sum,
+                     cudaStream_t stream);
+avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_sum, long long* seg_mean,
+                           uint8_t* picks, uint8_t* summary, uint32_t* keep_bits, long long* dp_ws,
+                           cudaStream_t stream);
+avs_status temporal_f1_device(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
+                              const int32_t* gt_start, int n, double* f1_dev, cudaStream_t stream);
+
+}  // namespace avs

@@ -1,0 +1,280 @@
+// K1/K2a/K3/K5/K6 -- the dense contractions of AVBiLSTMModel.forward
+// (nn.Linear call sites /root/reference/models/av_model.py:10-15, 26, 29-31 and the
+// LSTM input projections of av_model.py:18-23) as ONE tcgen05 + TMA + TMEM GEMM:
+//
+//     C[M, N] = epilogue(A[M, K] * W[N, K]^T)          (both operands K-major)
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32 or kind::f16)
+//   warps 2..5  : epilogue -- tcgen05.ld the fp32 accumulator, fuse bias / ReLU / tf32 rounding /
+//                 fp16-bf16 cast, or the whole frame-score head (64-wide ReLU, dot with
+//                 scorer.2.weight, sigmoid) and store.
+//
+// Tile 128 x BN x 128 B of K per stage (32 tf32 or 64 half elements), 4 MMAs (K = 32 B) per stage.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace avs {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * 128;
+    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 8;
+    static constexpr int TOTAL = 1024 /*alignment slack*/ + TILE_BYTES + BAR_BYTES;
+};
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int BN, int STAGES, bool TF32>
+__global__ void __launch_bounds__(GEMM_THREADS, (SmemLayout<BN, STAGES>::TOTAL <= 110 * 1024) ? 2 : 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+               int k_blocks, int bk_elems, uint32_t idesc, GemmEpilogue epi) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + L::TILE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                mbar_expect_tx(full + s, L::STAGE_BYTES);
+                uint8_t* a_dst = tiles + s * L::STAGE_BYTES;
+                tma_load_2d(a_dst, &tmA, full + s, kb * bk_elems, m0);
+                tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, full + s, kb * bk_elems, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(full + s, ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // 4 x (K = 32 bytes) per 128-byte swizzled row
+                    const uint64_t ad = umma_desc_sw128_kmajor(a_addr + k * 32);
+                    const uint64_t bd = umma_desc_sw128_kmajor(b_addr + k * 32);
+                    if (TF32)
+                        umma_tf32_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                    else
+                        umma_f16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                }
+                tc_commit(empty + s);  // smem slot reusable once these MMAs retire
+            }
+            tc_commit(tmem_full);  // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < M;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float score_acc = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c, r);
+            tmem_ld_wait();
+            const int nb = n0 + c;
+            if (nb >= N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(r[j]);
+                if (epi.bias != nullptr && nb + j < N) x += __ldg(epi.bias + nb + j);
+                if (epi.relu) x = fmaxf(x, 0.f);
+                v[j] = x;
+            }
+            if (epi.scores != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (nb + j < N) score_acc = fmaf(v[j], __ldg(epi.score_w2 + nb + j), score_acc);
+                continue;
+            }
+            if (!row_ok) continue;
+            if (epi.out_dtype == DT_F32) {
+                float* dst = reinterpret_cast<float*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (nb + j < N) {
+                        float4 o;
+                        if (epi.round_tf32) {
+                            o = make_float4(to_tf32_rn(v[j]), to_tf32_rn(v[j + 1]), to_tf32_rn(v[j + 2]),
+                                            to_tf32_rn(v[j + 3]));
+                        } else {
+                            o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                }
+            } else {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (nb + j < N) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            if (epi.out_dtype == DT_F16) {
+                                __half2 h = __floats2half2_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                                pk[t] = *reinterpret_cast<uint32_t*>(&h);
+                            } else {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                                pk[t] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+        }
+        if (epi.scores != nullptr && row_ok) {
+            epi.scores[row] = sigmoidf_acc(score_acc + __ldg(epi.score_b2));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D K-major operand [rows, K] with leading dimension ld (elements): box = 128 bytes of K x box_rows.
+avs_status make_tmap(CUtensorMap* tm, const void* ptr, int dtype, int64_t rows, int K, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    AVS_CHECK(fn != nullptr, AVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const int esz = dtype_size(dtype);
+    AVS_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, AVS_ERR_INVALID, "GEMM operand not 16-byte aligned");
+    AVS_CHECK((ld * esz) % 16 == 0, AVS_ERR_INVALID, "GEMM operand row pitch %lld B not a multiple of 16",
+              static_cast<long long>(ld * esz));
+    CUtensorMapDataType dt = dtype == DT_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                             : dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                               : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld * esz)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AVS_CHECK(r == CUDA_SUCCESS, AVS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return AVS_OK;
+}
+
+}  // namespace
+
+avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, int64_t M, int N, int K,
+                   const GemmEpilogue& epi, cudaStream_t stream) {
+    if (M == 0) return AVS_OK;
+    AVS_CHECK(M > 0 && N > 0 && K > 0, AVS_ERR_INVALID, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+    AVS_CHECK(M < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: M too large");
+    AVS_CHECK(N % 16 == 0, AVS_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 16", N);
+    if (epi.scores != nullptr)
+        AVS_CHECK(N == 64 && epi.score_w2 && epi.score_b2, AVS_ERR_INVALID, "score epilogue needs N == 64");
+    else
+        AVS_CHECK(epi.C != nullptr && epi.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0,
+                  AVS_ERR_INVALID, "gemm: output must be 16-byte aligned with ldc %% 4 == 0");
+    const int esz = dtype_size(in_dtype);
+    const int bk_elems = 128 / esz;
+    const int k_blocks = (K + bk_elems - 1) / bk_elems;
+    const bool tf32 = in_dtype == DT_F32;
+    const uint32_t fmt = tf32 ? UMMA_FMT_TF32 : (in_dtype == DT_F16 ? UMMA_FMT_F16 : UMMA_FMT_BF16);
+    const int BN = (N % 128 == 0) ? 128 : 64;
+
+    CUtensorMap tmA, tmB;
+    AVS_TRY(make_tmap(&tmA, A, in_dtype, M, K, lda, BM));
+    AVS_TRY(make_tmap(&tmB, W, in_dtype, N, K, ldw, BN));
+    dim3 grid((N + BN - 1) / BN, static_cast<unsigned>((M + BM - 1) / BM));
+    const uint32_t idesc = umma_idesc(fmt, BM, BN);
+
+#define AVS_GEMM_LAUNCH(BN_, ST_, TF_)                                                                       \
+    do {                                                                                                     \
+        using L = SmemLayout<BN_, ST_>;                                                                      \
+        auto kern = gemm_tc_kernel<BN_, ST_, TF_>;                                                           \
+        static bool configured = false;                                                                      \
+        if (!configured) {                                                                                   \
+            AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));     \
+            configured = true;                                                                               \
+        }                                                                                                    \
+        kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, static_cast<int>(M), N, k_blocks, bk_elems, \
+                                                       idesc, epi);                                          \
+    } while (0)
+
+    if (BN == 128) {
+        if (tf32) AVS_GEMM_LAUNCH(128, 3, true);
+        else AVS_GEMM_LAUNCH(128, 3, false);
+    } else {
+        if (tf32) AVS_GEMM_LAUNCH(64, 4, true);
+        else AVS_GEMM_LAUNCH(64, 4, false);
+    }
+#undef AVS_GEMM_LAUNCH
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
+
+}  // namespace avs

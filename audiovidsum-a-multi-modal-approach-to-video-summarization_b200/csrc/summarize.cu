@@ -1,0 +1,223 @@
+// K7 / K8 -- summary generation: shot pooling over change points, 0/1 knapsack at the length
+// budget, keyshot bitmap; plus the batched overlap-F1 of
+// /root/reference/evaluation/metrics.py:1-9 (== utils/shot_metrics.py:4-16).
+//
+// The reference has NO pooling / knapsack code; the algorithm is specified
+// by oracle/av_oracle.py (shot_pool, knapsack, generate_summary) in integer arithmetic and these
+// kernels are bit-exact against it:
+//   q_i        = clamp(rint(score_i * 2^24), 0, 2^24)                (the only fp step)
+//   seg_sum_s  = sum_i q_i * |[pos_i, pos_{i+1}) ^ [a_s, b_s]|        (int64, order independent)
+//   seg_mean_s = floor((2 seg_sum_s + nf_s) / (2 nf_s)),  nf_s = b_s - a_s + 1
+//   dp_s[w]    = max(dp_{s-1}[w], dp_{s-1}[w - nf_s] + seg_mean_s), item kept only on strict gain
+//   back-trace from (S-1, capacity), capacity = floor(n_frames * num / den).
+#include "common.cuh"
+
+namespace avs {
+
+namespace {
+
+constexpr int SCORE_FRAC_BITS = 24;
+
+__device__ __forceinline__ long long quantize_score(float s) {
+    if (!(s == s)) return 0;  // NaN
+    const float x = s * 16777216.0f;  // exact power-of-two scaling
+    if (x <= 0.f) return 0;
+    if (x >= 16777216.0f) return 1ll << SCORE_FRAC_BITS;
+    return __float2ll_rn(x);  // round half to even == numpy.rint
+}
+
+// ---------------------------------------------------------------------------- K7
+// One block per video; thread i owns sampled frame i (stride loop).  HBM-bound:
+// 8 B read per sampled frame + 8 B per shot, 8 B written per shot.
+__global__ void __launch_bounds__(256) shot_pool_kernel(const float* __restrict__ scores,
+                                                        const int32_t* __restrict__ positions, SummaryBatch b,
+                                                        unsigned long long* __restrict__ seg_sum) {
+    const int v = blockIdx.x;
+    const int row0 = b.row_start[v];
+    const int T = b.lengths[v];
+    const int nf = b.n_frames[v];
+    const int s0 = b.cps_start[v], S = b.cps_start[v + 1] - s0;
+    const int2* cps = reinterpret_cast<const int2*>(b.cps) + s0;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const long long q = quantize_score(scores[row0 + i]);
+        const int lo = positions[row0 + i];
+        const int hi = (i + 1 < T) ? positions[row0 + i + 1] : nf;
+        if (hi <= lo || q == 0) continue;
+        // first shot whose (inclusive) end >= lo; shots are sorted and disjoint (validated on host)
+        int a = 0, z = S;
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (cps[mid].y < lo) a = mid + 1; else z = mid;
+        }
+        for (int s = a; s < S; ++s) {
+            const int2 seg = cps[s];
+            if (seg.x >= hi) break;
+            const int ov = min(hi, seg.y + 1) - max(lo, seg.x);
+            if (ov > 0) atomicAdd(seg_sum + s0 + s, static_cast<unsigned long long>(q * ov));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- K8
+// One block per video.  DP rows live in shared memory when 2*(cap+1) int64 fit, else in a
+// global (L2-resident) workspace; the per-item "kept" bits go to global memory, one ballot word
+// per warp, and a single thread walks them backwards.
+constexpr int KNAP_THREADS = 512;
+
+__global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
+                                                                const unsigned long long* __restrict__ seg_sum,
+                                                                long long* __restrict__ seg_mean_out,
+                                                                uint8_t* __restrict__ picks,
+                                                                uint8_t* __restrict__ summary,
+                                                                uint32_t* __restrict__ keep_bits,
+                                                                long long* __restrict__ dp_ws, int smem_rows_cap) {
+    extern __shared__ long long dp_smem[];
+    const int v = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nf = b.n_frames[v];
+    const int s0 = b.cps_start[v], S = b.cps_start[v + 1] - s0;
+    const int2* cps = reinterpret_cast<const int2*>(b.cps) + s0;
+    const long long cap_ll = (static_cast<long long>(nf) * b.prop_num) / b.prop_den;
+    const int cap = static_cast<int>(cap_ll < 0 ? 0 : cap_ll);
+    const int words = (cap + 32) >> 5;  // ceil((cap + 1) / 32)
+    uint32_t* keep = keep_bits + b.keep_start[v];
+
+    long long* cur;
+    long long* nxt;
+    if (cap + 1 <= smem_rows_cap) {
+        cur = dp_smem;
+        nxt = dp_smem + smem_rows_cap;
+    } else {
+        cur = dp_ws + b.dp_start[v];
+        nxt = cur + (cap + 1);
+    }
+    for (int w = tid; w <= cap; w += KNAP_THREADS) cur[w] = 0;
+    __syncthreads();
+
+    for (int s = 0; s < S; ++s) {
+        const int2 seg = cps[s];
+        const int wt = seg.y - seg.x + 1;
+        const unsigned long long sum = seg_sum[s0 + s];
+        const long long val = wt > 0 ? static_cast<long long>((2ull * sum + wt) / (2ull * wt)) : 0ll;
+        if (tid == 0 && seg_mean_out != nullptr) seg_mean_out[s0 + s] = val;
+        for (int wbase = 0; wbase <= cap; wbase += KNAP_THREADS) {  // warp-uniform trip count
+            const int w = wbase + tid;
+            bool better = false;
+            if (w <= cap) {
+                const long long old = cur[w];
+                long long cand = old;
+                if (wt > 0 && w >= wt) {
+                    cand = cur[w - wt] + val;
+                    better = cand > old;
+                } else if (wt == 0 && val > 0) {
+                    cand = old + val;
+                    better = true;
+                }
+                nxt[w] = better ? cand : old;
+            }
+            const uint32_t bits = __ballot_sync(0xffffffffu, better);
+            if ((tid & 31) == 0 && (w >> 5) < words) keep[static_cast<size_t>(s) * words + (w >> 5)] = bits;
+        }
+        __syncthreads();
+        long long* t = cur; cur = nxt; nxt = t;
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) {
+        int w = cap;
+        for (int s = S - 1; s >= 0; --s) {
+            const uint32_t word = keep[static_cast<size_t>(s) * words + (w >> 5)];
+            const int take = (word >> (w & 31)) & 1;
+            picks[s0 + s] = static_cast<uint8_t>(take);
+            if (take) w -= (cps[s].y - cps[s].x + 1);
+        }
+    }
+    if (summary != nullptr) {
+        __syncthreads();
+        uint8_t* out = summary + b.summary_start[v];
+        for (int f = tid; f < nf; f += KNAP_THREADS) out[f] = 0;
+        __syncthreads();
+        for (int s = 0; s < S; ++s) {
+            if (!picks[s0 + s]) continue;
+            const int a = max(cps[s].x, 0), z = min(cps[s].y + 1, nf);
+            for (int f = a + tid; f < z; f += KNAP_THREADS) out[f] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- overlap F1
+__global__ void __launch_bounds__(256) temporal_f1_kernel(const int2* __restrict__ pred,
+                                                          const int32_t* __restrict__ pred_start,
+                                                          const int2* __restrict__ gt,
+                                                          const int32_t* __restrict__ gt_start,
+                                                          double* __restrict__ f1) {
+    const int v = blockIdx.x;
+    const int p0 = pred_start[v], P = pred_start[v + 1] - p0;
+    const int g0 = gt_start[v], G = gt_start[v + 1] - g0;
+    long long ov = 0, plen = 0, glen = 0;
+    for (long long idx = threadIdx.x; idx < static_cast<long long>(P) * G; idx += blockDim.x) {
+        const int2 p = pred[p0 + idx / G], g = gt[g0 + idx % G];
+        const int o = min(p.y, g.y) - max(p.x, g.x);
+        if (o > 0) ov += o;
+    }
+    for (int i = threadIdx.x; i < P; i += blockDim.x) plen += pred[p0 + i].y - pred[p0 + i].x;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) glen += gt[g0 + i].y - gt[g0 + i].x;
+    __shared__ long long red[3][256];
+    red[0][threadIdx.x] = ov; red[1][threadIdx.x] = plen; red[2][threadIdx.x] = glen;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st)
+            for (int k = 0; k < 3; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // evaluation/metrics.py:7-9 in IEEE double, no contraction
+        const double precision = __ddiv_rn(static_cast<double>(red[0][0]), static_cast<double>(red[1][0]));
+        const double recall = __ddiv_rn(static_cast<double>(red[0][0]), static_cast<double>(red[2][0]));
+        const double num = __dmul_rn(2.0, __dmul_rn(precision, recall));
+        const double den = __dadd_rn(__dadd_rn(precision, recall), 1e-8);
+        f1[v] = __ddiv_rn(num, den);
+    }
+}
+
+}  // namespace
+
+avs_status shot_pool(const float* scores, const int32_t* positions, const SummaryBatch& b, unsigned long long* seg_sum,
+                     cudaStream_t stream) {
+    if (b.n == 0) return AVS_OK;
+    shot_pool_kernel<<<b.n, 256, 0, stream>>>(scores, positions, b, seg_sum);
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
+
+avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_sum, long long* seg_mean,
+                           uint8_t* picks, uint8_t* summary, uint32_t* keep_bits, long long* dp_ws,
+                           cudaStream_t stream) {
+    if (b.n == 0) return AVS_OK;
+    // two dp rows in shared memory when they fit (<= 96 KiB keeps 2 blocks per SM)
+    int rows_cap = b.max_cap + 1;
+    size_t smem = 2ull * rows_cap * sizeof(long long);
+    const size_t limit = 200 * 1024;
+    if (smem > limit) { rows_cap = 0; smem = 0; }
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        AVS_CUDA(cudaFuncSetAttribute(knapsack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(limit)));
+        configured = limit;
+    }
+    knapsack_kernel<<<b.n, KNAP_THREADS, smem, stream>>>(b, seg_sum, seg_mean, picks, summary, keep_bits, dp_ws,
+                                                        rows_cap);
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
+
+avs_status temporal_f1_device(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
+                              const int32_t* gt_start, int n, double* f1_dev, cudaStream_t stream) {
+    if (n == 0) return AVS_OK;
+    temporal_f1_kernel<<<n, 256, 0, stream>>>(reinterpret_cast<const int2*>(pred), pred_start,
+                                              reinterpret_cast<const int2*>(gt), gt_start, f1_dev);
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
+
+}  // namespace avs

@@ -1,0 +1,212 @@
+"""Host-side plumbing between torch tensors and the C ABI.
+
+PyTorch is used for what it is good at here -- device memory, streams, pinned host
+buffers -- while every FLOP of the hot path runs inside ``libavsum_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from fractions import Fraction
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_LSTM_ORDER = [("visual_bilstm", ""), ("visual_bilstm", "_reverse"), ("audio_bilstm", ""), ("audio_bilstm", "_reverse")]
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("avsum_b200 needs a CUDA (sm_100) device: there is no CPU fallback")
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+class NativeModel:
+    """Owns one ``avs_model`` handle built from a reference-format state_dict."""
+
+    def __init__(self, state_dict, visual_dim: int, audio_dim: int, hidden_dim: int = 512, num_heads: int = 4,
+                 device: Optional[int] = None):
+        _require_cuda()
+        self.lib = _cabi.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dims = (visual_dim, audio_dim, hidden_dim, num_heads)
+        self._handle = C.c_void_p()
+        w, keep = self._weights_struct(state_dict)
+        _cabi.check(self.lib.avs_model_create(C.byref(w), self.device, C.byref(self._handle)))
+        del keep
+
+    # -- weights --------------------------------------------------------------
+    def _weights_struct(self, sd):
+        vd, ad, hd, nh = self.dims
+        keep = []
+
+        def ptr(name, shape):
+            t = sd[name].detach()
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+            t = t.to(dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        hc, e = hd // 2, hd * 2
+        w = _cabi.AvsWeights()
+        w.visual_dim, w.audio_dim, w.hidden_dim, w.num_heads = vd, ad, hd, nh
+        w.visual_fc_w, w.visual_fc_b = ptr("visual_fc.0.weight", (hd, vd)), ptr("visual_fc.0.bias", (hd,))
+        w.audio_fc_w, w.audio_fc_b = ptr("audio_fc.0.weight", (hd, ad)), ptr("audio_fc.0.bias", (hd,))
+        for i, (mod, suf) in enumerate(_LSTM_ORDER):
+            w.lstm_w_ih[i] = ptr(f"{mod}.weight_ih_l0{suf}", (4 * hc, hd))
+            w.lstm_w_hh[i] = ptr(f"{mod}.weight_hh_l0{suf}", (4 * hc, hc))
+            w.lstm_b_ih[i] = ptr(f"{mod}.bias_ih_l0{suf}", (4 * hc,))
+            w.lstm_b_hh[i] = ptr(f"{mod}.bias_hh_l0{suf}", (4 * hc,))
+        w.attn_in_w, w.attn_in_b = ptr("attention.in_proj_weight", (3 * e, e)), ptr("attention.in_proj_bias", (3 * e,))
+        w.attn_out_w, w.attn_out_b = ptr("attention.out_proj.weight", (e, e)), ptr("attention.out_proj.bias", (e,))
+        w.scorer0_w, w.scorer0_b = ptr("scorer.0.weight", (64, e)), ptr("scorer.0.bias", (64,))
+        w.scorer2_w, w.scorer2_b = ptr("scorer.2.weight", (1, 64)), ptr("scorer.2.bias", (1,))
+        return w, keep
+
+    def update(self, state_dict):
+        w, keep = self._weights_struct(state_dict)
+        _cabi.check(self.lib.avs_model_update(self._handle, C.byref(w)))
+        torch.cuda.synchronize(self.device)
+        del keep
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self.lib.avs_model_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- forward ----------------------------------------------------------------
+    def forward_rows(self, visual: torch.Tensor, audio: torch.Tensor, row_start, lengths, attn_axis: str = "literal",
+                     precision: str = "tf32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """visual [R, Dv], audio [R, Da] (both on the model's GPU, or both on the host) -> scores [R]."""
+        vd, ad, _, _ = self.dims
+        if visual.dim() != 2 or audio.dim() != 2 or visual.shape[1] != vd or audio.shape[1] != ad:
+            raise ValueError(f"expected visual [R, {vd}] and audio [R, {ad}], got {tuple(visual.shape)} / {tuple(audio.shape)}")
+        if visual.shape[0] != audio.shape[0]:
+            raise ValueError("visual and audio must have the same number of frames")
+        if visual.device != audio.device:
+            raise ValueError("visual and audio must live on the same device")
+        R = int(visual.shape[0])
+        visual = visual.to(torch.float32).contiguous()
+        audio = audio.to(torch.float32).contiguous()
+        rs, ln = _i32(row_start), _i32(lengths)
+        if rs.shape != ln.shape or rs.ndim != 1:
+            raise ValueError("row_start and lengths must be 1-D arrays of equal size")
+        on_gpu = visual.is_cuda
+        if on_gpu and visual.device.index != self.device:
+            raise ValueError(f"inputs are on cuda:{visual.device.index}, the model on cuda:{self.device}")
+        if out is None:
+            out = torch.empty(R, dtype=torch.float32, device=visual.device, pin_memory=(not on_gpu))
+        space = _cabi.AVS_DEVICE if on_gpu else _cabi.AVS_HOST
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.avs_forward(
+                self._handle, C.c_void_p(visual.data_ptr()), C.c_void_p(audio.data_ptr()), R, int(rs.size),
+                _cabi.np_ptr(rs), _cabi.np_ptr(ln), _cabi.ATTN_AXES[attn_axis], _cabi.PRECISIONS[precision],
+                C.c_void_p(out.data_ptr()), space, _stream_ptr(self.device)))
+        return out
+
+    # -- summary ------------------------------------------------------------------
+    def summarize_rows(self, scores: torch.Tensor, positions: torch.Tensor, row_start, lengths, n_frames, cps_list,
+                       proportion=0.15, want_summary: bool = True):
+        """Batched shot pooling + knapsack.  Returns (picks uint8[sum S], seg_mean int64[sum S],
+        summary uint8[sum n_frames] | None, cps_start, summary_start) as torch tensors in the
+        memory space of ``scores``."""
+        frac = Fraction(proportion).limit_denominator(10000) if not isinstance(proportion, tuple) else Fraction(*proportion)
+        rs, ln, nf = _i32(row_start), _i32(lengths), _i32(n_frames)
+        n = int(rs.size)
+        cps_start = np.zeros(n + 1, dtype=np.int32)
+        for i, c in enumerate(cps_list):
+            cps_start[i + 1] = cps_start[i] + int(np.asarray(c).reshape(-1, 2).shape[0])
+        cps = _i32(np.concatenate([np.asarray(c, dtype=np.int32).reshape(-1, 2) for c in cps_list], axis=0)
+                   if n else np.zeros((0, 2), np.int32))
+        total_S = int(cps_start[-1])
+        summary_start = np.zeros(n + 1, dtype=np.int64)
+        summary_start[1:] = np.cumsum(nf.astype(np.int64))
+        on_gpu = scores.is_cuda
+        dev = scores.device
+        scores = scores.to(torch.float32).contiguous()
+        positions = positions.to(device=dev, dtype=torch.int32).contiguous()
+        pin = not on_gpu
+        picks = torch.empty(total_S, dtype=torch.uint8, device=dev, pin_memory=pin)
+        seg_mean = torch.empty(total_S, dtype=torch.int64, device=dev, pin_memory=pin)
+        summary = torch.empty(int(summary_start[-1]), dtype=torch.uint8, device=dev, pin_memory=pin) if want_summary else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.avs_summarize(
+                self._handle, C.c_void_p(scores.data_ptr()), C.c_void_p(positions.data_ptr()), n, _cabi.np_ptr(rs),
+                _cabi.np_ptr(ln), _cabi.np_ptr(nf), _cabi.np_ptr(cps), _cabi.np_ptr(cps_start),
+                int(frac.numerator), int(frac.denominator), C.c_void_p(picks.data_ptr()),
+                C.c_void_p(seg_mean.data_ptr()), C.c_void_p(summary.data_ptr()) if want_summary else None,
+                _cabi.np_ptr(summary_start) if want_summary else None,
+                _cabi.AVS_DEVICE if on_gpu else _cabi.AVS_HOST, _stream_ptr(self.device)))
+        return picks, seg_mean, summary, cps_start, summary_start
+
+
+# ---- stateless building blocks (device tensors) ------------------------------------
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
+           precision: str = "tf32") -> torch.Tensor:
+    """nn.Linear(+ReLU) on a CUDA tensor [..., K] through avs_linear."""
+    _require_cuda()
+    if not x.is_cuda:
+        raise RuntimeError("avsum_b200.linear needs CUDA tensors (no CPU fallback)")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K).to(torch.float32).contiguous()
+    w = weight.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    b = None if bias is None else bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    out = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().avs_linear(
+            C.c_void_p(x2.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()) if b is not None else None,
+            int(x2.shape[0]), int(N), int(K), int(relu), _cabi.PRECISIONS[precision], C.c_void_p(out.data_ptr()),
+            _stream_ptr(x.device)))
+    return out.reshape(*x.shape[:-1], N)
+
+
+def attention(qkv: torch.Tensor, embed_dim: int, num_heads: int, seq_base, seq_stride, seq_len,
+              precision: str = "tf32") -> torch.Tensor:
+    """Multi-head softmax attention over row sequences of a packed [rows, 3E] q|k|v tensor."""
+    _require_cuda()
+    rows = int(qkv.shape[0])
+    qkv = qkv.to(torch.float32).contiguous()
+    ctx = torch.zeros(rows, embed_dim, dtype=torch.float32, device=qkv.device)
+    sb, ss, sl = _i32(seq_base), _i32(seq_stride), _i32(seq_len)
+    with torch.cuda.device(qkv.device):
+        _cabi.check(_cabi.lib().avs_attention(
+            C.c_void_p(qkv.data_ptr()), rows, int(embed_dim), int(num_heads), int(sb.size), _cabi.np_ptr(sb),
+            _cabi.np_ptr(ss), _cabi.np_ptr(sl), _cabi.PRECISIONS[precision], C.c_void_p(ctx.data_ptr()),
+            _stream_ptr(qkv.device)))
+    return ctx
+
+
+def temporal_f1_batch(pred_lists: Sequence[Sequence[Tuple[int, int]]], gt_lists: Sequence[Sequence[Tuple[int, int]]]) -> np.ndarray:
+    """Batched overlap-F1 (evaluation/metrics.py:1-9) on the GPU; returns float64[n]."""
+    _require_cuda()
+    n = len(pred_lists)
+    ps = np.zeros(n + 1, np.int32)
+    gs = np.zeros(n + 1, np.int32)
+    for i in range(n):
+        ps[i + 1] = ps[i] + len(pred_lists[i])
+        gs[i + 1] = gs[i] + len(gt_lists[i])
+    flat = lambda lists: _i32(np.asarray([p for l in lists for p in l], dtype=np.int32).reshape(-1, 2))
+    pred, gt = flat(pred_lists), flat(gt_lists)
+    out = np.empty(n, dtype=np.float64)
+    dev = torch.cuda.current_device()
+    _cabi.check(_cabi.lib().avs_temporal_f1(_cabi.np_ptr(pred), _cabi.np_ptr(ps), _cabi.np_ptr(gt), _cabi.np_ptr(gs),
+                                            n, _cabi.np_ptr(out), _stream_ptr(dev)))
+    return out

@@ -1,0 +1,152 @@
+/*
+ * avsum_b200 -- C ABI of the B200-native AudioVidSum hot path (libavsum_b200.so).
+ *
+ * The reference (Research-Implementation/AudioVidSum) is pure Python over torch.nn and
+ * defines NO plugin / operator / FFI interface; its boundary is the
+ * Python surface of models/av_model.py.  These entry points are what a binding for that
+ * surface calls; each one cites the reference code it replaces.  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an avs_status (0 = OK) and never throws;
+ *     avs_last_error() returns a thread-local message for the last failure;
+ *   - all tensors are dense row-major; "rows" are frames, videos are described by
+ *     (row_start[b], length[b]) so both packed (sum T rows) and padded [B, Tmax] batches work;
+ *   - `space` says where the caller's data buffers live: AVS_DEVICE pointers are used in
+ *     place on `stream`; AVS_HOST buffers (pinned recommended) are copied H2D / D2H inside the
+ *     call and the call returns after the results have landed (stream synchronised);
+ *   - small int32 descriptor arrays (row_start, lengths, cps offsets ...) are ALWAYS host memory;
+ *   - the model handle owns packed device weights and a grow-only device workspace; calls on
+ *     one handle must not overlap (one handle per stream / thread).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     AVS_ERR_CUDA.
+ */
+#ifndef AVSUM_B200_H
+#define AVSUM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int avs_status;
+enum {
+    AVS_OK = 0,
+    AVS_ERR_INVALID = 1,     /* bad argument (message says which)                     */
+    AVS_ERR_UNSUPPORTED = 2, /* shape outside what the sm_100a kernels are built for   */
+    AVS_ERR_CUDA = 3,        /* CUDA runtime / driver error, or no sm_100 device       */
+    AVS_ERR_OOM = 4
+};
+
+enum { AVS_HOST = 0, AVS_DEVICE = 1 };
+
+/* Which axis nn.MultiheadAttention attends over.
+ * AVS_ATTN_LITERAL  : exactly models/av_model.py:44 -- the module is built without batch_first
+ *                     (av_model.py:26) yet fed [B, T, E], so frame t attends over the B videos
+ *                     of the batch (weights == 1 when B == 1).  Requires equal lengths.
+ * AVS_ATTN_TEMPORAL : frame self-attention inside each video with variable-length masking
+ *                     (the arithmetic of models/attention.py:15-25 on in_proj/out_proj weights).
+ * AVS_ATTN_LITERAL_B1: every video is its own B = 1 call of the reference, i.e. the loop of
+ *                     scripts/evaluate.py:12-18 batched into one launch chain (lengths may differ). */
+enum { AVS_ATTN_LITERAL = 0, AVS_ATTN_TEMPORAL = 1, AVS_ATTN_LITERAL_B1 = 2 };
+
+/* Arithmetic of the dense contractions.
+ * AVS_PREC_TF32 : fp32 storage, tcgen05 kind::tf32 with round-to-nearest operands, fp32 accumulate
+ *                 (attention core: fp16 operands = the same 11-bit significand); LSTM recurrence,
+ *                 softmax and all pointwise math in fp32.  Target: <= 1e-3 relative on scores.
+ * AVS_PREC_BF16 : bf16 operands/activations, fp32 accumulate (stated looser tolerance).
+ * AVS_PREC_FP32_SIMT : CUDA-core fp32 contractions (slow; exact-order debugging aid). */
+enum { AVS_PREC_TF32 = 0, AVS_PREC_BF16 = 1, AVS_PREC_FP32_SIMT = 2 };
+
+/* fp32 parameters in the reference's state_dict layout (av_model.py:10-31).
+ * lstm_*[i]: i = 0 visual fwd, 1 visual reverse, 2 audio fwd, 3 audio reverse.
+ * Pointers may be host or device memory (copied with cudaMemcpyDefault). */
+typedef struct avs_weights {
+    int32_t visual_dim, audio_dim, hidden_dim, num_heads;
+    const float *visual_fc_w, *visual_fc_b; /* [H, Dv], [H]                       av_model.py:10-12 */
+    const float *audio_fc_w, *audio_fc_b;   /* [H, Da], [H]                       av_model.py:13-15 */
+    const float* lstm_w_ih[4];              /* [4*H/2, H]   gate order i,f,g,o    av_model.py:18-23 */
+    const float* lstm_w_hh[4];              /* [4*H/2, H/2]                                         */
+    const float* lstm_b_ih[4];              /* [4*H/2]                                              */
+    const float* lstm_b_hh[4];              /* [4*H/2]                                              */
+    const float *attn_in_w, *attn_in_b;     /* [3E, E], [3E]  E = 2H              av_model.py:26    */
+    const float *attn_out_w, *attn_out_b;   /* [E, E], [E]                                          */
+    const float *scorer0_w, *scorer0_b;     /* [64, E], [64]                      av_model.py:29-31 */
+    const float *scorer2_w, *scorer2_b;     /* [1, 64], [1]                                         */
+} avs_weights;
+
+typedef struct avs_model avs_model;
+
+const char* avs_last_error(void);
+int avs_version(void);
+/* 1 if a usable sm_100 device is visible, else 0 (never fails). */
+int avs_device_ok(void);
+
+/* Replaces AVBiLSTMModel.__init__ + .cuda() (av_model.py:7-31; scripts/evaluate.py:13):
+ * packs the weights for the kernels (gate interleave for the LSTM slices, tf32 rounding,
+ * bf16 copies) on `device`. */
+avs_status avs_model_create(const avs_weights* w, int device, avs_model** out);
+/* Re-pack after the caller changed parameters (load_state_dict / optimizer step). */
+avs_status avs_model_update(avs_model* m, const avs_weights* w);
+void avs_model_destroy(avs_model* m);
+
+/* Replaces AVBiLSTMModel.forward (av_model.py:33-46) for a batch of n_videos videos.
+ *   visual [total_rows, Dv], audio [total_rows, Da], scores [total_rows]  (fp32, `space`)
+ *   row_start[b], lengths[b] : host int32; rows outside every video (padding) never influence
+ *   a video's result and their scores are unspecified.  The caller applies the final
+ *   .squeeze() (a view). */
+avs_status avs_forward(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
+                       int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int attn_axis,
+                       int precision, float* scores, int space, void* cuda_stream);
+
+/* Summary generation for a batch (shot pooling over change points + 0/1 knapsack at the
+ * length budget + keyshot bitmap).  NOT IN THE REFERENCE: specified by
+ * oracle/av_oracle.py (integer arithmetic, bit-exact).
+ *   scores     fp32 [total_rows] (`space`), same row indexing as avs_forward
+ *   positions  int32 [total_rows] (`space`): original frame index of every sampled frame
+ *   n_frames   host int32 [n]; cps host int32 [sum S, 2] inclusive; cps_start host int32 [n+1]
+ *   capacity_b = floor(n_frames_b * prop_num / prop_den)
+ * outputs (`space`): picks uint8 [sum S]; seg_mean int64 [sum S] (2^-24 fixed point, may be NULL);
+ *   summary uint8 [sum n_frames] addressed by host int64 summary_start[n+1] (may be NULL). */
+avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* positions, int32_t n_videos,
+                         const int32_t* row_start, const int32_t* lengths, const int32_t* n_frames,
+                         const int32_t* cps, const int32_t* cps_start, int32_t prop_num, int32_t prop_den,
+                         uint8_t* picks, int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start,
+                         int space, void* cuda_stream);
+
+/* ---- building blocks (device pointers only), exported so each kernel can be parity-tested
+ * against the reference sub-module it replaces and reused by
+ * models/attention.py's drop-in. ---- */
+
+/* nn.Linear (+ReLU): C[M, N] = act(A[M, K] * W[N, K]^T + bias[N]); fp32 in/out.
+ * `precision` as above; K % 4 == 0, N % 16 == 0 for the tensor-core paths. */
+avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t M, int32_t N, int32_t K,
+                      int relu, int precision, float* C, void* cuda_stream);
+
+/* Both nn.LSTM modules of the model (av_model.py:39-40) on packed rows:
+ * v_emb, a_emb [total_rows, H] -> fused [total_rows, 2H] = [v_fwd | v_bwd | a_fwd | a_bwd]. */
+avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows,
+                           int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int precision,
+                           float* fused, void* cuda_stream);
+
+/* Scaled-dot-product multi-head attention core on a packed qkv buffer [rows, 3E] (q | k | v),
+ * heads = contiguous dh-wide column slices (attention.py:17-23).  Sequence s consists of rows
+ * seq_base[s] + i * seq_stride[s], i < seq_len[s] (host int32 arrays).  ctx [rows, E] fp32. */
+avs_status avs_attention(const float* qkv, int64_t rows, int32_t E, int32_t num_heads, int32_t n_seqs,
+                         const int32_t* seq_base, const int32_t* seq_stride, const int32_t* seq_len,
+                         int precision, float* ctx, void* cuda_stream);
+
+/* Overlap-F1 between predicted and ground-truth shot lists for a batch (evaluation/metrics.py:1-9,
+ * utils/shot_metrics.py:4-16): shots int32 [*, 2] half-open (start, end), offsets host int32 [n+1].
+ * f1 double [n] written to host memory. */
+avs_status avs_temporal_f1(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
+                           const int32_t* gt_start, int32_t n_videos, double* f1_host, void* cuda_stream);
+
+/* Counters: number of kernel launches issued by this library since load (gpu_launches in bench.py). */
+int64_t avs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSUM_B200_H */

@@ -1,0 +1,160 @@
+"""Generate tests/golden/*.npz by IMPORTING THE REFERENCE from /root/reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+Every fixture stores the seeded-input recipe, the reference's outputs and a
+checksum of the weights, so the tests can rebuild identical inputs without the
+reference.  Also cross-checks oracle/av_oracle_torch.py (bit-exact) and
+oracle/av_oracle.py (numpy, <= 2e-5 abs) against the imported reference.
+"""
+import os
+import sys
+import types
+
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(1, "/root/reference")
+
+import numpy as np
+import torch
+
+# features/fusion.py imports the absent third-party `fastdtw`; stub it
+_stub = types.ModuleType("fastdtw")
+_stub.fastdtw = lambda *a, **k: (_ for _ in ()).throw(TypeError("fastdtw stub"))
+sys.modules.setdefault("fastdtw", _stub)
+
+from models.av_model import AVBiLSTMModel            # noqa: E402  (the reference)
+from models.attention import MultiHeadSelfAttention  # noqa: E402
+from features import fusion as ref_fusion            # noqa: E402
+from utils.alignments import align_shots_to_annotations as ref_align  # noqa: E402
+from utils.shot_metrics import compute_f1 as ref_compute_f1, calculate_overlap as ref_overlap  # noqa: E402
+from evaluation.metrics import compute_temporal_f1 as ref_tf1  # noqa: E402
+
+import avsum_b200  # noqa: E402,F401
+from avsum_b200 import synth  # noqa: E402
+from oracle import av_oracle, av_oracle_torch  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(8)
+
+
+def ref_model(vd, ad, hd=512, seed=0, spread=False):
+    torch.manual_seed(seed)
+    m = AVBiLSTMModel(vd, ad, hd).eval()
+    if spread:
+        with torch.no_grad():
+            m.scorer[2].weight.mul_(50.0)
+    sd = synth.seeded_state_dict(vd, ad, hd, seed, spread)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    return m, sd
+
+
+@torch.no_grad()
+def ref_forward(m, visual, audio, axis):
+    if axis == "literal":
+        return m(visual, audio)
+    # temporal: same parameters, frames as the sequence axis
+    v_out, _ = m.visual_bilstm(m.visual_fc(visual))
+    a_out, _ = m.audio_bilstm(m.audio_fc(audio))
+    fused = torch.cat([v_out, a_out], dim=-1).transpose(0, 1)
+    attn = m.attention(fused, fused, fused)[0].transpose(0, 1)
+    return m.scorer(attn).squeeze()
+
+
+def check_ports(m, sd, visual, audio, axis, want):
+    port = av_oracle_torch.RefPortModel(visual.shape[-1], audio.shape[-1], 512).eval()
+    port.load_state_dict(sd)
+    with torch.no_grad():
+        got = port(visual, audio, axis)
+    assert torch.equal(got, want), "torch port differs from reference"
+    npy = av_oracle.forward({k: v.numpy() for k, v in sd.items()}, visual.numpy(), audio.numpy(), 4, axis)
+    err = float(np.max(np.abs(npy - want.numpy())))
+    assert err < 2e-5, err
+    return err
+
+
+def model_case(name, vd, ad, B, T, seed_in, spread=False):
+    m, sd = ref_model(vd, ad, spread=spread)
+    g = torch.Generator().manual_seed(seed_in)
+    visual = torch.randn(B, T, vd, generator=g)
+    audio = torch.randn(B, T, ad, generator=g)
+    rec = dict(visual_dim=vd, audio_dim=ad, B=B, T=T, seed_in=seed_in, spread=int(spread),
+               weights_checksum=synth.state_dict_checksum(sd))
+    for axis in ("literal", "temporal"):
+        want = ref_forward(m, visual, audio, axis)
+        err = check_ports(m, sd, visual, audio, axis, want)
+        rec["scores_" + axis] = want.numpy()
+        print(f"{name:28s} {axis:8s} shape={tuple(want.shape)} range=[{want.min():.4f},{want.max():.4f}] numpy-oracle err={err:.2e}")
+    np.savez(os.path.join(OUT, name + ".npz"), **rec)
+
+
+def main():
+    # config 1 of BASELINE.json (layout [1, T, D] drawn as synth.make_video does: visual then audio, seed 1234)
+    m, sd = ref_model(1024, 128)
+    for spread in (False, True):
+        m, sd = ref_model(1024, 128, spread=spread)
+        vid = synth.config1()
+        rec = dict(weights_checksum=synth.state_dict_checksum(sd), spread=int(spread))
+        for axis in ("literal", "temporal"):
+            want = ref_forward(m, vid.visual[None], vid.audio[None], axis)
+            err = check_ports(m, sd, vid.visual[None], vid.audio[None], axis, want)
+            rec["scores_" + axis] = want.numpy()
+            print(f"config1 spread={int(spread)} {axis:8s} range=[{want.min():.4f},{want.max():.4f}] numpy-oracle err={err:.2e}")
+        np.savez(os.path.join(OUT, f"config1_spread{int(spread)}.npz"), **rec)
+
+    model_case("batch3_T17", 1024, 128, 3, 17, 77)            # literal B>1 mixes videos
+    model_case("batch2_T1", 1024, 128, 2, 1, 78)              # squeeze -> (2,)
+    model_case("batch1_T1", 1024, 128, 1, 1, 79)              # squeeze -> ()
+    model_case("default_dims_T40", 4096, 296, 1, 40, 80)      # reference default ctor dims
+    model_case("batch2_T130_spread", 1024, 128, 2, 130, 81, spread=True)
+
+    # a few videos of config 2 (first 4) -- temporal + literal B=1 scores
+    m, sd = ref_model(1024, 128, spread=True)
+    vids = synth.config2()[:4]
+    rec = dict(weights_checksum=synth.state_dict_checksum(sd), lengths=np.asarray([v.T for v in vids]))
+    for axis in ("literal", "temporal"):
+        rec["scores_" + axis] = np.concatenate(
+            [ref_forward(m, v.visual[None], v.audio[None], axis).numpy().reshape(-1) for v in vids])
+    np.savez(os.path.join(OUT, "config2_first4_spread1.npz"), **rec)
+    print("config2_first4", rec["lengths"])
+
+    # MultiHeadSelfAttention (models/attention.py)
+    torch.manual_seed(5)
+    att = MultiHeadSelfAttention(1024, 4).eval()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 33, 1024, generator=g)
+    with torch.no_grad():
+        y = att(x)
+    asd = {k: v.numpy() for k, v in att.state_dict().items()}
+    err = float(np.max(np.abs(av_oracle.mhsa_forward(asd, x.numpy(), 4) - y.numpy())))
+    assert err < 2e-5, err
+    np.savez(os.path.join(OUT, "mhsa_E1024_H4.npz"), out=y.numpy()[:, :, ::8], seed_w=5, seed_in=6, B=2, T=33,
+             weights_checksum=synth.state_dict_checksum(att.state_dict()))
+    print("mhsa numpy-oracle err", err)
+
+    # features/fusion.py helpers (a9, a11), utils + evaluation helpers (a12, f-rows)
+    g = torch.Generator().manual_seed(11)
+    fv = torch.randn(23, 64, generator=g)
+    fa = torch.randn(31, 64, generator=g)
+    dtw = ref_fusion.compute_dtw(fv, fa)
+    path = np.stack([np.sort(np.random.default_rng(3).integers(0, 23, 60)), np.arange(60) % 31], axis=1)
+    interp = ref_fusion.interpolate_features(fv, path, 20)
+    shots = [(0, 45), (45, 200), (200, 260), (260, 1000)]
+    ann = np.random.default_rng(4).random(40)
+    al = ref_align(shots, ann, 30.0)
+    pred = [(0, 50), (120, 180), (400, 460)]
+    gt = [(30, 140), (170, 420)]
+    np.savez(os.path.join(OUT, "helpers.npz"), dtw=dtw, path=path, interp=interp.numpy(),
+             shots=np.asarray(shots), ann=ann, aligned=al.numpy(), pred=np.asarray(pred), gt=np.asarray(gt),
+             f1_metrics=ref_tf1(pred, gt, 1000), f1_shot=ref_compute_f1(pred, gt, 1000), overlap=ref_overlap(pred, gt))
+    assert abs(av_oracle.temporal_f1(pred, gt) - ref_tf1(pred, gt, 1000)) == 0
+    assert np.array_equal(av_oracle.align_shots_to_annotations(shots, ann, 30.0), al.numpy())
+    print("helpers ok; dtw dtype", dtw.dtype, "aligned dtype", al.dtype)
+
+
+if __name__ == "__main__":
+    main()
