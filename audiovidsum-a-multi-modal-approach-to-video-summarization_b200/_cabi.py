@@ -25,7 +25,8 @@ PRECISIONS = {"tf32": AVS_PREC_TF32, "bf16": AVS_PREC_BF16, "fp32_simt": AVS_PRE
 EXPORTS = [
     "avs_last_error", "avs_version", "avs_device_ok", "avs_model_create", "avs_model_update",
     "avs_model_destroy", "avs_forward", "avs_summarize", "avs_linear", "avs_bilstm_pair",
-    "avs_attention", "avs_temporal_f1", "avs_launch_count",
+    "avs_attention", "avs_temporal_f1", "avs_launch_count", "avs_profile", "avs_profile_stages",
+    "avs_profile_stage_name", "avs_profile_read",
 ]
 
 
@@ -101,6 +102,13 @@ def lib() -> C.CDLL:
     L.avs_attention.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, C.c_int, vp, vp]
     L.avs_temporal_f1.restype = C.c_int
     L.avs_temporal_f1.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    L.avs_profile.restype = None
+    L.avs_profile.argtypes = [C.c_int]
+    L.avs_profile_stages.restype = C.c_int
+    L.avs_profile_stage_name.restype = C.c_char_p
+    L.avs_profile_stage_name.argtypes = [C.c_int]
+    L.avs_profile_read.restype = None
+    L.avs_profile_read.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -126,3 +134,18 @@ def np_ptr(a):
 
 def launch_count() -> int:
     return int(lib().avs_launch_count())
+
+
+def profile(enable: int) -> None:
+    lib().avs_profile(int(enable))
+
+
+def profile_read():
+    """{stage name: (total ms, calls)} accumulated since the last reset."""
+    import numpy as np
+    L = lib()
+    n = L.avs_profile_stages()
+    ms = np.zeros(n, dtype=np.float64)
+    calls = np.zeros(n, dtype=np.int64)
+    L.avs_profile_read(C.c_void_p(ms.ctypes.data), C.c_void_p(calls.ctypes.data))
+    return {L.avs_profile_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}

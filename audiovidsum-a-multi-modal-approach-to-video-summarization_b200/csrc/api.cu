@@ -24,6 +24,63 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional per-stage device timing (CUDA events on the launching stream) -------------
+// Enabled by avs_profile(1); events are resolved lazily in avs_profile_read so the hot path
+// never synchronises because of profiling.
+enum Stage : int { ST_CONVERT = 0, ST_FC, ST_IH_PROJ, ST_LSTM, ST_QKV_PROJ, ST_ATTENTION, ST_OUT_PROJ, ST_SCORER,
+                   ST_POOL, ST_KNAPSACK, ST_COUNT };
+static const char* const kStageNames[ST_COUNT] = {"convert_tf32", "fc_gemm", "lstm_input_gemm", "lstm_recurrence",
+                                                  "attn_in_proj_gemm", "attention_core", "attn_out_proj_gemm",
+                                                  "score_head_gemm", "shot_pool", "knapsack_select"};
+struct Profiler {
+    bool enabled = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int stage; cudaEvent_t a, b; };
+    std::vector<Rec> pending;
+    double ms[ST_COUNT] = {};
+    long long calls[ST_COUNT] = {};
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void resolve() {
+        for (auto& r : pending) {
+            cudaEventSynchronize(r.b);
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+                ms[r.stage] += t;
+                calls[r.stage] += 1;
+            }
+        }
+        pending.clear();
+        used = 0;
+    }
+};
+static Profiler g_prof;
+struct StageTimer {
+    int stage;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr;
+    StageTimer(int stage_, cudaStream_t st_) : stage(stage_), st(st_) {
+        if (g_prof.enabled) {
+            a = g_prof.get();
+            cudaEventRecord(a, st);
+        }
+    }
+    ~StageTimer() {
+        if (a) {
+            cudaEvent_t b = g_prof.get();
+            cudaEventRecord(b, st);
+            g_prof.pending.push_back({stage, a, b});
+        }
+    }
+};
+
 namespace {
 
 constexpr int HC = 256;  // the kernels are built for hidden_dim = 512 (SURVEY.md 8a defaults)
@@ -269,6 +326,24 @@ const char* avs_last_error(void) { return g_err; }
 int avs_version(void) { return 100; }
 int64_t avs_launch_count(void) { return g_launches.load(); }
 
+void avs_profile(int enable) {
+    g_prof.resolve();
+    g_prof.enabled = enable != 0;
+    if (enable == 2) {  // reset accumulators
+        for (int i = 0; i < ST_COUNT; ++i) { g_prof.ms[i] = 0; g_prof.calls[i] = 0; }
+        g_prof.enabled = true;
+    }
+}
+int avs_profile_stages(void) { return ST_COUNT; }
+const char* avs_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+void avs_profile_read(double* ms, int64_t* calls) {
+    g_prof.resolve();
+    for (int i = 0; i < ST_COUNT; ++i) {
+        if (ms) ms[i] = g_prof.ms[i];
+        if (calls) calls[i] = g_prof.calls[i];
+    }
+}
+
 int avs_device_ok(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -408,40 +483,48 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         xv = in_v;
         xa = in_a;
     }
+    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
     if (!simt) {
+        StageTimer tm(ST_CONVERT, st);
         AVS_TRY(convert_f32(xv, in_v, R * Dv, DT_F32, 1, st));
         AVS_TRY(convert_f32(xa, in_a, R * Da, DT_F32, 1, st));
         xv = in_v;
         xa = in_a;
     }
-    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
 
     // ---- K1: visual_fc / audio_fc (Linear + ReLU; Dropout is identity in eval)  av_model.py:35-36
-    GemmEpilogue e1;
-    e1.relu = 1;
-    e1.round_tf32 = rnd;
-    e1.ldc = H;
-    e1.bias = m->fc_v_b;
-    e1.C = v_emb;
-    AVS_TRY(run_gemm(precision, xv, Dv, m->fc_v_w_x, m->fc_v_w_t, Dv, R, H, Dv, e1, st));
-    e1.bias = m->fc_a_b;
-    e1.C = a_emb;
-    AVS_TRY(run_gemm(precision, xa, Da, m->fc_a_w_x, m->fc_a_w_t, Da, R, H, Da, e1, st));
+    {
+        StageTimer tm(ST_FC, st);
+        GemmEpilogue e1;
+        e1.relu = 1;
+        e1.round_tf32 = rnd;
+        e1.ldc = H;
+        e1.bias = m->fc_v_b;
+        e1.C = v_emb;
+        AVS_TRY(run_gemm(precision, xv, Dv, m->fc_v_w_x, m->fc_v_w_t, Dv, R, H, Dv, e1, st));
+        e1.bias = m->fc_a_b;
+        e1.C = a_emb;
+        AVS_TRY(run_gemm(precision, xa, Da, m->fc_a_w_x, m->fc_a_w_t, Da, R, H, Da, e1, st));
+    }
 
     // ---- K2a: LSTM input projections, both directions at once  av_model.py:39-40
-    GemmEpilogue e2;
-    e2.ldc = 2 * G4;
-    e2.bias = m->ih_v_b;
-    e2.C = xg_v;
-    AVS_TRY(run_gemm(precision, v_emb, H, m->ih_v_x, m->ih_v_t, H, R, 2 * G4, H, e2, st));
-    e2.bias = m->ih_a_b;
-    e2.C = xg_a;
-    AVS_TRY(run_gemm(precision, a_emb, H, m->ih_a_x, m->ih_a_t, H, R, 2 * G4, H, e2, st));
+    {
+        StageTimer tm(ST_IH_PROJ, st);
+        GemmEpilogue e2;
+        e2.ldc = 2 * G4;
+        e2.bias = m->ih_v_b;
+        e2.C = xg_v;
+        AVS_TRY(run_gemm(precision, v_emb, H, m->ih_v_x, m->ih_v_t, H, R, 2 * G4, H, e2, st));
+        e2.bias = m->ih_a_b;
+        e2.C = xg_a;
+        AVS_TRY(run_gemm(precision, a_emb, H, m->ih_a_x, m->ih_a_t, H, R, 2 * G4, H, e2, st));
+    }
 
     // ---- K2b: recurrences; writes [v_fwd | v_bwd | a_fwd | a_bwd] = torch.cat of av_model.py:43
     {
         const int slots = plan.n_groups * plan.nb;
         LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
+        StageTimer tm(ST_LSTM, st);
         AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, rnd, nullptr, 0, st));
     }
 
@@ -455,13 +538,17 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         e3.C = ctx;
         e3.ldc = E;
         e3.round_tf32 = rnd;
+        StageTimer tm(ST_QKV_PROJ, st);
         AVS_TRY(run_gemm(precision, fused, E, m->in_w_x + 2ull * E * E, m->in_w_t + 2ull * E * E, E, R, E, E, e3, st));
     } else {
         GemmEpilogue e3;
         e3.bias = m->in_b;
         e3.C = qkv;
         e3.ldc = 3 * E;
-        AVS_TRY(run_gemm(precision, fused, E, m->in_w_x, m->in_w_t, E, R, 3 * E, E, e3, st));
+        {
+            StageTimer tm(ST_QKV_PROJ, st);
+            AVS_TRY(run_gemm(precision, fused, E, m->in_w_x, m->in_w_t, E, R, 3 * E, E, e3, st));
+        }
         std::vector<int32_t> sd(3 * static_cast<size_t>(n_seqs));
         int seq_max = 0;
         if (attn_axis == AVS_ATTN_TEMPORAL) {
@@ -481,6 +568,7 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         }
         AVS_CUDA(cudaMemcpyAsync(seq_dev, sd.data(), sd.size() * 4, cudaMemcpyHostToDevice, st));
         SeqDesc seqs{seq_dev, seq_dev + n_seqs, seq_dev + 2 * n_seqs, n_seqs, seq_max};
+        StageTimer tm(ST_ATTENTION, st);
         AVS_TRY(attention_simt(qkv, 3 * E, E, m->heads, seqs, ctx, E, rnd, st));
     }
 
@@ -490,7 +578,10 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     e5.C = attn_out;
     e5.ldc = E;
     e5.round_tf32 = rnd;
-    AVS_TRY(run_gemm(precision, ctx_ptr, ctx_ld, m->out_w_x, m->out_w_t, E, R, E, E, e5, st));
+    {
+        StageTimer tm(ST_OUT_PROJ, st);
+        AVS_TRY(run_gemm(precision, ctx_ptr, ctx_ld, m->out_w_x, m->out_w_t, E, R, E, E, e5, st));
+    }
 
     // ---- K6: scorer (Linear 1024->64 + ReLU + Linear 64->1 + Sigmoid fused)  av_model.py:29-31,46
     GemmEpilogue e6;
@@ -499,7 +590,10 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     e6.score_w2 = m->sc2_w;
     e6.score_b2 = m->sc2_b;
     e6.scores = scores_dev;
-    AVS_TRY(run_gemm(precision, attn_out, E, m->sc0_w_x, m->sc0_w_t, E, R, 64, E, e6, st));
+    {
+        StageTimer tm(ST_SCORER, st);
+        AVS_TRY(run_gemm(precision, attn_out, E, m->sc0_w_x, m->sc0_w_t, E, R, 64, E, e6, st));
+    }
 
     if (space == AVS_HOST) {
         AVS_CUDA(cudaMemcpyAsync(scores, scores_dev, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost, st));
@@ -610,10 +704,16 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
     sb.prop_num = prop_num;
     sb.prop_den = prop_den;
     sb.max_cap = max_cap;
-    AVS_TRY(shot_pool(sc, pos, sb, seg_sum, st));
+    {
+        StageTimer tm(ST_POOL, st);
+        AVS_TRY(shot_pool(sc, pos, sb, seg_sum, st));
+    }
     long long* seg_mean_target = space == AVS_HOST ? (seg_mean ? seg_mean_dev : nullptr)
                                                     : reinterpret_cast<long long*>(seg_mean);
-    AVS_TRY(knapsack_select(sb, seg_sum, seg_mean_target, picks_dev, summary_dev, keep, dp_ws, st));
+    {
+        StageTimer tm(ST_KNAPSACK, st);
+        AVS_TRY(knapsack_select(sb, seg_sum, seg_mean_target, picks_dev, summary_dev, keep, dp_ws, st));
+    }
     if (space == AVS_HOST) {
         AVS_CUDA(cudaMemcpyAsync(picks, picks_dev, total_S, cudaMemcpyDeviceToHost, st));
         if (seg_mean) AVS_CUDA(cudaMemcpyAsync(seg_mean, seg_mean_dev, static_cast<size_t>(total_S) * 8,

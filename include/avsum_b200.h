@@ -146,6 +146,14 @@ avs_status avs_temporal_f1(const int32_t* pred, const int32_t* pred_start, const
 /* Counters: number of kernel launches issued by this library since load (gpu_launches in bench.py). */
 int64_t avs_launch_count(void);
 
+/* Per-stage device timing with CUDA events on the launching stream (used by bench.py's roofline).
+ * avs_profile(1) enables, (0) disables, (2) resets the accumulators and enables.  Events are
+ * resolved lazily by avs_profile_read, which fills ms[avs_profile_stages()] and calls[...]. */
+void avs_profile(int enable);
+int avs_profile_stages(void);
+const char* avs_profile_stage_name(int stage);
+void avs_profile_read(double* ms, int64_t* calls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,330 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200).  Every check goes through the C ABI
+(``libavsum_b200.so``) and compares with the oracle / golden vectors on identical seeded
+inputs.  Tolerances: fp32 frame scores <= 1e-3 relative in the tf32 tensor-core mode
+(BASELINE.json north_star), <= 2e-5 in the CUDA-core fp32 mode; integer outputs bit-exact.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from avsum_b200 import _cabi, runtime, synth
+from oracle import av_oracle, av_oracle_torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = {"tf32": 1e-3, "fp32_simt": 2e-5}
+
+
+def rel(got, want):
+    return float(np.max(np.abs(np.asarray(got, np.float64) - want) / np.abs(want)))
+
+
+def make_model(vd=1024, ad=128, spread=False, **kw):
+    from avsum_b200.models.av_model import AVBiLSTMModel
+    m = AVBiLSTMModel(vd, ad, 512, **kw).eval()
+    m.load_state_dict(synth.seeded_state_dict(vd, ad, 512, 0, spread))
+    return m.cuda()
+
+
+@pytest.fixture(scope="module")
+def native(cuda_ready):
+    sd = synth.seeded_state_dict()
+    return runtime.NativeModel({k: v.cuda() for k, v in sd.items()}, 1024, 128)
+
+
+# ------------------------------------------------------------------ K1/K3/K5: nn.Linear
+@pytest.mark.parametrize("prec", ["tf32", "fp32_simt"])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (300, 512, 128), (1000, 2048, 512), (500, 64, 1024),
+                                   (320, 512, 296), (77, 1024, 1024), (1, 512, 4096), (129, 3072, 1024)])
+def test_linear_matches_torch(cuda_ready, prec, shape):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    for relu in (False, True):
+        want = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        want = want.relu() if relu else want
+        got = runtime.linear(x, w, b, relu=relu, precision=prec)
+        err = float((got.double() - want).abs().max() / want.abs().max())
+        assert err < (2e-3 if prec == "tf32" else 2e-6), (shape, relu, err)
+
+
+def test_linear_without_bias_and_bad_shapes(cuda_ready):
+    x = torch.randn(40, 64, device="cuda")
+    w = torch.randn(32, 64, device="cuda")
+    got = runtime.linear(x, w, None, precision="fp32_simt")
+    assert float((got - x @ w.T).abs().max()) < 1e-4
+    with pytest.raises(_cabi.AvsUnsupported):   # N % 16 != 0 on the tensor-core path
+        runtime.linear(x, torch.randn(30, 64, device="cuda"), None, precision="tf32")
+    with pytest.raises(ValueError):             # K % 4 != 0 breaks the 16-byte TMA pitch
+        runtime.linear(torch.randn(8, 30, device="cuda"), torch.randn(32, 30, device="cuda"), None, precision="tf32")
+
+
+# ------------------------------------------------------------------ K2: both BiLSTMs
+@pytest.mark.parametrize("lens", [[37], [5, 64, 1, 33], list(range(20, 39)), [3] * 70])
+def test_bilstm_pair_matches_torch_lstm(native, lens):
+    sd = synth.seeded_state_dict()
+    R = sum(lens)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    g = torch.Generator().manual_seed(len(lens))
+    v, a = torch.randn(R, 512, generator=g), torch.randn(R, 512, generator=g)
+    lv = torch.nn.LSTM(512, 256, bidirectional=True, batch_first=True)
+    la = torch.nn.LSTM(512, 256, bidirectional=True, batch_first=True)
+    lv.load_state_dict({k.split(".", 1)[1]: t for k, t in sd.items() if k.startswith("visual_bilstm")})
+    la.load_state_dict({k.split(".", 1)[1]: t for k, t in sd.items() if k.startswith("audio_bilstm")})
+    want = torch.empty(R, 1024)
+    with torch.no_grad():
+        for s, n in zip(starts, lens):
+            want[s:s + n, :512] = lv(v[None, s:s + n])[0][0]
+            want[s:s + n, 512:] = la(a[None, s:s + n])[0][0]
+    ln = np.asarray(lens, dtype=np.int32)
+    for prec, tol in (("fp32_simt", 2e-5), ("tf32", 3e-3)):
+        fused = torch.zeros(R, 1024, device="cuda")
+        vc, ac = v.cuda(), a.cuda()
+        _cabi.check(native.lib.avs_bilstm_pair(native._handle, C.c_void_p(vc.data_ptr()), C.c_void_p(ac.data_ptr()), R,
+                                               len(lens), _cabi.np_ptr(starts), _cabi.np_ptr(ln), _cabi.PRECISIONS[prec],
+                                               C.c_void_p(fused.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert float((fused.cpu() - want).abs().max()) < tol
+
+
+# ------------------------------------------------------------------ full forward vs reference goldens
+@pytest.mark.parametrize("prec", ["tf32", "fp32_simt"])
+@pytest.mark.parametrize("spread", [0, 1])
+def test_forward_config1_matches_reference(cuda_ready, golden_dir, prec, spread):
+    g = np.load(os.path.join(golden_dir, f"config1_spread{spread}.npz"))
+    m = make_model(spread=bool(spread), precision=prec)
+    vid = synth.config1()
+    for axis in ("literal", "temporal"):
+        got = m(vid.visual[None].cuda(), vid.audio[None].cuda(), attn_axis=axis)
+        assert got.shape == (320,) and got.is_cuda
+        assert rel(got.cpu().numpy(), g["scores_" + axis]) < REL_TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["tf32", "fp32_simt"])
+@pytest.mark.parametrize("name", ["batch3_T17", "batch2_T1", "batch1_T1", "default_dims_T40", "batch2_T130_spread"])
+def test_forward_cases_match_reference(cuda_ready, golden_dir, prec, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    vd, ad, B, T = int(g["visual_dim"]), int(g["audio_dim"]), int(g["B"]), int(g["T"])
+    m = make_model(vd, ad, bool(int(g["spread"])), precision=prec)
+    gen = torch.Generator().manual_seed(int(g["seed_in"]))
+    visual, audio = torch.randn(B, T, vd, generator=gen), torch.randn(B, T, ad, generator=gen)
+    for axis in ("literal", "temporal"):
+        got = m(visual.cuda(), audio.cuda(), attn_axis=axis).cpu().numpy()
+        want = g["scores_" + axis]
+        assert got.shape == want.shape          # .squeeze() semantics of av_model.py:46
+        assert rel(got, want) < REL_TOL[prec]
+
+
+def test_forward_host_tensors_and_state_dict_reload(cuda_ready, golden_dir):
+    g0 = np.load(os.path.join(golden_dir, "config1_spread0.npz"))
+    g1 = np.load(os.path.join(golden_dir, "config1_spread1.npz"))
+    m = make_model()
+    vid = synth.config1()
+    got = m(vid.visual[None], vid.audio[None])            # host inputs: H2D/D2H inside the native call
+    assert not got.is_cuda and rel(got.numpy(), g0["scores_literal"]) < 1e-3
+    m.load_state_dict(synth.seeded_state_dict(spread=True))   # in-place parameter change -> re-pack
+    got = m(vid.visual[None].cuda(), vid.audio[None].cuda()).cpu().numpy()
+    assert rel(got, g1["scores_literal"]) < 1e-3
+
+
+def test_unbatched_input_is_temporal_attention(cuda_ready, golden_dir):
+    g = np.load(os.path.join(golden_dir, "config1_spread1.npz"))
+    m = make_model(spread=True)
+    vid = synth.config1()
+    got = m(vid.visual.cuda(), vid.audio.cuda()).cpu().numpy()   # [T, D] -> torch unbatched semantics
+    assert rel(got, g["scores_temporal"]) < 1e-3
+
+
+def test_masked_batch_equals_unbatched(cuda_ready):
+    """SURVEY section 4 'masking parity': batched+masked output for video i == B=1 run of video i."""
+    m = make_model(spread=True, attn_axis="temporal")
+    lens = [57, 130, 1, 88]
+    T = max(lens)
+    g = torch.Generator().manual_seed(9)
+    visual, audio = torch.randn(4, T, 1024, generator=g).cuda(), torch.randn(4, T, 128, generator=g).cuda()
+    visual[1, 100:] = float("nan")   # garbage in padding of shorter videos must not leak
+    visual[0, 57:] = float("inf")
+    lens[1] = 100
+    batched = m(visual, audio, lengths=lens)
+    assert batched.shape == (4, T)
+    for b, n in enumerate(lens):
+        alone = m(visual[b:b + 1, :n], audio[b:b + 1, :n]).reshape(-1)
+        assert torch.equal(batched[b, :n], alone), b      # same kernels, same data -> bit identical
+        assert float(batched[b, n:].abs().sum()) == 0.0
+    # literal_b1 accepts ragged lengths too and equals the per-video literal call
+    b1 = m(visual, audio, lengths=lens, attn_axis="literal_b1")
+    for b, n in enumerate(lens):
+        alone = m(visual[b:b + 1, :n], audio[b:b + 1, :n], attn_axis="literal").reshape(-1)
+        assert torch.equal(b1[b, :n], alone)
+    with pytest.raises(ValueError):
+        m(visual, audio, lengths=lens, attn_axis="literal")
+
+
+def test_config2_full_batch_matches_cpu_port(cuda_ready, golden_dir):
+    """BASELINE configs[1] at full size: 50 videos, 21,477 frames, scores vs the torch CPU port
+    (bit-identical to the reference, tests/test_oracle_golden.py) and vs the reference goldens."""
+    g = np.load(os.path.join(golden_dir, "config2_first4_spread1.npz"))
+    vids = synth.config2()
+    sd = synth.seeded_state_dict(spread=True)
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
+    port.load_state_dict(sd)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for axis, key in (("literal_b1", "scores_literal"), ("temporal", "scores_temporal")):
+        m = make_model(spread=True, attn_axis=axis)
+        got = m.score_videos([(v.visual, v.audio) for v in vids])            # host in / host out
+        got_dev = m.score_videos([(v.visual.cuda(), v.audio.cuda()) for v in vids])
+        assert all(torch.equal(a, b.cpu()) for a, b in zip(got, got_dev))
+        assert rel(torch.cat(got[:4]).numpy(), g[key]) < 1e-3
+        want = av_oracle_torch.run_videos(port, [(v.visual, v.audio) for v in vids],
+                                          "literal" if axis == "literal_b1" else "temporal")
+        worst = max(rel(a.numpy(), b.numpy()) for a, b in zip(got, want))
+        assert worst < 1e-3, (axis, worst)
+
+
+# ------------------------------------------------------------------ MultiHeadSelfAttention drop-in
+def test_mhsa_matches_reference(cuda_ready, golden_dir):
+    from avsum_b200.models.attention import MultiHeadSelfAttention
+    g = np.load(os.path.join(golden_dir, "mhsa_E1024_H4.npz"))
+    torch.manual_seed(int(g["seed_w"]))
+    att = MultiHeadSelfAttention(1024, 4).eval()
+    assert abs(synth.state_dict_checksum(att.state_dict()) - float(g["weights_checksum"])) < 1e-6
+    x = torch.randn(2, 33, 1024, generator=torch.Generator().manual_seed(int(g["seed_in"])))
+    for prec, tol in (("fp32_simt", 5e-6), ("tf32", 2e-3)):
+        att.precision = prec
+        y = att.cuda()(x.cuda()).cpu().numpy()
+        assert y.shape == (2, 33, 1024)
+        assert float(np.max(np.abs(y[:, :, ::8] - g["out"]))) < tol * float(np.max(np.abs(g["out"])))
+
+
+# ------------------------------------------------------------------ K7/K8: pooling + knapsack (bit-exact)
+def _summarize_and_compare(native, vids, scores, space):
+    lens = [v.T for v in vids]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    pos = np.concatenate([v.positions for v in vids]).astype(np.int32)
+    picks, seg_mean, summary, cps_start, sum_start = native.summarize_rows(
+        torch.from_numpy(scores).to(space), torch.from_numpy(pos).to(space), starts, lens,
+        [v.n_frames for v in vids], [v.cps for v in vids], 0.15)
+    torch.cuda.synchronize()
+    picks, seg_mean, summary = picks.cpu().numpy(), seg_mean.cpu().numpy(), summary.cpu().numpy()
+    for i, v in enumerate(vids):
+        wp, ws, wm = av_oracle.generate_summary(scores[starts[i]:starts[i] + lens[i]], v.cps, v.n_frames, v.positions)
+        assert np.array_equal(wm, seg_mean[cps_start[i]:cps_start[i + 1]]), i
+        assert np.array_equal(wp, picks[cps_start[i]:cps_start[i + 1]]), i
+        assert np.array_equal(ws, summary[sum_start[i]:sum_start[i + 1]]), i
+        nf = v.cps[:, 1] - v.cps[:, 0] + 1
+        assert int(ws.sum()) == int((wp * nf).sum()) <= (v.n_frames * 15) // 100
+    return picks
+
+
+@pytest.mark.parametrize("kind", ["uniform", "near_tie", "spiky", "constant", "zeros"])
+@pytest.mark.parametrize("space", ["cuda", "cpu"])
+def test_summarize_config2_bit_exact(native, kind, space):
+    vids = synth.config2()
+    n = sum(v.T for v in vids)
+    rng = np.random.default_rng(11)
+    scores = {"uniform": rng.random(n), "near_tie": 0.52 + 1e-4 * rng.standard_normal(n),
+              "spiky": rng.random(n) ** 8, "constant": np.full(n, 0.5), "zeros": np.zeros(n)}[kind].astype(np.float32)
+    _summarize_and_compare(native, vids, scores, space)
+
+
+def test_summarize_edge_cases(native):
+    rng = np.random.default_rng(5)
+    # single-shot video, a one-frame video, irregular positions, shots not covering the tail
+    v1 = synth.Video(torch.zeros(1, 1), torch.zeros(1, 1), 40, np.array([0], np.int32), np.array([[0, 39]], np.int32))
+    v2 = synth.Video(torch.zeros(7, 1), torch.zeros(7, 1), 100, np.array([3, 10, 11, 40, 41, 90, 99], np.int32),
+                     np.array([[0, 4], [5, 5], [6, 50], [60, 98]], np.int32))
+    v3 = synth.Video(torch.zeros(3, 1), torch.zeros(3, 1), 6, np.array([0, 2, 4], np.int32),
+                     np.array([[0, 0], [1, 1], [2, 2], [3, 3], [4, 4], [5, 5]], np.int32))
+    vids = [v1, v2, v3]
+    scores = rng.random(sum(v.T for v in vids)).astype(np.float32)
+    scores[0] = np.nan
+    scores[3] = 7.0      # out-of-range scores are clamped by the quantiser
+    scores[4] = -1.0
+    _summarize_and_compare(native, vids, scores, "cuda")
+    # invalid change points are rejected, not mis-computed
+    bad = synth.Video(torch.zeros(2, 1), torch.zeros(2, 1), 10, np.array([0, 5], np.int32), np.array([[0, 6], [5, 9]], np.int32))
+    with pytest.raises(ValueError):
+        native.summarize_rows(torch.zeros(2, device="cuda"), torch.tensor([0, 5], dtype=torch.int32, device="cuda"),
+                              [0], [2], [10], [bad.cps], 0.15)
+
+
+def test_summarize_long_video_uses_global_dp_rows(native):
+    """T = 8192 (BASELINE configs[3]): capacity 18,432 exceeds the shared-memory DP rows."""
+    vids = [synth.make_video(8192, 4, 4, 9000), synth.make_video(300, 4, 4, 9001)]
+    scores = np.random.default_rng(2).random(sum(v.T for v in vids)).astype(np.float32)
+    picks = _summarize_and_compare(native, vids, scores, "cuda")
+    assert picks.sum() > 0
+
+
+def test_generate_summary_single_video_api(cuda_ready):
+    from avsum_b200.evaluation.summary import generate_summary
+    m = make_model()
+    v = synth.config2()[3]
+    sc = np.random.default_rng(1).random(v.T).astype(np.float32)
+    got = generate_summary(m, sc, v.cps, v.n_frames, v.positions, 0.15)
+    assert np.array_equal(got, av_oracle.generate_summary(sc, v.cps, v.n_frames, v.positions)[1])
+
+
+def test_end_to_end_keyshots_match_reference_scores(cuda_ready):
+    """Identical keyshot summaries to the reference pipeline: reference scores (CPU port) ->
+    oracle summary  vs  GPU scores -> GPU summary, on the spread weight set."""
+    from avsum_b200.evaluation.summary import summarize_videos
+    vids = synth.config2()[:12]
+    sd = synth.seeded_state_dict(spread=True)
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
+    port.load_state_dict(sd)
+    ref_scores = av_oracle_torch.run_videos(port, [(v.visual, v.audio) for v in vids])
+    m = make_model(spread=True)
+    res = summarize_videos(m, vids)
+    same = 0
+    for v, r, rs in zip(vids, res, ref_scores):
+        # on identical inputs (the GPU's own scores) the selection is bit-exact ...
+        wp, ws, _ = av_oracle.generate_summary(r.scores.numpy(), v.cps, v.n_frames, v.positions)
+        assert np.array_equal(wp, r.picks) and np.array_equal(ws, r.summary)
+        # ... and it agrees with the selection made from the reference's fp32 scores
+        same += int(np.array_equal(av_oracle.generate_summary(rs.numpy(), v.cps, v.n_frames, v.positions)[0], r.picks))
+    assert same == len(vids)
+
+
+# ------------------------------------------------------------------ overlap F1 (bit-exact doubles)
+def test_temporal_f1_bit_exact(cuda_ready, golden_dir):
+    from avsum_b200.evaluation.metrics import compute_temporal_f1, compute_temporal_f1_batch
+    from avsum_b200.utils.shot_metrics import compute_f1
+    g = np.load(os.path.join(golden_dir, "helpers.npz"))
+    pred = [tuple(int(x) for x in p) for p in g["pred"]]
+    gt = [tuple(int(x) for x in p) for p in g["gt"]]
+    assert compute_temporal_f1(pred, gt, 1000) == float(g["f1_metrics"])
+    assert compute_f1(pred, gt, 1000) == float(g["f1_shot"])
+    rng = np.random.default_rng(3)
+    preds, gts = [], []
+    for _ in range(60):
+        def shots():
+            e = np.sort(rng.choice(5000, size=2 * int(rng.integers(1, 30)), replace=False))
+            return [(int(e[2 * i]), int(e[2 * i + 1])) for i in range(len(e) // 2)]
+        preds.append(shots())
+        gts.append(shots())
+    got = compute_temporal_f1_batch(preds, gts)
+    want = np.asarray([av_oracle.temporal_f1(p, q) for p, q in zip(preds, gts)])
+    assert np.array_equal(got, want)
+    with pytest.raises(ZeroDivisionError):
+        compute_temporal_f1([], gt, 1000)
+
+
+# ------------------------------------------------------------------ ragged / empty inputs
+def test_empty_and_zero_length_videos(native):
+    out = native.forward_rows(torch.zeros(0, 1024, device="cuda"), torch.zeros(0, 128, device="cuda"), [], [])
+    assert out.numel() == 0
+    v = torch.randn(10, 1024, device="cuda")
+    a = torch.randn(10, 128, device="cuda")
+    got = native.forward_rows(v, a, [0, 4, 4], [4, 0, 6], "temporal")
+    a1 = native.forward_rows(v[:4], a[:4], [0], [4], "temporal")
+    a2 = native.forward_rows(v[4:], a[4:], [0], [6], "temporal")
+    assert torch.equal(got[:4], a1) and torch.equal(got[4:], a2)
+    with pytest.raises(ValueError):
+        native.forward_rows(v, a, [0, 8], [4, 6], "temporal")      # rows outside the buffer

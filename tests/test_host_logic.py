@@ -1,0 +1,74 @@
+"""CPU tests of the host-side mirror of the reference interface (no compute)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from avsum_b200 import synth
+from avsum_b200.models.av_model import AVBiLSTMModel, AVModel, AVSummarizer
+from avsum_b200.models.attention import MultiHeadSelfAttention
+from avsum_b200.utils.alignments import align_shots_to_annotations
+from avsum_b200.utils.shot_metrics import calculate_overlap
+
+# the 28 state_dict keys of the reference (measured on the imported class)
+REFERENCE_KEYS = (
+    ["visual_fc.0.weight", "visual_fc.0.bias", "audio_fc.0.weight", "audio_fc.0.bias"]
+    + [f"{m}.{p}{s}" for m in ("visual_bilstm", "audio_bilstm") for s in ("", "_reverse")
+       for p in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")]
+    + ["attention.in_proj_weight", "attention.in_proj_bias", "attention.out_proj.weight", "attention.out_proj.bias",
+       "scorer.0.weight", "scorer.0.bias", "scorer.2.weight", "scorer.2.bias"])
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    m = AVBiLSTMModel()
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == sorted(REFERENCE_KEYS) and len(sd) == 28
+    assert sd["visual_fc.0.weight"].shape == (512, 4096) and sd["audio_fc.0.weight"].shape == (512, 296)
+    assert sd["visual_bilstm.weight_ih_l0"].shape == (1024, 512) and sd["audio_bilstm.weight_hh_l0_reverse"].shape == (1024, 256)
+    assert sd["attention.in_proj_weight"].shape == (3072, 1024) and sd["scorer.2.weight"].shape == (1, 64)
+    assert sum(p.numel() for p in m.parameters()) == 9_667_713
+    assert sum(p.numel() for p in AVBiLSTMModel(1024, 128, 512).parameters()) == 8_008_833
+    assert AVModel is AVBiLSTMModel and AVSummarizer is AVBiLSTMModel
+
+
+def test_seeded_construction_reproduces_reference_weights(golden_dir):
+    g = np.load(os.path.join(golden_dir, "config1_spread0.npz"))
+    torch.manual_seed(0)
+    m = AVBiLSTMModel(1024, 128, 512)
+    assert abs(synth.state_dict_checksum(m.state_dict()) - float(g["weights_checksum"])) < 1e-6
+
+
+def test_mhsa_surface():
+    a = MultiHeadSelfAttention(1024, 4)
+    assert sorted(a.state_dict().keys()) == sorted(f"{n}.{p}" for n in ("query", "key", "value", "out") for p in ("weight", "bias"))
+    assert a.num_heads == 4 and a.dim_head == 256
+
+
+def test_training_mode_is_refused():
+    m = AVBiLSTMModel(1024, 128, 512).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 2, 1024), torch.zeros(1, 2, 128))
+
+
+def test_synthetic_workloads_are_deterministic():
+    vids = synth.config2()
+    assert len(vids) == 50 and sum(v.T for v in vids) == 21_477
+    assert all(200 <= v.T <= 700 for v in vids)
+    v0 = synth.config2()[0]
+    assert torch.equal(v0.visual, vids[0].visual) and np.array_equal(v0.cps, vids[0].cps)
+    for v in vids[:5]:
+        assert v.cps[0, 0] == 0 and v.cps[-1, 1] == v.n_frames - 1
+        assert np.all(v.cps[1:, 0] == v.cps[:-1, 1] + 1)
+    c1 = synth.config1()
+    assert c1.visual.shape == (320, 1024) and c1.audio.shape == (320, 128)
+
+
+def test_alignment_and_overlap_helpers(golden_dir):
+    g = np.load(os.path.join(golden_dir, "helpers.npz"))
+    shots = [tuple(int(x) for x in s) for s in g["shots"]]
+    got = align_shots_to_annotations(shots, g["ann"], 30.0)
+    assert got.dtype == torch.float64 and np.array_equal(got.numpy(), g["aligned"])
+    pred = [tuple(int(x) for x in p) for p in g["pred"]]
+    gt = [tuple(int(x) for x in p) for p in g["gt"]]
+    assert calculate_overlap(pred, gt) == int(g["overlap"])

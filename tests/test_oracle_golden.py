@@ -1,0 +1,135 @@
+"""CPU tests: the oracle against the golden vectors produced by the imported reference
+(tools/make_golden.py), plus property tests of the repo-specified summary oracle."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from avsum_b200 import synth
+from oracle import av_oracle, av_oracle_torch
+
+TOL = 2e-5  # numpy fp32 restatement vs torch fp32 reference (different summation order)
+
+
+def _np_sd(sd):
+    return {k: v.numpy() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("spread", [0, 1])
+@pytest.mark.parametrize("axis", ["literal", "temporal"])
+def test_config1_oracle_matches_reference(golden_dir, spread, axis):
+    g = np.load(os.path.join(golden_dir, f"config1_spread{spread}.npz"))
+    sd = synth.seeded_state_dict(spread=bool(spread))
+    assert abs(synth.state_dict_checksum(sd) - float(g["weights_checksum"])) < 1e-6
+    vid = synth.config1()
+    got = av_oracle.forward(_np_sd(sd), vid.visual[None].numpy(), vid.audio[None].numpy(), 4, axis)
+    assert got.shape == g["scores_" + axis].shape == (320,)
+    assert np.max(np.abs(got - g["scores_" + axis])) < TOL
+
+
+@pytest.mark.parametrize("name", ["batch3_T17", "batch2_T1", "batch1_T1", "default_dims_T40", "batch2_T130_spread"])
+@pytest.mark.parametrize("axis", ["literal", "temporal"])
+def test_model_cases_oracle_matches_reference(golden_dir, name, axis):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    vd, ad, B, T = int(g["visual_dim"]), int(g["audio_dim"]), int(g["B"]), int(g["T"])
+    sd = synth.seeded_state_dict(vd, ad, 512, 0, bool(int(g["spread"])))
+    assert abs(synth.state_dict_checksum(sd) - float(g["weights_checksum"])) < 1e-6 * max(1.0, float(g["weights_checksum"]))
+    gen = torch.Generator().manual_seed(int(g["seed_in"]))
+    visual = torch.randn(B, T, vd, generator=gen)
+    audio = torch.randn(B, T, ad, generator=gen)
+    want = g["scores_" + axis]
+    got = av_oracle.forward(_np_sd(sd), visual.numpy(), audio.numpy(), 4, axis)
+    assert got.shape == want.shape  # the reference's .squeeze() removes every unit dim (av_model.py:46)
+    assert np.max(np.abs(got - want)) < TOL
+    # the torch restatement used as CPU timing baseline is bit-exact
+    port = av_oracle_torch.RefPortModel(vd, ad, 512).eval()
+    port.load_state_dict(sd)
+    with torch.no_grad():
+        assert np.array_equal(port(visual, audio, axis).numpy(), want)
+
+
+def test_literal_axis_mixes_videos_but_b1_does_not(golden_dir):
+    """with B>1 the literal forward differs from the same video run alone."""
+    g = np.load(os.path.join(golden_dir, "batch3_T17.npz"))
+    sd = _np_sd(synth.seeded_state_dict())
+    gen = torch.Generator().manual_seed(int(g["seed_in"]))
+    visual = torch.randn(3, 17, 1024, generator=gen).numpy()
+    audio = torch.randn(3, 17, 128, generator=gen).numpy()
+    alone = av_oracle.forward(sd, visual[:1], audio[:1], 4, "literal")
+    assert np.max(np.abs(alone - g["scores_literal"][0])) > 1e-5
+    masked = av_oracle.forward(sd, visual, audio, 4, "temporal", lengths=[17, 9, 1])
+    assert np.max(np.abs(masked[0] - g["scores_temporal"][0])) < TOL
+    assert masked[1].shape == (9,) and masked[2].shape == (1,)
+
+
+def test_mhsa_oracle_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mhsa_E1024_H4.npz"))
+    torch.manual_seed(int(g["seed_w"]))
+    import torch.nn as nn
+    mods = nn.ModuleDict(dict(query=nn.Linear(1024, 1024), key=nn.Linear(1024, 1024), value=nn.Linear(1024, 1024),
+                              out=nn.Linear(1024, 1024)))
+    assert abs(synth.state_dict_checksum(mods.state_dict()) - float(g["weights_checksum"])) < 1e-6
+    x = torch.randn(2, 33, 1024, generator=torch.Generator().manual_seed(int(g["seed_in"])))
+    got = av_oracle.mhsa_forward(_np_sd(mods.state_dict()), x.numpy(), 4)
+    assert np.max(np.abs(got[:, :, ::8] - g["out"])) < TOL
+
+
+def test_helper_oracles_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "helpers.npz"))
+    pred = [tuple(int(x) for x in p) for p in g["pred"]]
+    gt = [tuple(int(x) for x in p) for p in g["gt"]]
+    assert av_oracle.temporal_f1(pred, gt) == float(g["f1_metrics"]) == float(g["f1_shot"])
+    shots = [tuple(int(x) for x in s) for s in g["shots"]]
+    assert np.array_equal(av_oracle.align_shots_to_annotations(shots, g["ann"], 30.0), g["aligned"])
+
+
+# ---------------------------------------------------------------- summary oracle (repo-specified)
+
+def test_quantize_scores_edges():
+    q = av_oracle.quantize_scores(np.array([0.0, 1.0, 0.5, -0.1, 1.5, np.nan, np.inf, 2.0 ** -25, 3 * 2.0 ** -25], np.float32))
+    assert q.tolist() == [0, 1 << 24, 1 << 23, 0, 1 << 24, 0, 1 << 24, 0, 2]  # half-to-even
+
+
+def test_knapsack_is_optimal_and_within_budget():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        S = int(rng.integers(1, 10))
+        w, v = rng.integers(1, 20, S), rng.integers(0, 50, S)
+        cap = int(rng.integers(0, 60))
+        picks = av_oracle.knapsack(v, w, cap)
+        best = max(sum(v[i] for i in c) for r in range(S + 1) for c in itertools.combinations(range(S), r)
+                   if sum(w[i] for i in c) <= cap)
+        assert picks @ w <= cap and picks @ v == best
+
+
+def test_shot_pool_equals_naive_upsampling():
+    rng = np.random.default_rng(1)
+    for trial in range(30):
+        T, stride = int(rng.integers(1, 40)), int(rng.integers(1, 20))
+        n_frames = T * stride + int(rng.integers(0, 5))
+        pos = np.arange(T) * stride
+        sc = rng.random(T).astype(np.float32)
+        cps = synth.make_change_points(n_frames, trial, 3, 40)
+        seg_sum, nfps, seg_mean = av_oracle.shot_pool(sc, pos, n_frames, cps)
+        up = np.zeros(n_frames, np.int64)
+        edges = list(pos) + [n_frames]
+        q = av_oracle.quantize_scores(sc)
+        for i in range(T):
+            up[edges[i]:edges[i + 1]] = q[i]
+        for s, (a, b) in enumerate(cps):
+            assert seg_sum[s] == up[a:b + 1].sum() and nfps[s] == b - a + 1
+            assert seg_mean[s] == (2 * seg_sum[s] + nfps[s]) // (2 * nfps[s])
+
+
+def test_generate_summary_budget_and_bitmap():
+    for v in synth.config2()[:6]:
+        sc = np.random.default_rng(v.T).random(v.T).astype(np.float32)
+        picks, summary, _ = av_oracle.generate_summary(sc, v.cps, v.n_frames, v.positions)
+        nf = v.cps[:, 1] - v.cps[:, 0] + 1
+        assert summary.sum() == (picks * nf).sum() <= (v.n_frames * 15) // 100
+        assert summary.shape == (v.n_frames,)
+    # degenerate inputs
+    picks, summary, _ = av_oracle.generate_summary(np.zeros(0, np.float32), np.zeros((0, 2), np.int32), 0, np.zeros(0, np.int32))
+    assert picks.size == 0 and summary.size == 0

@@ -1,0 +1,55 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: LPT sharding + result gather.  The compute
+itself needs a GPU, so each rank produces deterministic stand-in picks; what is tested is that
+every video is processed exactly once and the gathered summaries are identical on all ranks and
+equal to the single-process result."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import avsum_b200  # noqa: F401
+from avsum_b200 import sharding, synth
+
+
+def _fake_picks(i, S):
+    return (np.random.default_rng(i).random(S) < 0.3).astype(np.uint8)
+
+
+def _worker(rank, world, port, lengths, n_segs, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shards = sharding.shard_videos(lengths, world)
+    mine = shards[rank]
+    picks = [_fake_picks(i, n_segs[i]) for i in mine]
+    full = sharding.gather_picks(mine, picks, len(lengths))
+    ret[rank] = [p.tolist() for p in full]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_videos_is_a_balanced_partition():
+    lengths = [v.T for v in synth.config2()]
+    for world in (1, 2, 4, 8):
+        shards = sharding.shard_videos(lengths, world)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(len(lengths)))
+        loads = [sum(sharding.video_cost(lengths[i]) for i in s) for s in shards]
+        assert max(loads) <= 1.15 * (sum(loads) / world)
+    assert sharding.shard_videos([], 4) == [[], [], [], []]
+    assert sharding.shard_videos([5], 2) == [[0], []]
+
+
+def test_two_rank_gather_equals_single_process():
+    vids = synth.config2()[:11]
+    lengths = [v.T for v in vids]
+    n_segs = [int(v.cps.shape[0]) for v in vids]
+    want = [_fake_picks(i, n_segs[i]).tolist() for i in range(len(vids))]
+    single = sharding.gather_picks(list(range(len(vids))), [np.asarray(w, np.uint8) for w in want], len(vids))
+    assert [p.tolist() for p in single] == want
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, lengths, n_segs, ret), nprocs=2, join=True)
+    assert ret[0] == want and ret[1] == want
