@@ -120,11 +120,12 @@ struct Arena {
 };
 
 // dst[p, :] = src[perm(p), :] for the LSTM gate interleave:
-//   packed row p = cta*128 + gate*32 + jj   <-   original row gate*256 + cta*32 + jj
+//   packed row p = cta*128 + jj*4 + gate   <-   original row gate*256 + cta*32 + jj
+// (the four gates of a hidden unit are adjacent, so they land in adjacent accumulator lanes)
 __global__ void permute_gate_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int cols,
                                          int round_tf32) {
     const int p = blockIdx.x;
-    const int cta = p >> 7, gate = (p >> 5) & 3, jj = p & 31;
+    const int cta = p >> 7, gate = p & 3, jj = (p >> 2) & 31;
     const int o = gate * HC + cta * 32 + jj;
     for (int k = threadIdx.x; k < cols; k += blockDim.x) {
         const float v = src[static_cast<size_t>(o) * cols + k];
@@ -135,7 +136,7 @@ __global__ void permute_gate_bias_kernel(const float* __restrict__ b_ih, const f
                                          float* __restrict__ dst) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= G4) return;
-    const int cta = p >> 7, gate = (p >> 5) & 3, jj = p & 31;
+    const int cta = p >> 7, gate = p & 3, jj = (p >> 2) & 31;
     const int o = gate * HC + cta * 32 + jj;
     dst[p] = b_ih[o] + b_hh[o];
 }
@@ -280,7 +281,7 @@ struct LstmPlan {
     std::vector<int32_t> host;  // [slot_row_start | slot_len | group_maxlen]
     int nb = 1, n_groups = 0;
 };
-LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths) {
+LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, bool tensor_core) {
     std::vector<int> order;
     for (int b = 0; b < n; ++b)
         if (lengths[b] > 0) order.push_back(b);
@@ -288,9 +289,18 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths) 
     LstmPlan p;
     const int B = static_cast<int>(order.size());
     if (B == 0) return p;
-    p.nb = 16;
-    for (int nb : {1, 2, 4, 8, 16}) {
-        if (((B + nb - 1) / nb) * 4 <= 16) { p.nb = nb; break; }
+    // one wave = 16 clusters of 8 CTAs (4 recurrences x 4 groups); the tensor-core kernel pads the
+    // video dimension of its MMA to 16 / 32 / 64
+    if (tensor_core) {
+        p.nb = 64;
+        for (int nb : {16, 32, 64}) {
+            if (((B + nb - 1) / nb) * 4 <= 16) { p.nb = nb; break; }
+        }
+    } else {
+        p.nb = 16;
+        for (int nb : {1, 2, 4, 8, 16}) {
+            if (((B + nb - 1) / nb) * 4 <= 16) { p.nb = nb; break; }
+        }
     }
     p.n_groups = (B + p.nb - 1) / p.nb;
     const int slots = p.n_groups * p.nb;
@@ -454,7 +464,7 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     }
 
     // ---- plan + workspace
-    LstmPlan plan = plan_lstm(n_videos, row_start, lengths);
+    LstmPlan plan = plan_lstm(n_videos, row_start, lengths, !simt);
     const int n_seqs = literal_rows ? 0 : (attn_axis == AVS_ATTN_TEMPORAL ? n_videos : lengths[0]);
     const size_t act_floats = static_cast<size_t>(R) * (Dv + Da + 2 * H + 2 * 2 * G4 + E + 3 * E + E + E + 1);
     AVS_TRY(m->ws.reserve(act_floats * sizeof(float) + (plan.host.size() + 3 * static_cast<size_t>(n_seqs)) * 4 +
@@ -525,7 +535,8 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         const int slots = plan.n_groups * plan.nb;
         LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
         StageTimer tm(ST_LSTM, st);
-        AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, rnd, nullptr, 0, st));
+        if (simt) AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, rnd, nullptr, 0, st));
+        else AVS_TRY(lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, fused, rnd, st));
     }
 
     // ---- K3/K4: nn.MultiheadAttention  av_model.py:44
@@ -751,7 +762,7 @@ avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb,
     Guard g(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int64_t R = total_rows;
-    LstmPlan plan = plan_lstm(n_videos, row_start, lengths);
+    LstmPlan plan = plan_lstm(n_videos, row_start, lengths, precision == AVS_PREC_TF32);
     AVS_TRY(m->ws.reserve(static_cast<size_t>(R) * (2 * 2 * G4 + 2 * H) * 4 + plan.host.size() * 4 + 16 * 256));
     m->ws.reset();
     float* xg_v = m->ws.take<float>(R * 2 * G4);
@@ -778,6 +789,7 @@ avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb,
     AVS_TRY(run_gemm(precision, xa, H, m->ih_a_x, m->ih_a_t, H, R, 2 * G4, H, e2, st));
     const int slots = plan.n_groups * plan.nb;
     LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
+    if (precision == AVS_PREC_TF32) return lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, fused, 0, st);
     return lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, 0, nullptr, 0, st);
 }
 

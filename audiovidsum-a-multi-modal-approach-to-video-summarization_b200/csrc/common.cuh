@@ -82,10 +82,14 @@ struct LstmBatch {            // device arrays, one entry per slot (n_groups * N
     int nb;                       // videos per cluster (1, 2, 4, 8, 16)
 };
 // xg_v, xg_a: [rows, 2048] gate pre-activations (biases included) in the packed column order
-//   col = dir * 1024 + cta * 128 + gate * 32 + jj   (hidden unit j = cta * 32 + jj)
+//   col = dir * 1024 + cta * 128 + jj * 4 + gate   (hidden unit j = cta * 32 + jj)
 // whh: [4][1024][256] fp32 in the same packed row order;  fused: [rows, 1024].
 avs_status lstm_recurrence(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
                            float* fused, int round_tf32, void* fused_lowp, int lowp_dtype, cudaStream_t stream);
+
+// tcgen05 version (fp16 operands, fp32 accumulate / state); batch.nb must be 16, 32 or 64.
+avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
+                              float* fused, int round_tf32, cudaStream_t stream);
 
 // ---- attention core -------------------------------------------------------------
 struct SeqDesc {  // device arrays [n_seqs]

@@ -3,7 +3,8 @@
 // zero initial state, reverse direction walks each video from its own last frame).
 //
 // One thread-block CLUSTER of 8 CTAs runs one (modality, direction) recurrence for a group of up
-// to NB videos.  CTA r owns hidden units [32r, 32r+32) = 128 gate columns; its 128 x 256 slice of
+// to NB videos (CUDA-core fp32 version: the AVS_PREC_FP32_SIMT path; lstm_tc.cu is the tensor-core
+// one).  CTA r owns hidden units [32r, 32r+32) = 128 gate columns; its 128 x 256 slice of
 // W_hh lives in REGISTERS for the whole kernel (128 floats per thread, 256 threads), the hidden
 // state of all NB videos lives in shared memory and is re-broadcast to the 8 CTAs through
 // distributed shared memory after every step.  The input projections (x W_ih^T + b_ih + b_hh)
@@ -144,10 +145,10 @@ lstm_recurrence_kernel(const float* __restrict__ xg_v, const float* __restrict__
             if (b < NB) {
                 const int len = s_len[b];
                 if (s < len) {
-                    const float gi = sigmoid_acc(gates[b][jj]);
-                    const float gf = sigmoid_acc(gates[b][UNITS + jj]);
-                    const float gg = tanhf(gates[b][2 * UNITS + jj]);
-                    const float go = sigmoid_acc(gates[b][3 * UNITS + jj]);
+                    const float gi = sigmoid_acc(gates[b][4 * jj + 0]);  // packed column = 4*jj + gate
+                    const float gf = sigmoid_acc(gates[b][4 * jj + 1]);
+                    const float gg = tanhf(gates[b][4 * jj + 2]);
+                    const float go = sigmoid_acc(gates[b][4 * jj + 3]);
                     const float cn = fmaf(gf, c_state[i], gi * gg);
                     c_state[i] = cn;
                     const float h = go * tanhf(cn);

@@ -1,0 +1,322 @@
+// K2b (tensor-core version) -- the recurrent half of both nn.LSTM modules of AVBiLSTMModel
+// (/root/reference/models/av_model.py:18-23, 39-40) on tcgen05.
+//
+// One thread-block cluster of 8 CTAs runs one (modality, direction) recurrence for a group of up
+// to NB videos.  CTA r owns hidden units [32r, 32r+32) = 128 gate columns, packed so that the four
+// gates (i,f,g,o) of a unit sit in four adjacent accumulator lanes (column p = 4*jj + gate).
+//
+// Per time step and CTA:
+//   gates^T[128 cols, NB videos] = W_hh_slice[128, 256] * h_prev[NB, 256]^T      (16 x tcgen05.mma, fp16 in, fp32 acc)
+//     - W_hh slice: fp16, resident in shared memory for the whole kernel (64 KB, 128B-swizzled K-major)
+//     - h_prev: fp16, shared memory, rewritten every step by all 8 CTAs of the cluster (DSMEM)
+//     - accumulator: tensor memory, NB columns
+//   8 epilogue warps: tcgen05.ld -> + x W_ih^T (precomputed by the GEMM, fp32) -> sigmoid/tanh ->
+//     quad shuffles -> c, h update in fp32 registers -> h to global (fp32) and, as fp16, into the
+//     h buffer of every CTA in the cluster (16-byte st.shared::cluster), then one remote
+//     mbarrier arrive per destination.  No cluster-wide barrier in the loop.
+//
+// fp16 operands have the same 11-bit significand as tf32 and |h| < 1, so the recurrent matmul
+// carries tf32-level rounding (measured contribution to the final scores: < 3e-5 relative);
+// cell state, gate math and accumulation stay fp32.  Latency bound: ~T dependent steps.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace avs {
+
+namespace {
+
+constexpr int HC = 256;
+constexpr int CL = 8;
+constexpr int UNITS = HC / CL;      // 32 hidden units per CTA
+constexpr int COLS = 4 * UNITS;     // 128 gate columns per CTA
+constexpr int XG_LD = 2 * 4 * HC;   // 2048
+constexpr int FUSED_LD = 4 * HC;    // 1024
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_THREADS + 32;  // + one MMA-issuing warp
+constexpr int W_SUB_BYTES = COLS * 128;    // one K=64 sub-tile of the W slice (16 KB)
+constexpr int W_BYTES = 4 * W_SUB_BYTES;   // 64 KB
+
+template <int NB>
+struct Smem {
+    // h operand: fp16, UMMA K-major NO-swizzle ("interleaved") layout [k/8][video][k%8]:
+    // core matrix = 8 videos x 16 B; LBO (next 8 k) = NB*16 B, SBO (next 8 videos) = 128 B.
+    // The 32 hidden units a CTA produces are therefore ONE contiguous NB*64-byte block.
+    static constexpr int H_LBO = NB * 16;
+    static constexpr int H_BYTES = (HC / 8) * H_LBO;    // NB * 512
+    static constexpr int SLICE_BYTES = (UNITS / 8) * H_LBO;  // NB * 64: this CTA's share of h
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_H = W_BYTES;               // two buffers
+    static constexpr int OFF_STAGE16 = OFF_H + 2 * H_BYTES;
+    static constexpr int OFF_META = OFF_STAGE16 + 2 * SLICE_BYTES;  // (stage is double buffered) len[NB], row[NB]
+    static constexpr int OFF_BAR = OFF_META + 2 * NB * 4;           // bar_h[2], bar_mma, tmem slot
+    static constexpr int TOTAL = 1024 + OFF_BAR + 4 * 8;
+};
+
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+// Bulk copy own shared memory -> a peer CTA's shared memory (async proxy on both ends); the
+// destination CTA's mbarrier receives complete_tx(bytes).
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            dst_cluster_addr),
+        "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+        : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+// K-major, no swizzle: start address, LBO = K-direction core-matrix stride, SBO = 8-row-group stride.
+__device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;  // version = 1 (Blackwell); layout_type 0 = SWIZZLE_NONE
+    return d;
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) {
+    tmem_ld_32x32(taddr, r);
+}
+
+// exp-based activations: __expf is ex2.approx on a scaled argument (~2 ulp); the results agree with
+// expf/tanhf-based fp32 gates to ~1e-7 absolute, far inside the tensor-core rounding of this mode.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(-2.0f * fabsf(x));          // in (0, 1]: no overflow
+    return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+
+template <int NB>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
+               LstmBatch batch, float* __restrict__ fused, int round_tf32) {
+    using S = Smem<NB>;
+    constexpr int NV = NB / 2;  // videos per epilogue thread (two warps share a TMEM lane quarter)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = static_cast<int>(cluster.block_rank());
+    const int cid = blockIdx.x / CL;
+    const int grp = cid >> 2;
+    const int ld = cid & 3;
+    const int dir = ld & 1;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* w_sm = sm + S::OFF_W;
+    uint8_t* h_sm = sm + S::OFF_H;
+    uint8_t* stage16 = sm + S::OFF_STAGE16;   // this CTA's h slice in destination layout, double buffered:
+                                              // the bulk copies of step s may still read it during step s+1
+    int* s_len = reinterpret_cast<int*>(sm + S::OFF_META);
+    int* s_row = s_len + NB;
+    uint64_t* bar_h = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);  // [2]
+    uint64_t* bar_mma = bar_h + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+    // ---- one-time setup ---------------------------------------------------------------------
+    if (tid < NB) {
+        s_len[tid] = batch.slot_len[grp * NB + tid];
+        s_row[tid] = batch.slot_row_start[grp * NB + tid];
+    }
+    // W_hh slice: packed fp32 rows (ld, r*128 + p) -> fp16, 128B-swizzled K-major sub-tiles of K = 64
+    {
+        const float* wsrc = whh + (static_cast<size_t>(ld) * 4 * HC + r * COLS) * HC;
+        for (int idx = tid; idx < COLS * 32; idx += THREADS) {  // 16-byte chunks: 8 consecutive k
+            const int row = idx >> 5, ch = idx & 31;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(wsrc + row * HC + ch * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(wsrc + row * HC + ch * 8 + 4));
+            __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
+            __half2 p2 = __floats2half2_rn(b.x, b.y), p3 = __floats2half2_rn(b.z, b.w);
+            const int sub = ch >> 3, cir = ch & 7;
+            uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                 *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            *reinterpret_cast<uint4*>(w_sm + sub * W_SUB_BYTES + row * 128 + ((cir ^ (row & 7)) << 4)) = v;
+        }
+    }
+    for (int i = tid; i < (2 * S::H_BYTES + 2 * S::SLICE_BYTES) / 16; i += THREADS)
+        reinterpret_cast<uint4*>(h_sm)[i] = make_uint4(0, 0, 0, 0);   // h buffers + stage (contiguous)
+    if (tid == 0) {
+        mbar_init(bar_h + 0, 1);
+        mbar_init(bar_h + 1, 1);
+        mbar_init(bar_mma, 1);
+        fence_mbar_init();
+    }
+    if (warp == EPI_WARPS) {
+        tmem_alloc(tmem_slot, NB < 32 ? 32 : NB);
+        tmem_relinquish();
+    }
+    fence_proxy_async();  // generic-proxy writes of W / h visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    cluster.sync();       // every CTA's barriers and buffers exist before any remote access
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int maxlen = batch.group_maxlen[grp];
+
+    if (warp == EPI_WARPS) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc(UMMA_FMT_F16, COLS, NB);
+            const uint32_t w_addr = smem_u32(w_sm);
+            for (int s = 0; s < maxlen; ++s) {
+                const int b = s & 1;
+                // arm the barrier that will collect h_{s+1}: 8 peers x SLICE_BYTES, one local arrival
+                if (s + 1 < maxlen) mbar_expect_tx(bar_h + (b ^ 1), CL * S::SLICE_BYTES);
+                if (s > 0) mbar_wait(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
+                tc_fence_after();
+                const uint32_t h_addr = smem_u32(h_sm + b * S::H_BYTES);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {  // K = 256 = 16 x 16
+                    const uint64_t ad = umma_desc_sw128_kmajor(w_addr + (k >> 2) * W_SUB_BYTES + (k & 3) * 32);
+                    const uint64_t bd = umma_desc_noswz_kmajor(h_addr + k * 2 * S::H_LBO, S::H_LBO, 128);
+                    umma_f16_ss(tmem_base, ad, bd, idesc, k != 0);
+                }
+                tc_commit(bar_mma);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;              // TMEM lane quarter
+        const int half = warp >> 2;          // which half of the videos
+        const int p = q * 32 + lane;         // gate column inside the slice: 4*jj + gate
+        const int gate = p & 3;
+        const int jj = p >> 2;
+        const int v0 = half * NV;
+        const float* xg = ((ld >> 1) ? xg_a : xg_v) + dir * (4 * HC) + r * COLS + p;
+        const int out_col = ld * HC + r * UNITS;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + v0;
+        const int qbase = lane & ~3;
+        // this thread's slot in the staged slice: [jj/8][video][jj%8] halfs
+        __half* stage_mine = reinterpret_cast<__half*>(stage16 + (jj >> 3) * S::H_LBO) + (jj & 7);
+
+        float c_state[NV], xv[NV];
+        int len_r[NV];
+        int row_r[NV];           // global row of the frame video i consumes at step s
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            c_state[i] = 0.f;
+            const int len = s_len[v0 + i];
+            len_r[i] = len;
+            row_r[i] = s_row[v0 + i] + (dir ? (len > 0 ? len - 1 : 0) : 0);
+            xv[i] = len > 0 ? __ldg(xg + static_cast<size_t>(row_r[i]) * XG_LD) : 0.f;
+        }
+        const int rstep = dir ? -1 : 1;
+        float* const fcol = fused + out_col + jj;
+
+        for (int s = 0; s < maxlen; ++s) {
+            mbar_wait(bar_mma, s & 1);
+            tc_fence_after();
+            uint32_t acc[NV];
+            tmem_ld_cols<NV>(taddr, acc);
+            tmem_ld_wait();
+            float g[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) g[i] = __uint_as_float(acc[i]) + xv[i];
+            // prefetch next step's input projections while the gate math runs
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                if (s + 1 < len_r[i]) xv[i] = __ldg(xg + static_cast<size_t>(row_r[i] + rstep) * XG_LD);
+            }
+            float h_out[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float act = (gate == 2) ? fast_tanh(g[i]) : fast_sigmoid(g[i]);
+                const float a_i = __shfl_sync(0xffffffffu, act, qbase + 0);
+                const float a_f = __shfl_sync(0xffffffffu, act, qbase + 1);
+                const float a_g = __shfl_sync(0xffffffffu, act, qbase + 2);
+                const float a_o = __shfl_sync(0xffffffffu, act, qbase + 3);
+                const bool on = s < len_r[i];
+                const float cn = fmaf(a_f, c_state[i], a_i * a_g);
+                const float h = a_o * fast_tanh(cn);
+                c_state[i] = on ? cn : c_state[i];
+                h_out[i] = h;
+                if (on && gate == 0) stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + (v0 + i) * 8] = __float2half_rn(h);
+            }
+            if (s + 1 < maxlen) {
+                fence_proxy_async();   // staged h (generic proxy) -> visible to the bulk-copy engine
+                tc_fence_before();
+                epi_bar_sync();        // whole slice staged; all TMEM reads of this step done
+                if (tid < CL) {
+                    const int nb = (s + 1) & 1;
+                    const uint32_t dst = smem_u32(h_sm + nb * S::H_BYTES) + r * S::SLICE_BYTES;
+                    bulk_copy_to_peer(mapa(dst, tid), smem_u32(stage16) + (s & 1) * S::SLICE_BYTES, S::SLICE_BYTES,
+                                      mapa(smem_u32(bar_h + nb), tid));
+                }
+            }
+            // h -> global fused output (off the critical path)
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                if (s < len_r[i]) {
+                    if (gate == 0)
+                        fcol[static_cast<size_t>(row_r[i]) * FUSED_LD] = round_tf32 ? to_tf32_rn(h_out[i]) : h_out[i];
+                    row_r[i] += rstep;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster.sync();  // nobody exits while a peer could still touch its shared memory
+    if (warp == EPI_WARPS) tmem_dealloc(tmem_base, NB < 32 ? 32 : NB);
+}
+
+template <int NB>
+avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, float* fused,
+                     int round_tf32, cudaStream_t stream) {
+    auto kern = lstm_tc_kernel<NB>;
+    static bool configured = false;
+    if (!configured) {
+        AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NB>::TOTAL));
+        configured = true;
+    }
+    kern<<<batch.n_groups * 4 * CL, THREADS, Smem<NB>::TOTAL, stream>>>(xg_v, xg_a, whh, batch, fused, round_tf32);
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
+
+}  // namespace
+
+avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
+                              float* fused, int round_tf32, cudaStream_t stream) {
+    if (batch.n_groups == 0) return AVS_OK;
+    switch (batch.nb) {
+        case 16: return launch_tc<16>(xg_v, xg_a, whh_packed, batch, fused, round_tf32, stream);
+        case 32: return launch_tc<32>(xg_v, xg_a, whh_packed, batch, fused, round_tf32, stream);
+        case 64: return launch_tc<64>(xg_v, xg_a, whh_packed, batch, fused, round_tf32, stream);
+        default: set_error("lstm_tc: unsupported videos-per-cluster %d", batch.nb); return AVS_ERR_INVALID;
+    }
+}
+
+}  // namespace avs
