@@ -7,13 +7,15 @@
 //
 // Per time step and CTA:
 //   gates^T[128 cols, NB videos] = W_hh_slice[128, 256] * h_prev[NB, 256]^T      (16 x tcgen05.mma, fp16 in, fp32 acc)
-//     - W_hh slice: fp16, resident in shared memory for the whole kernel (64 KB, 128B-swizzled K-major)
-//     - h_prev: fp16, shared memory, rewritten every step by all 8 CTAs of the cluster (DSMEM)
+//     - W_hh slice: fp16, resident in TENSOR MEMORY for the whole kernel (A operand from TMEM:
+//       128 lanes x 128 columns), so a step never re-streams the 64 KB slice through shared memory
+//     - h_prev: fp16, shared memory (no-swizzle K-major), rewritten every step by all 8 CTAs
 //     - accumulator: tensor memory, NB columns
-//   8 epilogue warps: tcgen05.ld -> + x W_ih^T (precomputed by the GEMM, fp32) -> sigmoid/tanh ->
-//     quad shuffles -> c, h update in fp32 registers -> h to global (fp32) and, as fp16, into the
-//     h buffer of every CTA in the cluster (16-byte st.shared::cluster), then one remote
-//     mbarrier arrive per destination.  No cluster-wide barrier in the loop.
+//   16 epilogue warps: tcgen05.ld -> + x W_ih^T (precomputed by the GEMM, fp32) -> SFU sigmoid/tanh ->
+//     quad shuffles -> c, h update in fp32 registers -> h to global (fp32) and, as fp16, staged in the
+//     destination layout; 8 threads then push the CTA's contiguous NB*64-byte slice into every peer's
+//     next-step buffer with cp.async.bulk (DSMEM, async proxy) which complete_tx's the peer's
+//     mbarrier.  No cluster-wide barrier, no generic-proxy remote stores, no fences at cluster scope.
 //
 // fp16 operands have the same 11-bit significand as tf32 and |h| < 1, so the recurrent matmul
 // carries tf32-level rounding (measured contribution to the final scores: < 3e-5 relative);
@@ -35,11 +37,10 @@ constexpr int UNITS = HC / CL;      // 32 hidden units per CTA
 constexpr int COLS = 4 * UNITS;     // 128 gate columns per CTA
 constexpr int XG_LD = 2 * 4 * HC;   // 2048
 constexpr int FUSED_LD = 4 * HC;    // 1024
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;       // 4 warps per TMEM lane quarter, each owning NB/4 videos
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_THREADS + 32;  // + one MMA-issuing warp
-constexpr int W_SUB_BYTES = COLS * 128;    // one K=64 sub-tile of the W slice (16 KB)
-constexpr int W_BYTES = 4 * W_SUB_BYTES;   // 64 KB
+constexpr int W_TMEM_COLS = HC / 2;        // W_hh slice as packed fp16 pairs: 128 columns
 
 template <int NB>
 struct Smem {
@@ -47,14 +48,14 @@ struct Smem {
     // core matrix = 8 videos x 16 B; LBO (next 8 k) = NB*16 B, SBO (next 8 videos) = 128 B.
     // The 32 hidden units a CTA produces are therefore ONE contiguous NB*64-byte block.
     static constexpr int H_LBO = NB * 16;
-    static constexpr int H_BYTES = (HC / 8) * H_LBO;    // NB * 512
+    static constexpr int H_BYTES = (HC / 8) * H_LBO;         // NB * 512
     static constexpr int SLICE_BYTES = (UNITS / 8) * H_LBO;  // NB * 64: this CTA's share of h
-    static constexpr int OFF_W = 0;
-    static constexpr int OFF_H = W_BYTES;               // two buffers
-    static constexpr int OFF_STAGE16 = OFF_H + 2 * H_BYTES;
-    static constexpr int OFF_META = OFF_STAGE16 + 2 * SLICE_BYTES;  // (stage is double buffered) len[NB], row[NB]
+    static constexpr int OFF_H = 0;                           // two buffers
+    static constexpr int OFF_STAGE16 = OFF_H + 2 * H_BYTES;   // double buffered
+    static constexpr int OFF_META = OFF_STAGE16 + 2 * SLICE_BYTES;  // len[NB], row[NB]
     static constexpr int OFF_BAR = OFF_META + 2 * NB * 4;           // bar_h[2], bar_mma, tmem slot
     static constexpr int TOTAL = 1024 + OFF_BAR + 4 * 8;
+    static constexpr int TMEM_COLS = (W_TMEM_COLS + NB) <= 256 ? 256 : 512;
 };
 
 __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta_rank) {
@@ -87,6 +88,13 @@ __device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, u
 template <int N>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]);
 template <>
+__device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+template <>
 __device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -103,17 +111,26 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[1
         : "r"(taddr)
         : "memory");
 }
-template <>
-__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) {
-    tmem_ld_32x32(taddr, r);
-}
 
-// exp-based activations: __expf is ex2.approx on a scaled argument (~2 ulp); the results agree with
-// expf/tanhf-based fp32 gates to ~1e-7 absolute, far inside the tensor-core rounding of this mode.
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) {
-    const float e = __expf(-2.0f * fabsf(x));          // in (0, 1]: no overflow
-    return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+// Branch-free gate activation on the SFU: act = a * sigmoid(k * x) + b with per-lane constants
+// (i, f, o lanes: k=1, a=1, b=0 -> sigmoid;  g lane: k=2, a=2, b=-1 -> tanh(x) = 2*sigmoid(2x) - 1).
+// ex2.approx / rcp.approx are ~1-2 ulp; saturate correctly at +-inf.  Absolute error ~1e-7, far
+// inside the fp16/tf32 operand rounding of this mode.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gate_act(float x, float neg_k_log2e, float a, float b) {
+    return fmaf(a, rcp_approx(1.0f + ex2_approx(x * neg_k_log2e)), b);
+}
+__device__ __forceinline__ float tanh_sfu(float x) {
+    return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(x * -2.885390082f)), -1.0f);
 }
 
 template <int NB>
@@ -121,7 +138,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
                LstmBatch batch, float* __restrict__ fused, int round_tf32) {
     using S = Smem<NB>;
-    constexpr int NV = NB / 2;  // videos per epilogue thread (two warps share a TMEM lane quarter)
+    constexpr int NV = NB / 4;  // videos per epilogue thread (four warps share a TMEM lane quarter)
     cg::cluster_group cluster = cg::this_cluster();
     const int r = static_cast<int>(cluster.block_rank());
     const int cid = blockIdx.x / CL;
@@ -134,7 +151,6 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    uint8_t* w_sm = sm + S::OFF_W;
     uint8_t* h_sm = sm + S::OFF_H;
     uint8_t* stage16 = sm + S::OFF_STAGE16;   // this CTA's h slice in destination layout, double buffered:
                                               // the bulk copies of step s may still read it during step s+1
@@ -149,21 +165,6 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         s_len[tid] = batch.slot_len[grp * NB + tid];
         s_row[tid] = batch.slot_row_start[grp * NB + tid];
     }
-    // W_hh slice: packed fp32 rows (ld, r*128 + p) -> fp16, 128B-swizzled K-major sub-tiles of K = 64
-    {
-        const float* wsrc = whh + (static_cast<size_t>(ld) * 4 * HC + r * COLS) * HC;
-        for (int idx = tid; idx < COLS * 32; idx += THREADS) {  // 16-byte chunks: 8 consecutive k
-            const int row = idx >> 5, ch = idx & 31;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(wsrc + row * HC + ch * 8));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(wsrc + row * HC + ch * 8 + 4));
-            __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
-            __half2 p2 = __floats2half2_rn(b.x, b.y), p3 = __floats2half2_rn(b.z, b.w);
-            const int sub = ch >> 3, cir = ch & 7;
-            uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                 *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-            *reinterpret_cast<uint4*>(w_sm + sub * W_SUB_BYTES + row * 128 + ((cir ^ (row & 7)) << 4)) = v;
-        }
-    }
     for (int i = tid; i < (2 * S::H_BYTES + 2 * S::SLICE_BYTES) / 16; i += THREADS)
         reinterpret_cast<uint4*>(h_sm)[i] = make_uint4(0, 0, 0, 0);   // h buffers + stage (contiguous)
     if (tid == 0) {
@@ -173,22 +174,45 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         fence_mbar_init();
     }
     if (warp == EPI_WARPS) {
-        tmem_alloc(tmem_slot, NB < 32 ? 32 : NB);
+        tmem_alloc(tmem_slot, S::TMEM_COLS);
         tmem_relinquish();
     }
-    fence_proxy_async();  // generic-proxy writes of W / h visible to the tensor core (async proxy)
+    fence_proxy_async();  // zeroed h visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_w = tmem_base;                 // columns [0, 128): W_hh slice, fp16 pairs
+    const uint32_t tmem_d = tmem_base + W_TMEM_COLS;   // columns [128, 128 + NB): gate accumulator
+
+    if (warp < EPI_WARPS) {
+        // W_hh slice -> tensor memory, resident for the whole kernel.  A-operand layout of
+        // kind::f16 with M = 128: lane = row (gate column), 32-bit column c holds k = 2c, 2c+1.
+        const int q = warp & 3, part = warp >> 2;          // lane quarter, 32-column part of the row
+        const int row = q * 32 + lane;
+        const float4* src = reinterpret_cast<const float4*>(
+            whh + (static_cast<size_t>(ld) * 4 * HC + r * COLS + row) * HC + part * 64);
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 v = __ldg(src + i);
+            __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+            pk[2 * i] = *reinterpret_cast<uint32_t*>(&lo);
+            pk[2 * i + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        tmem_st_32x32(tmem_w + (static_cast<uint32_t>(q * 32) << 16) + part * 32, pk);
+        tmem_st_wait();
+    }
     tc_fence_before();
     __syncthreads();
     cluster.sync();       // every CTA's barriers and buffers exist before any remote access
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
     const int maxlen = batch.group_maxlen[grp];
 
     if (warp == EPI_WARPS) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (elect_one()) {
             const uint32_t idesc = umma_idesc(UMMA_FMT_F16, COLS, NB);
-            const uint32_t w_addr = smem_u32(w_sm);
             for (int s = 0; s < maxlen; ++s) {
                 const int b = s & 1;
                 // arm the barrier that will collect h_{s+1}: 8 peers x SLICE_BYTES, one local arrival
@@ -197,10 +221,9 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 tc_fence_after();
                 const uint32_t h_addr = smem_u32(h_sm + b * S::H_BYTES);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {  // K = 256 = 16 x 16
-                    const uint64_t ad = umma_desc_sw128_kmajor(w_addr + (k >> 2) * W_SUB_BYTES + (k & 3) * 32);
+                for (int k = 0; k < 16; ++k) {  // K = 256 = 16 x 16; A from TMEM (8 columns per K step)
                     const uint64_t bd = umma_desc_noswz_kmajor(h_addr + k * 2 * S::H_LBO, S::H_LBO, 128);
-                    umma_f16_ss(tmem_base, ad, bd, idesc, k != 0);
+                    umma_f16_ts(tmem_d, tmem_w + k * 8, bd, idesc, k != 0);
                 }
                 tc_commit(bar_mma);
             }
@@ -209,57 +232,59 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;              // TMEM lane quarter
-        const int half = warp >> 2;          // which half of the videos
+        const int part = warp >> 2;          // which quarter of the videos
         const int p = q * 32 + lane;         // gate column inside the slice: 4*jj + gate
         const int gate = p & 3;
         const int jj = p >> 2;
-        const int v0 = half * NV;
+        const int v0 = part * NV;
         const float* xg = ((ld >> 1) ? xg_a : xg_v) + dir * (4 * HC) + r * COLS + p;
         const int out_col = ld * HC + r * UNITS;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + v0;
+        const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + v0;
         const int qbase = lane & ~3;
+        const float act_k = (gate == 2) ? -2.885390082f : -1.442695041f;   // -k * log2(e)
+        const float act_a = (gate == 2) ? 2.0f : 1.0f;
+        const float act_b = (gate == 2) ? -1.0f : 0.0f;
         // this thread's slot in the staged slice: [jj/8][video][jj%8] halfs
         __half* stage_mine = reinterpret_cast<__half*>(stage16 + (jj >> 3) * S::H_LBO) + (jj & 7);
+        float* const fcol = fused + out_col + jj;
+        const int rstep = dir ? -1 : 1;
 
-        float c_state[NV], xv[NV];
-        int len_r[NV];
-        int row_r[NV];           // global row of the frame video i consumes at step s
+        float c_state[NV], xv0[NV], xv1[NV];   // xv0: this step's input projection, xv1: next step's
+        int len_r[NV], row_r[NV];              // row_r: global row of the frame consumed at step s
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             c_state[i] = 0.f;
             const int len = s_len[v0 + i];
             len_r[i] = len;
             row_r[i] = s_row[v0 + i] + (dir ? (len > 0 ? len - 1 : 0) : 0);
-            xv[i] = len > 0 ? __ldg(xg + static_cast<size_t>(row_r[i]) * XG_LD) : 0.f;
+            xv0[i] = len > 0 ? __ldg(xg + static_cast<size_t>(row_r[i]) * XG_LD) : 0.f;
+            xv1[i] = len > 1 ? __ldg(xg + static_cast<size_t>(row_r[i] + rstep) * XG_LD) : 0.f;
         }
-        const int rstep = dir ? -1 : 1;
-        float* const fcol = fused + out_col + jj;
 
         for (int s = 0; s < maxlen; ++s) {
+            // two-step-deep register prefetch of the input projections (DRAM latency >> one step)
+            float xv2[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                xv2[i] = 0.f;
+                if (s + 2 < len_r[i]) xv2[i] = __ldg(xg + static_cast<size_t>(row_r[i] + 2 * rstep) * XG_LD);
+            }
             mbar_wait(bar_mma, s & 1);
             tc_fence_after();
             uint32_t acc[NV];
             tmem_ld_cols<NV>(taddr, acc);
             tmem_ld_wait();
-            float g[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i) g[i] = __uint_as_float(acc[i]) + xv[i];
-            // prefetch next step's input projections while the gate math runs
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                if (s + 1 < len_r[i]) xv[i] = __ldg(xg + static_cast<size_t>(row_r[i] + rstep) * XG_LD);
-            }
             float h_out[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
-                const float act = (gate == 2) ? fast_tanh(g[i]) : fast_sigmoid(g[i]);
+                const float act = gate_act(__uint_as_float(acc[i]) + xv0[i], act_k, act_a, act_b);
                 const float a_i = __shfl_sync(0xffffffffu, act, qbase + 0);
                 const float a_f = __shfl_sync(0xffffffffu, act, qbase + 1);
                 const float a_g = __shfl_sync(0xffffffffu, act, qbase + 2);
                 const float a_o = __shfl_sync(0xffffffffu, act, qbase + 3);
                 const bool on = s < len_r[i];
                 const float cn = fmaf(a_f, c_state[i], a_i * a_g);
-                const float h = a_o * fast_tanh(cn);
+                const float h = a_o * tanh_sfu(cn);
                 c_state[i] = on ? cn : c_state[i];
                 h_out[i] = h;
                 if (on && gate == 0) stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + (v0 + i) * 8] = __float2half_rn(h);
@@ -275,21 +300,22 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                                       mapa(smem_u32(bar_h + nb), tid));
                 }
             }
-            // h -> global fused output (off the critical path)
+            // h -> global fused output (off the critical path), advance the per-video cursors
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
-                if (s < len_r[i]) {
-                    if (gate == 0)
-                        fcol[static_cast<size_t>(row_r[i]) * FUSED_LD] = round_tf32 ? to_tf32_rn(h_out[i]) : h_out[i];
-                    row_r[i] += rstep;
-                }
+                const bool on = s < len_r[i];
+                if (on && gate == 0)
+                    fcol[static_cast<size_t>(row_r[i]) * FUSED_LD] = round_tf32 ? to_tf32_rn(h_out[i]) : h_out[i];
+                row_r[i] += on ? rstep : 0;
+                xv0[i] = xv1[i];
+                xv1[i] = xv2[i];
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     cluster.sync();  // nobody exits while a peer could still touch its shared memory
-    if (warp == EPI_WARPS) tmem_dealloc(tmem_base, NB < 32 ? 32 : NB);
+    if (warp == EPI_WARPS) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
 template <int NB>
