@@ -534,6 +534,10 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     {
         const int slots = plan.n_groups * plan.nb;
         LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
+        int64_t covered = 0;
+        for (int b = 0; b < n_videos; ++b) covered += lengths[b];
+        if (covered < R)  // padded layout: rows no video owns must stay finite (0 * NaN would poison P*V)
+            AVS_CUDA(cudaMemsetAsync(fused, 0, static_cast<size_t>(R) * E * sizeof(float), st));
         StageTimer tm(ST_LSTM, st);
         if (simt) AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, rnd, nullptr, 0, st));
         else AVS_TRY(lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, fused, rnd, st));
@@ -552,10 +556,12 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         StageTimer tm(ST_QKV_PROJ, st);
         AVS_TRY(run_gemm(precision, fused, E, m->in_w_x + 2ull * E * E, m->in_w_t + 2ull * E * E, E, R, E, E, e3, st));
     } else {
+        const bool tc_attn = !simt && attn_axis == AVS_ATTN_TEMPORAL && E == m->heads * 256;
         GemmEpilogue e3;
         e3.bias = m->in_b;
         e3.C = qkv;
         e3.ldc = 3 * E;
+        if (tc_attn) e3.out_dtype = DT_F16;   // q | k | v straight to fp16 for the tcgen05 attention core
         {
             StageTimer tm(ST_QKV_PROJ, st);
             AVS_TRY(run_gemm(precision, fused, E, m->in_w_x, m->in_w_t, E, R, 3 * E, E, e3, st));
@@ -580,7 +586,8 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         AVS_CUDA(cudaMemcpyAsync(seq_dev, sd.data(), sd.size() * 4, cudaMemcpyHostToDevice, st));
         SeqDesc seqs{seq_dev, seq_dev + n_seqs, seq_dev + 2 * n_seqs, n_seqs, seq_max};
         StageTimer tm(ST_ATTENTION, st);
-        AVS_TRY(attention_simt(qkv, 3 * E, E, m->heads, seqs, ctx, E, rnd, st));
+        if (tc_attn) AVS_TRY(attention_tc(qkv, R, E, m->heads, seqs, ctx, E, rnd, st));
+        else AVS_TRY(attention_simt(qkv, 3 * E, E, m->heads, seqs, ctx, E, rnd, st));
     }
 
     // ---- K5: out_proj
@@ -798,7 +805,6 @@ avs_status avs_attention(const float* qkv, int64_t rows, int32_t E_, int32_t num
                          float* ctx, void* cuda_stream) {
     AVS_CHECK(qkv && ctx && (n_seqs == 0 || (seq_base && seq_stride && seq_len)), AVS_ERR_INVALID,
               "avs_attention: null pointer");
-    (void)precision;
     if (n_seqs == 0) return AVS_OK;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     std::vector<int32_t> sd(3 * static_cast<size_t>(n_seqs));
@@ -817,7 +823,18 @@ avs_status avs_attention(const float* qkv, int64_t rows, int32_t E_, int32_t num
     AVS_CUDA(cudaMallocAsync(&dev, sd.size() * 4, st));
     AVS_CUDA(cudaMemcpyAsync(dev, sd.data(), sd.size() * 4, cudaMemcpyHostToDevice, st));
     SeqDesc seqs{dev, dev + n_seqs, dev + 2 * n_seqs, n_seqs, mx};
-    avs_status s = attention_simt(qkv, 3ll * E_, E_, num_heads, seqs, ctx, E_, 0, st);
+    bool contiguous = true;
+    for (int i = 0; i < n_seqs; ++i) contiguous &= seq_stride[i] == 1;
+    avs_status s;
+    if (precision == AVS_PREC_TF32 && contiguous && E_ == num_heads * 256) {
+        void* qkv_h = nullptr;   // fp16 copy of q | k | v for the tcgen05 kernel
+        AVS_CUDA(cudaMallocAsync(&qkv_h, static_cast<size_t>(rows) * 3 * E_ * 2, st));
+        s = convert_f32(qkv, qkv_h, rows * 3 * E_, DT_F16, 0, st);
+        if (s == AVS_OK) s = attention_tc(qkv_h, rows, E_, num_heads, seqs, ctx, E_, 0, st);
+        cudaFreeAsync(qkv_h, st);
+    } else {
+        s = attention_simt(qkv, 3ll * E_, E_, num_heads, seqs, ctx, E_, 0, st);
+    }
     cudaFreeAsync(dev, st);
     return s;
 }

@@ -103,6 +103,10 @@ struct SeqDesc {  // device arrays [n_seqs]
 avs_status attention_simt(const float* qkv, int64_t ld_qkv, int E, int H, const SeqDesc& seqs, float* ctx,
                           int64_t ld_ctx, int round_tf32, cudaStream_t stream);
 
+// tcgen05 flash-style kernel: fp16 qkv [rows, 3E], contiguous sequences (stride 1), head dim 256.
+avs_status attention_tc(const void* qkv_h, int64_t rows, int E, int H, const SeqDesc& seqs, float* ctx, int64_t ld_ctx,
+                        int round_tf32, cudaStream_t stream);
+
 // ---- summary generation -----------------------------------------------------------
 struct SummaryBatch {   // device arrays, [n] unless noted
     const int32_t* row_start;
