@@ -157,8 +157,17 @@ struct avs_model {
     float* whh;                                // [4][1024][256] packed gate order, exact fp32
     float *in_w_x, *in_w_t, *in_b, *out_w_x, *out_w_t, *out_b;
     float *sc0_w_x, *sc0_w_t, *sc0_b, *sc2_w, *sc2_b;
+    // 16-bit copies of the GEMM weights, [0] = fp16 (AVS_PREC_TF32 mode, everything behind the fc layers),
+    // [1] = bf16 (AVS_PREC_BF16 mode); same packed row order as the fp32 tensors
+    uint16_t *fc_v_w_l[2], *fc_a_w_l[2], *ih_v_l[2], *ih_a_l[2], *in_w_l[2], *out_w_l[2], *sc0_w_l[2];
     Arena ws;       // activations
     Arena staging;  // raw weights during packing
+    // host-space calls: H2D copies run on their own stream, chunked, so that the row-parallel
+    // front of the pipeline (tf32 rounding, fc and LSTM-input GEMMs) overlaps the PCIe transfer
+    static constexpr int MAX_CHUNKS = 4;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr;
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
 };
 
 namespace {
@@ -227,6 +236,14 @@ avs_status pack_weights(avs_model* m, const avs_weights* w) {
     AVS_TRY(both(r_inw, 3ull * E * E, m->in_w_x, m->in_w_t));
     AVS_TRY(both(r_outw, static_cast<size_t>(E) * E, m->out_w_x, m->out_w_t));
     AVS_TRY(both(r_sc0, 64ull * E, m->sc0_w_x, m->sc0_w_t));
+    for (int l = 0; l < 2; ++l) {
+        const int dt = l ? DT_BF16 : DT_F16;
+        AVS_TRY(convert_f32(r_fcv, m->fc_v_w_l[l], static_cast<int64_t>(H) * Dv, dt, 0, st));
+        AVS_TRY(convert_f32(r_fca, m->fc_a_w_l[l], static_cast<int64_t>(H) * Da, dt, 0, st));
+        AVS_TRY(convert_f32(r_inw, m->in_w_l[l], 3ll * E * E, dt, 0, st));
+        AVS_TRY(convert_f32(r_outw, m->out_w_l[l], static_cast<int64_t>(E) * E, dt, 0, st));
+        AVS_TRY(convert_f32(r_sc0, m->sc0_w_l[l], 64ll * E, dt, 0, st));
+    }
     // LSTM: gate-interleaved row order so that cluster CTA r owns 128 contiguous gate columns
     for (int i = 0; i < 4; ++i) {
         const int mod = i >> 1, dir = i & 1;
@@ -241,6 +258,11 @@ avs_status pack_weights(avs_model* m, const avs_weights* w) {
         AVS_LAUNCH_CHECK();
         permute_gate_bias_kernel<<<(G4 + 255) / 256, 256, 0, st>>>(r_bih[i], r_bhh[i], bias);
         AVS_LAUNCH_CHECK();
+    }
+    for (int l = 0; l < 2; ++l) {
+        const int dt = l ? DT_BF16 : DT_F16;
+        AVS_TRY(convert_f32(m->ih_v_x, m->ih_v_l[l], 2ll * G4 * H, dt, 0, st));
+        AVS_TRY(convert_f32(m->ih_a_x, m->ih_a_l[l], 2ll * G4 * H, dt, 0, st));
     }
     AVS_CUDA(cudaStreamSynchronize(st));
     return AVS_OK;
@@ -318,13 +340,28 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
     return p;
 }
 
-avs_status run_gemm(int precision, const float* A, int64_t lda, const float* w_exact, const float* w_tf32, int64_t ldw,
+// One weight matrix in every operand format the kernels consume.
+struct GemmW {
+    const float* x;              // exact fp32 (CUDA-core path)
+    const float* t;              // tf32-rounded fp32
+    uint16_t* const* l;          // [0] fp16, [1] bf16
+};
+
+// C = epilogue(A * W[off : off + N*ldw]^T).  The operand format follows the dtype of A:
+// fp32 -> kind::tf32 (or the CUDA-core path in AVS_PREC_FP32_SIMT), fp16 / bf16 -> kind::f16.
+avs_status run_gemm(int precision, const void* A, int a_dtype, int64_t lda, const GemmW& w, int64_t w_off, int64_t ldw,
                     int64_t M, int N, int K, GemmEpilogue epi, cudaStream_t st) {
     if (precision == AVS_PREC_FP32_SIMT) {
+        AVS_CHECK(a_dtype == DT_F32, AVS_ERR_INVALID, "fp32_simt GEMM needs fp32 operands");
         epi.round_tf32 = 0;
-        return gemm_simt(A, lda, w_exact, ldw, M, N, K, epi, st);
+        return gemm_simt(static_cast<const float*>(A), lda, w.x + w_off, ldw, M, N, K, epi, st);
     }
-    return gemm_tc(A, lda, w_tf32, ldw, DT_F32, M, N, K, epi, st);
+    if (a_dtype == DT_F32) return gemm_tc(A, lda, w.t + w_off, ldw, DT_F32, M, N, K, epi, st);
+    return gemm_tc(A, lda, w.l[a_dtype == DT_BF16 ? 1 : 0] + w_off, ldw, a_dtype, M, N, K, epi, st);
+}
+
+bool precision_ok(int precision) {
+    return precision == AVS_PREC_TF32 || precision == AVS_PREC_BF16 || precision == AVS_PREC_FP32_SIMT;
 }
 
 }  // namespace
@@ -385,17 +422,25 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
     m->Da = w->audio_dim;
     m->heads = w->num_heads;
     const size_t Dv = m->Dv, Da = m->Da;
-    struct Item { float** p; size_t n; };
-    Item items[] = {
-        {&m->fc_v_w_x, H * Dv}, {&m->fc_v_w_t, H * Dv}, {&m->fc_a_w_x, H * Da}, {&m->fc_a_w_t, H * Da},
-        {&m->fc_v_b, H}, {&m->fc_a_b, H},
-        {&m->ih_v_x, 2ull * G4 * H}, {&m->ih_v_t, 2ull * G4 * H}, {&m->ih_a_x, 2ull * G4 * H}, {&m->ih_a_t, 2ull * G4 * H},
-        {&m->ih_v_b, 2 * G4}, {&m->ih_a_b, 2 * G4}, {&m->whh, 4ull * G4 * HC},
-        {&m->in_w_x, 3ull * E * E}, {&m->in_w_t, 3ull * E * E}, {&m->in_b, 3 * E},
-        {&m->out_w_x, 1ull * E * E}, {&m->out_w_t, 1ull * E * E}, {&m->out_b, E},
-        {&m->sc0_w_x, 64ull * E}, {&m->sc0_w_t, 64ull * E}, {&m->sc0_b, 64}, {&m->sc2_w, 64}, {&m->sc2_b, 64}};
+    struct Item { void** p; size_t bytes; };
+    std::vector<Item> items;
+    auto f32 = [&](float** p, size_t n) { items.push_back({reinterpret_cast<void**>(p), n * sizeof(float)}); };
+    auto l16 = [&](uint16_t** p, size_t n) { items.push_back({reinterpret_cast<void**>(p), n * 2}); };
+    f32(&m->fc_v_w_x, H * Dv); f32(&m->fc_v_w_t, H * Dv); f32(&m->fc_a_w_x, H * Da); f32(&m->fc_a_w_t, H * Da);
+    f32(&m->fc_v_b, H); f32(&m->fc_a_b, H);
+    f32(&m->ih_v_x, 2ull * G4 * H); f32(&m->ih_v_t, 2ull * G4 * H);
+    f32(&m->ih_a_x, 2ull * G4 * H); f32(&m->ih_a_t, 2ull * G4 * H);
+    f32(&m->ih_v_b, 2 * G4); f32(&m->ih_a_b, 2 * G4); f32(&m->whh, 4ull * G4 * HC);
+    f32(&m->in_w_x, 3ull * E * E); f32(&m->in_w_t, 3ull * E * E); f32(&m->in_b, 3 * E);
+    f32(&m->out_w_x, 1ull * E * E); f32(&m->out_w_t, 1ull * E * E); f32(&m->out_b, E);
+    f32(&m->sc0_w_x, 64ull * E); f32(&m->sc0_w_t, 64ull * E); f32(&m->sc0_b, 64); f32(&m->sc2_w, 64); f32(&m->sc2_b, 64);
+    for (int l = 0; l < 2; ++l) {
+        l16(&m->fc_v_w_l[l], H * Dv); l16(&m->fc_a_w_l[l], H * Da);
+        l16(&m->ih_v_l[l], 2ull * G4 * H); l16(&m->ih_a_l[l], 2ull * G4 * H);
+        l16(&m->in_w_l[l], 3ull * E * E); l16(&m->out_w_l[l], 1ull * E * E); l16(&m->sc0_w_l[l], 64ull * E);
+    }
     size_t total = 0;
-    for (auto& it : items) total += align_up(it.n * sizeof(float), 256);
+    for (auto& it : items) total += align_up(it.bytes, 256);
     cudaError_t e = cudaMalloc(&m->slab, total);
     if (e != cudaSuccess) {
         set_error("cudaMalloc(%zu) for packed weights failed: %s", total, cudaGetErrorString(e));
@@ -404,10 +449,20 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
     }
     size_t off = 0;
     for (auto& it : items) {
-        *it.p = reinterpret_cast<float*>(m->slab + off);
-        off += align_up(it.n * sizeof(float), 256);
+        *it.p = m->slab + off;
+        off += align_up(it.bytes, 256);
     }
     avs_status s = pack_weights(m, w);
+    if (s == AVS_OK) {
+        cudaError_t ce = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming);
+        for (int i = 0; i < avs_model::MAX_CHUNKS && ce == cudaSuccess; ++i)
+            ce = cudaEventCreateWithFlags(&m->ev_chunk[i], cudaEventDisableTiming);
+        if (ce != cudaSuccess) {
+            set_error("creating the copy stream / events failed: %s", cudaGetErrorString(ce));
+            s = AVS_ERR_CUDA;
+        }
+    }
     if (s != AVS_OK) {
         avs_model_destroy(m);
         return s;
@@ -429,8 +484,13 @@ avs_status avs_model_update(avs_model* m, const avs_weights* w) {
 void avs_model_destroy(avs_model* m) {
     if (!m) return;
     Guard g(m->device);
+    cudaDeviceSynchronize();
     m->ws.release();
     m->staging.release();
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->ev_start) cudaEventDestroy(m->ev_start);
+    for (cudaEvent_t e : m->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (m->slab) cudaFree(m->slab);
     delete m;
 }
@@ -440,8 +500,7 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
                        int space, void* cuda_stream) {
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
     AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
-    AVS_CHECK(precision == AVS_PREC_TF32 || precision == AVS_PREC_FP32_SIMT, AVS_ERR_UNSUPPORTED,
-              "precision %d not available in this build", precision);
+    AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
     AVS_CHECK(attn_axis == AVS_ATTN_LITERAL || attn_axis == AVS_ATTN_TEMPORAL || attn_axis == AVS_ATTN_LITERAL_B1,
               AVS_ERR_INVALID, "bad attn_axis %d", attn_axis);
     int max_len = 0;
@@ -453,7 +512,14 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     const int64_t R = total_rows;
     const int Dv = m->Dv, Da = m->Da;
     const bool simt = precision == AVS_PREC_FP32_SIMT;
-    const int rnd = simt ? 0 : 1;
+    const bool bf16 = precision == AVS_PREC_BF16;
+    // Operand formats.  AVS_PREC_TF32: the user's fp32 features are rounded (RN) to tf32 and feed kind::tf32
+    // GEMMs (fp32 exponent range); every activation behind the fc layers is fp16 (same 11-bit significand,
+    // saturating) and feeds kind::f16.  AVS_PREC_BF16: bf16 everywhere.  Accumulation, gate pre-activations,
+    // cell state, softmax statistics and the score head stay fp32 in all modes.
+    const int act = simt ? DT_F32 : (bf16 ? DT_BF16 : DT_F16);   // internal activations
+    const int in_dt = bf16 ? DT_BF16 : DT_F32;                   // what the fc GEMMs read
+    const size_t asz = dtype_size(act);
 
     bool literal_rows = attn_axis == AVS_ATTN_LITERAL_B1 || (attn_axis == AVS_ATTN_LITERAL && n_videos == 1);
     if (attn_axis == AVS_ATTN_LITERAL && n_videos > 1) {
@@ -466,68 +532,97 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     // ---- plan + workspace
     LstmPlan plan = plan_lstm(n_videos, row_start, lengths, !simt);
     const int n_seqs = literal_rows ? 0 : (attn_axis == AVS_ATTN_TEMPORAL ? n_videos : lengths[0]);
-    const size_t act_floats = static_cast<size_t>(R) * (Dv + Da + 2 * H + 2 * 2 * G4 + E + 3 * E + E + E + 1);
-    AVS_TRY(m->ws.reserve(act_floats * sizeof(float) + (plan.host.size() + 3 * static_cast<size_t>(n_seqs)) * 4 +
-                          64 * 256));
+    const bool tc_attn = !simt && attn_axis == AVS_ATTN_TEMPORAL && E == m->heads * 256;
+    const int qkv_dt = tc_attn ? act : DT_F32;
+    const size_t uR = static_cast<size_t>(R);
+    const size_t bytes = uR * (Dv + Da) * 4 + (bf16 ? uR * (Dv + Da) * 2 : 0) + 2 * uR * H * asz + 2 * uR * 2 * G4 * 4 +
+                         3 * uR * E * asz + (literal_rows ? 0 : uR * 3 * E * dtype_size(qkv_dt)) + uR * 4 +
+                         (plan.host.size() + 3 * static_cast<size_t>(n_seqs)) * 4 + 64 * 256;
+    AVS_TRY(m->ws.reserve(bytes));
     m->ws.reset();
-    float* in_v = m->ws.take<float>(R * Dv);
-    float* in_a = m->ws.take<float>(R * Da);
-    float* v_emb = m->ws.take<float>(R * H);
-    float* a_emb = m->ws.take<float>(R * H);
-    float* xg_v = m->ws.take<float>(R * 2 * G4);
-    float* xg_a = m->ws.take<float>(R * 2 * G4);
-    float* fused = m->ws.take<float>(R * E);
-    float* qkv = m->ws.take<float>(R * 3 * E);
-    float* ctx = m->ws.take<float>(R * E);
-    float* attn_out = m->ws.take<float>(R * E);
-    float* scores_dev = space == AVS_DEVICE ? scores : m->ws.take<float>(R);
+    float* in_v = m->ws.take<float>(uR * Dv);
+    float* in_a = m->ws.take<float>(uR * Da);
+    uint16_t* in_v16 = bf16 ? m->ws.take<uint16_t>(uR * Dv) : nullptr;
+    uint16_t* in_a16 = bf16 ? m->ws.take<uint16_t>(uR * Da) : nullptr;
+    char* v_emb = m->ws.take<char>(uR * H * asz);
+    char* a_emb = m->ws.take<char>(uR * H * asz);
+    float* xg_v = m->ws.take<float>(uR * 2 * G4);
+    float* xg_a = m->ws.take<float>(uR * 2 * G4);
+    char* fused = m->ws.take<char>(uR * E * asz);
+    char* qkv = literal_rows ? nullptr : m->ws.take<char>(uR * 3 * E * dtype_size(qkv_dt));
+    char* ctx = m->ws.take<char>(uR * E * asz);
+    char* attn_out = m->ws.take<char>(uR * E * asz);
+    float* scores_dev = space == AVS_DEVICE ? scores : m->ws.take<float>(uR);
     int32_t* plan_dev = m->ws.take<int32_t>(plan.host.size());
     int32_t* seq_dev = m->ws.take<int32_t>(3 * static_cast<size_t>(std::max(n_seqs, 1)));
 
-    // ---- inputs: H2D (host space) and tf32 rounding of the user features
-    const float* xv = visual;
-    const float* xa = audio;
-    if (space == AVS_HOST) {
-        AVS_CUDA(cudaMemcpyAsync(in_v, visual, static_cast<size_t>(R) * Dv * 4, cudaMemcpyHostToDevice, st));
-        AVS_CUDA(cudaMemcpyAsync(in_a, audio, static_cast<size_t>(R) * Da * 4, cudaMemcpyHostToDevice, st));
-        xv = in_v;
-        xa = in_a;
-    }
+    const GemmW w_fc_v{m->fc_v_w_x, m->fc_v_w_t, m->fc_v_w_l}, w_fc_a{m->fc_a_w_x, m->fc_a_w_t, m->fc_a_w_l};
+    const GemmW w_ih_v{m->ih_v_x, m->ih_v_t, m->ih_v_l}, w_ih_a{m->ih_a_x, m->ih_a_t, m->ih_a_l};
+    const GemmW w_in{m->in_w_x, m->in_w_t, m->in_w_l}, w_out{m->out_w_x, m->out_w_t, m->out_w_l};
+    const GemmW w_sc0{m->sc0_w_x, m->sc0_w_t, m->sc0_w_l};
+
+    // ---- front of the pipeline, row-parallel and therefore chunked: H2D (host space) -> operand conversion of the
+    // user features -> K1 visual_fc / audio_fc (Linear + ReLU; Dropout is identity in eval, av_model.py:35-36)
+    // -> K2a LSTM input projections for both directions (av_model.py:39-40).  In host space chunk c+1 is in
+    // flight on the copy stream while chunk c is being computed.
     AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
-    if (!simt) {
-        StageTimer tm(ST_CONVERT, st);
-        AVS_TRY(convert_f32(xv, in_v, R * Dv, DT_F32, 1, st));
-        AVS_TRY(convert_f32(xa, in_a, R * Da, DT_F32, 1, st));
-        xv = in_v;
-        xa = in_a;
+    const int n_chunks = (space == AVS_HOST && R >= 2048) ? avs_model::MAX_CHUNKS : 1;
+    const int64_t chunk_rows = ((R + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+    if (space == AVS_HOST) {
+        AVS_CUDA(cudaEventRecord(m->ev_start, st));              // the workspace is free once prior work on st is done
+        AVS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
+        for (int c = 0; c < n_chunks; ++c) {
+            const int64_t r0 = c * chunk_rows, r1 = std::min<int64_t>(R, r0 + chunk_rows);
+            if (r0 >= r1) break;
+            AVS_CUDA(cudaMemcpyAsync(in_v + r0 * Dv, visual + r0 * Dv, static_cast<size_t>(r1 - r0) * Dv * 4,
+                                     cudaMemcpyHostToDevice, m->copy_stream));
+            AVS_CUDA(cudaMemcpyAsync(in_a + r0 * Da, audio + r0 * Da, static_cast<size_t>(r1 - r0) * Da * 4,
+                                     cudaMemcpyHostToDevice, m->copy_stream));
+            AVS_CUDA(cudaEventRecord(m->ev_chunk[c], m->copy_stream));
+        }
     }
-
-    // ---- K1: visual_fc / audio_fc (Linear + ReLU; Dropout is identity in eval)  av_model.py:35-36
-    {
-        StageTimer tm(ST_FC, st);
-        GemmEpilogue e1;
-        e1.relu = 1;
-        e1.round_tf32 = rnd;
-        e1.ldc = H;
-        e1.bias = m->fc_v_b;
-        e1.C = v_emb;
-        AVS_TRY(run_gemm(precision, xv, Dv, m->fc_v_w_x, m->fc_v_w_t, Dv, R, H, Dv, e1, st));
-        e1.bias = m->fc_a_b;
-        e1.C = a_emb;
-        AVS_TRY(run_gemm(precision, xa, Da, m->fc_a_w_x, m->fc_a_w_t, Da, R, H, Da, e1, st));
-    }
-
-    // ---- K2a: LSTM input projections, both directions at once  av_model.py:39-40
-    {
-        StageTimer tm(ST_IH_PROJ, st);
-        GemmEpilogue e2;
-        e2.ldc = 2 * G4;
-        e2.bias = m->ih_v_b;
-        e2.C = xg_v;
-        AVS_TRY(run_gemm(precision, v_emb, H, m->ih_v_x, m->ih_v_t, H, R, 2 * G4, H, e2, st));
-        e2.bias = m->ih_a_b;
-        e2.C = xg_a;
-        AVS_TRY(run_gemm(precision, a_emb, H, m->ih_a_x, m->ih_a_t, H, R, 2 * G4, H, e2, st));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t r0 = c * chunk_rows, r1 = std::min<int64_t>(R, r0 + chunk_rows);
+        if (r0 >= r1) break;
+        const int64_t Rc = r1 - r0;
+        const float* src_v = (space == AVS_HOST ? in_v : visual) + r0 * Dv;
+        const float* src_a = (space == AVS_HOST ? in_a : audio) + r0 * Da;
+        const void* xv = src_v;
+        const void* xa = src_a;
+        if (space == AVS_HOST) AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[c], 0));
+        if (!simt) {
+            StageTimer tm(ST_CONVERT, st);
+            void* dv = bf16 ? static_cast<void*>(in_v16 + r0 * Dv) : static_cast<void*>(in_v + r0 * Dv);
+            void* da = bf16 ? static_cast<void*>(in_a16 + r0 * Da) : static_cast<void*>(in_a + r0 * Da);
+            AVS_TRY(convert_f32(src_v, dv, Rc * Dv, in_dt, 1, st));
+            AVS_TRY(convert_f32(src_a, da, Rc * Da, in_dt, 1, st));
+            xv = dv;
+            xa = da;
+        }
+        {
+            StageTimer tm(ST_FC, st);
+            GemmEpilogue e1;
+            e1.relu = 1;
+            e1.out_dtype = act;
+            e1.ldc = H;
+            e1.bias = m->fc_v_b;
+            e1.C = v_emb + r0 * H * asz;
+            AVS_TRY(run_gemm(precision, xv, in_dt, Dv, w_fc_v, 0, Dv, Rc, H, Dv, e1, st));
+            e1.bias = m->fc_a_b;
+            e1.C = a_emb + r0 * H * asz;
+            AVS_TRY(run_gemm(precision, xa, in_dt, Da, w_fc_a, 0, Da, Rc, H, Da, e1, st));
+        }
+        {
+            StageTimer tm(ST_IH_PROJ, st);
+            GemmEpilogue e2;
+            e2.ldc = 2 * G4;
+            e2.bias = m->ih_v_b;
+            e2.C = xg_v + r0 * 2 * G4;
+            AVS_TRY(run_gemm(precision, v_emb + r0 * H * asz, act, H, w_ih_v, 0, H, Rc, 2 * G4, H, e2, st));
+            e2.bias = m->ih_a_b;
+            e2.C = xg_a + r0 * 2 * G4;
+            AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, st));
+        }
     }
 
     // ---- K2b: recurrences; writes [v_fwd | v_bwd | a_fwd | a_bwd] = torch.cat of av_model.py:43
@@ -537,34 +632,31 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         int64_t covered = 0;
         for (int b = 0; b < n_videos; ++b) covered += lengths[b];
         if (covered < R)  // padded layout: rows no video owns must stay finite (0 * NaN would poison P*V)
-            AVS_CUDA(cudaMemsetAsync(fused, 0, static_cast<size_t>(R) * E * sizeof(float), st));
+            AVS_CUDA(cudaMemsetAsync(fused, 0, uR * E * asz, st));
         StageTimer tm(ST_LSTM, st);
-        if (simt) AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, rnd, nullptr, 0, st));
-        else AVS_TRY(lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, fused, rnd, st));
+        if (simt) AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, reinterpret_cast<float*>(fused), 0, nullptr, 0, st));
+        else AVS_TRY(lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, act, fused, act, 0, st));
     }
 
     // ---- K3/K4: nn.MultiheadAttention  av_model.py:44
-    const float* ctx_ptr = ctx;
-    int64_t ctx_ld = E;
     if (literal_rows) {
         // sequence length 1: softmax weight == 1, context == value projection
         GemmEpilogue e3;
         e3.bias = m->in_b + 2 * E;
         e3.C = ctx;
         e3.ldc = E;
-        e3.round_tf32 = rnd;
+        e3.out_dtype = act;
         StageTimer tm(ST_QKV_PROJ, st);
-        AVS_TRY(run_gemm(precision, fused, E, m->in_w_x + 2ull * E * E, m->in_w_t + 2ull * E * E, E, R, E, E, e3, st));
+        AVS_TRY(run_gemm(precision, fused, act, E, w_in, 2ll * E * E, E, R, E, E, e3, st));
     } else {
-        const bool tc_attn = !simt && attn_axis == AVS_ATTN_TEMPORAL && E == m->heads * 256;
         GemmEpilogue e3;
         e3.bias = m->in_b;
         e3.C = qkv;
         e3.ldc = 3 * E;
-        if (tc_attn) e3.out_dtype = DT_F16;   // q | k | v straight to fp16 for the tcgen05 attention core
+        e3.out_dtype = qkv_dt;   // q | k | v straight to 16 bit for the tcgen05 attention core
         {
             StageTimer tm(ST_QKV_PROJ, st);
-            AVS_TRY(run_gemm(precision, fused, E, m->in_w_x, m->in_w_t, E, R, 3 * E, E, e3, st));
+            AVS_TRY(run_gemm(precision, fused, act, E, w_in, 0, E, R, 3 * E, E, e3, st));
         }
         std::vector<int32_t> sd(3 * static_cast<size_t>(n_seqs));
         int seq_max = 0;
@@ -586,8 +678,8 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
         AVS_CUDA(cudaMemcpyAsync(seq_dev, sd.data(), sd.size() * 4, cudaMemcpyHostToDevice, st));
         SeqDesc seqs{seq_dev, seq_dev + n_seqs, seq_dev + 2 * n_seqs, n_seqs, seq_max};
         StageTimer tm(ST_ATTENTION, st);
-        if (tc_attn) AVS_TRY(attention_tc(qkv, R, E, m->heads, seqs, ctx, E, rnd, st));
-        else AVS_TRY(attention_simt(qkv, 3 * E, E, m->heads, seqs, ctx, E, rnd, st));
+        if (tc_attn) AVS_TRY(attention_tc(qkv, act, R, E, m->heads, seqs, ctx, E, act, 0, st));
+        else AVS_TRY(attention_simt(reinterpret_cast<const float*>(qkv), 3 * E, E, m->heads, seqs, ctx, E, act, 0, st));
     }
 
     // ---- K5: out_proj
@@ -595,10 +687,10 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     e5.bias = m->out_b;
     e5.C = attn_out;
     e5.ldc = E;
-    e5.round_tf32 = rnd;
+    e5.out_dtype = act;
     {
         StageTimer tm(ST_OUT_PROJ, st);
-        AVS_TRY(run_gemm(precision, ctx_ptr, ctx_ld, m->out_w_x, m->out_w_t, E, R, E, E, e5, st));
+        AVS_TRY(run_gemm(precision, ctx, act, E, w_out, 0, E, R, E, E, e5, st));
     }
 
     // ---- K6: scorer (Linear 1024->64 + ReLU + Linear 64->1 + Sigmoid fused)  av_model.py:29-31,46
@@ -610,11 +702,11 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     e6.scores = scores_dev;
     {
         StageTimer tm(ST_SCORER, st);
-        AVS_TRY(run_gemm(precision, attn_out, E, m->sc0_w_x, m->sc0_w_t, E, R, 64, E, e6, st));
+        AVS_TRY(run_gemm(precision, attn_out, act, E, w_sc0, 0, E, R, 64, E, e6, st));
     }
 
     if (space == AVS_HOST) {
-        AVS_CUDA(cudaMemcpyAsync(scores, scores_dev, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost, st));
+        AVS_CUDA(cudaMemcpyAsync(scores, scores_dev, uR * 4, cudaMemcpyDeviceToHost, st));
         AVS_CUDA(cudaStreamSynchronize(st));
     }
     return AVS_OK;
@@ -745,8 +837,7 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
 avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t M, int32_t N, int32_t K, int relu,
                       int precision, float* C, void* cuda_stream) {
     AVS_CHECK(A && W && C, AVS_ERR_INVALID, "avs_linear: null pointer");
-    AVS_CHECK(precision == AVS_PREC_TF32 || precision == AVS_PREC_FP32_SIMT, AVS_ERR_UNSUPPORTED,
-              "precision %d not available in this build", precision);
+    AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
     GemmEpilogue e;
     e.bias = bias;
     e.C = C;
@@ -754,49 +845,62 @@ avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t
     e.relu = relu;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     if (precision == AVS_PREC_FP32_SIMT) return gemm_simt(A, K, W, K, M, N, K, e, st);
-    return gemm_tc(A, K, W, K, DT_F32, M, N, K, e, st);
+    if (precision == AVS_PREC_TF32) return gemm_tc(A, K, W, K, DT_F32, M, N, K, e, st);
+    // bf16 operands: cast both sides for this call
+    AVS_CHECK(M >= 0 && N > 0 && K > 0 && K % 8 == 0, AVS_ERR_UNSUPPORTED,
+              "avs_linear[bf16]: K=%d must be a multiple of 8 (16-byte TMA row pitch)", K);
+    if (M == 0) return AVS_OK;
+    uint16_t* tmp = nullptr;
+    AVS_CUDA(cudaMallocAsync(&tmp, (static_cast<size_t>(M) + N) * K * 2, st));
+    avs_status s = convert_f32(A, tmp, M * K, DT_BF16, 0, st);
+    if (s == AVS_OK) s = convert_f32(W, tmp + M * K, static_cast<int64_t>(N) * K, DT_BF16, 0, st);
+    if (s == AVS_OK) s = gemm_tc(tmp, K, tmp + M * K, K, DT_BF16, M, N, K, e, st);
+    cudaFreeAsync(tmp, st);
+    return s;
 }
 
 avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows, int32_t n_videos,
                            const int32_t* row_start, const int32_t* lengths, int precision, float* fused,
                            void* cuda_stream) {
     AVS_CHECK(m && v_emb && a_emb && fused, AVS_ERR_INVALID, "avs_bilstm_pair: null pointer");
-    AVS_CHECK(precision == AVS_PREC_TF32 || precision == AVS_PREC_FP32_SIMT, AVS_ERR_UNSUPPORTED,
-              "precision %d not available in this build", precision);
+    AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
     int max_len = 0;
     AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
     if (total_rows == 0 || max_len == 0) return AVS_OK;
     Guard g(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int64_t R = total_rows;
-    LstmPlan plan = plan_lstm(n_videos, row_start, lengths, precision == AVS_PREC_TF32);
+    const bool simt = precision == AVS_PREC_FP32_SIMT;
+    const int act = simt ? DT_F32 : (precision == AVS_PREC_BF16 ? DT_BF16 : DT_F16);
+    LstmPlan plan = plan_lstm(n_videos, row_start, lengths, !simt);
     AVS_TRY(m->ws.reserve(static_cast<size_t>(R) * (2 * 2 * G4 + 2 * H) * 4 + plan.host.size() * 4 + 16 * 256));
     m->ws.reset();
     float* xg_v = m->ws.take<float>(R * 2 * G4);
     float* xg_a = m->ws.take<float>(R * 2 * G4);
     int32_t* plan_dev = m->ws.take<int32_t>(plan.host.size());
-    const float* xv = v_emb;
-    const float* xa = a_emb;
-    if (precision == AVS_PREC_TF32) {
-        float* rv = m->ws.take<float>(R * H);
-        float* ra = m->ws.take<float>(R * H);
-        AVS_TRY(convert_f32(v_emb, rv, R * H, DT_F32, 1, st));
-        AVS_TRY(convert_f32(a_emb, ra, R * H, DT_F32, 1, st));
+    const void* xv = v_emb;
+    const void* xa = a_emb;
+    if (!simt) {   // the embeddings reach the input projection as 16-bit operands, exactly as in avs_forward
+        uint16_t* rv = m->ws.take<uint16_t>(R * H);
+        uint16_t* ra = m->ws.take<uint16_t>(R * H);
+        AVS_TRY(convert_f32(v_emb, rv, R * H, act, 0, st));
+        AVS_TRY(convert_f32(a_emb, ra, R * H, act, 0, st));
         xv = rv;
         xa = ra;
     }
     AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
+    const GemmW w_ih_v{m->ih_v_x, m->ih_v_t, m->ih_v_l}, w_ih_a{m->ih_a_x, m->ih_a_t, m->ih_a_l};
     GemmEpilogue e2;
     e2.ldc = 2 * G4;
     e2.bias = m->ih_v_b;
     e2.C = xg_v;
-    AVS_TRY(run_gemm(precision, xv, H, m->ih_v_x, m->ih_v_t, H, R, 2 * G4, H, e2, st));
+    AVS_TRY(run_gemm(precision, xv, act, H, w_ih_v, 0, H, R, 2 * G4, H, e2, st));
     e2.bias = m->ih_a_b;
     e2.C = xg_a;
-    AVS_TRY(run_gemm(precision, xa, H, m->ih_a_x, m->ih_a_t, H, R, 2 * G4, H, e2, st));
+    AVS_TRY(run_gemm(precision, xa, act, H, w_ih_a, 0, H, R, 2 * G4, H, e2, st));
     const int slots = plan.n_groups * plan.nb;
     LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
-    if (precision == AVS_PREC_TF32) return lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, fused, 0, st);
+    if (!simt) return lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, act, fused, DT_F32, 0, st);
     return lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, 0, nullptr, 0, st);
 }
 
@@ -805,6 +909,7 @@ avs_status avs_attention(const float* qkv, int64_t rows, int32_t E_, int32_t num
                          float* ctx, void* cuda_stream) {
     AVS_CHECK(qkv && ctx && (n_seqs == 0 || (seq_base && seq_stride && seq_len)), AVS_ERR_INVALID,
               "avs_attention: null pointer");
+    AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
     if (n_seqs == 0) return AVS_OK;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     std::vector<int32_t> sd(3 * static_cast<size_t>(n_seqs));
@@ -826,14 +931,15 @@ avs_status avs_attention(const float* qkv, int64_t rows, int32_t E_, int32_t num
     bool contiguous = true;
     for (int i = 0; i < n_seqs; ++i) contiguous &= seq_stride[i] == 1;
     avs_status s;
-    if (precision == AVS_PREC_TF32 && contiguous && E_ == num_heads * 256) {
-        void* qkv_h = nullptr;   // fp16 copy of q | k | v for the tcgen05 kernel
+    if (precision != AVS_PREC_FP32_SIMT && contiguous && E_ == num_heads * 256) {
+        const int dt = precision == AVS_PREC_BF16 ? DT_BF16 : DT_F16;
+        void* qkv_h = nullptr;   // 16-bit copy of q | k | v for the tcgen05 kernel
         AVS_CUDA(cudaMallocAsync(&qkv_h, static_cast<size_t>(rows) * 3 * E_ * 2, st));
-        s = convert_f32(qkv, qkv_h, rows * 3 * E_, DT_F16, 0, st);
-        if (s == AVS_OK) s = attention_tc(qkv_h, rows, E_, num_heads, seqs, ctx, E_, 0, st);
+        s = convert_f32(qkv, qkv_h, rows * 3 * E_, dt, 0, st);
+        if (s == AVS_OK) s = attention_tc(qkv_h, dt, rows, E_, num_heads, seqs, ctx, E_, DT_F32, 0, st);
         cudaFreeAsync(qkv_h, st);
     } else {
-        s = attention_simt(qkv, 3ll * E_, E_, num_heads, seqs, ctx, E_, 0, st);
+        s = attention_simt(qkv, 3ll * E_, E_, num_heads, seqs, ctx, E_, DT_F32, 0, st);
     }
     cudaFreeAsync(dev, st);
     return s;

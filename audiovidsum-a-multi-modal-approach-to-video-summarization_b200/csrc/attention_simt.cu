@@ -19,8 +19,9 @@ namespace {
 constexpr int MAX_DPL = 8;  // head dim <= 256
 
 __global__ void __launch_bounds__(128) attention_simt_kernel(const float* __restrict__ qkv, int64_t ld_qkv, int E,
-                                                             int H, SeqDesc seqs, float* __restrict__ ctx,
-                                                             int64_t ld_ctx, int round_tf32, float scale) {
+                                                             int H, SeqDesc seqs, void* __restrict__ ctx,
+                                                             int64_t ld_ctx, int out_dtype, int round_tf32,
+                                                             float scale) {
     const int seq = blockIdx.z;
     const int head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -59,16 +60,22 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const float* __rest
         m = m_new;
     }
     const float inv = 1.0f / l;
-    float* orow = ctx + (base + static_cast<int64_t>(qi) * stride) * ld_ctx + col;
+    const int64_t ooff = (base + static_cast<int64_t>(qi) * stride) * ld_ctx + col;
 #pragma unroll
-    for (int d = 0; d < MAX_DPL; ++d)
-        if (d < dpl) orow[d] = round_tf32 ? to_tf32_rn(o[d] * inv) : o[d] * inv;
+    for (int d = 0; d < MAX_DPL; ++d) {
+        if (d < dpl) {
+            if (out_dtype != DT_F32)
+                reinterpret_cast<uint16_t*>(ctx)[ooff + d] = to_lowp_bits(o[d] * inv, out_dtype);
+            else
+                reinterpret_cast<float*>(ctx)[ooff + d] = round_tf32 ? to_tf32_rn(o[d] * inv) : o[d] * inv;
+        }
+    }
 }
 
 }  // namespace
 
-avs_status attention_simt(const float* qkv, int64_t ld_qkv, int E, int H, const SeqDesc& seqs, float* ctx,
-                          int64_t ld_ctx, int round_tf32, cudaStream_t stream) {
+avs_status attention_simt(const float* qkv, int64_t ld_qkv, int E, int H, const SeqDesc& seqs, void* ctx,
+                          int64_t ld_ctx, int out_dtype, int round_tf32, cudaStream_t stream) {
     if (seqs.n_seqs == 0 || seqs.max_len == 0) return AVS_OK;
     AVS_CHECK(H > 0 && E % H == 0, AVS_ERR_INVALID, "attention: embed dim %d not divisible by %d heads", E, H);
     const int dh = E / H;
@@ -76,7 +83,7 @@ avs_status attention_simt(const float* qkv, int64_t ld_qkv, int E, int H, const 
               "attention: head dim %d must be a multiple of 32 and <= 256", dh);
     AVS_CHECK(seqs.n_seqs <= 65535 && H <= 65535, AVS_ERR_UNSUPPORTED, "attention: too many sequences in one launch");
     dim3 grid((seqs.max_len + 3) / 4, H, seqs.n_seqs);
-    attention_simt_kernel<<<grid, 128, 0, stream>>>(qkv, ld_qkv, E, H, seqs, ctx, ld_ctx, round_tf32,
+    attention_simt_kernel<<<grid, 128, 0, stream>>>(qkv, ld_qkv, E, H, seqs, ctx, ld_ctx, out_dtype, round_tf32,
                                                     1.0f / sqrtf(static_cast<float>(dh)));
     AVS_LAUNCH_CHECK();
     return AVS_OK;

@@ -62,8 +62,8 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, int E, float* __restrict__ ctx,
-                    int64_t ld_ctx, int round_tf32, float scale_log2) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, int E, int in_dtype,
+                    void* __restrict__ ctx, int64_t ld_ctx, int out_dtype, int round_tf32, float scale_log2) {
     const int seq = blockIdx.z, head = blockIdx.y;
     const int len = seqs.len[seq];
     const int q0 = blockIdx.x * BM;
@@ -133,8 +133,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {
-            const uint32_t idesc_s = umma_idesc(UMMA_FMT_F16, BM, BN);
-            const uint32_t idesc_o = umma_idesc(UMMA_FMT_F16, BM, DH) | (1u << 16);  // B (= V) is MN-major
+            const uint32_t fmt = in_dtype == DT_BF16 ? UMMA_FMT_BF16 : UMMA_FMT_F16;
+            const uint32_t idesc_s = umma_idesc(fmt, BM, BN);
+            const uint32_t idesc_o = umma_idesc(fmt, BM, DH) | (1u << 16);  // B (= V) is MN-major
             const uint32_t q_addr = smem_u32(sm + OFF_Q);
             auto issue_s = [&](int j) {
                 const int st = j & 1;
@@ -174,6 +175,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
         const int q = warp & 3;
         const int row = q0 + q * 32 + lane;                       // query index inside the video
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const bool p_bf16 = in_dtype == DT_BF16;
         float m_used = -INFINITY;   // the max the stored exponentials are relative to (scaled units)
         float l = 0.f;
         for (int j = 0; j < nblk; ++j) {
@@ -221,11 +223,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
             for (int c = 0; c < 32; c += 2) {
                 const float p0 = ex2f(__uint_as_float(s0[c]) - m_used), p1 = ex2f(__uint_as_float(s0[c + 1]) - m_used);
                 const float p2 = ex2f(__uint_as_float(s1[c]) - m_used), p3 = ex2f(__uint_as_float(s1[c + 1]) - m_used);
-                __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
                 // the row sum uses the SAME rounded values the tensor core will multiply with
-                lsum += (__low2float(h01) + __high2float(h01)) + (__low2float(h23) + __high2float(h23));
-                pk[c >> 1] = *reinterpret_cast<uint32_t*>(&h01);
-                pk[16 + (c >> 1)] = *reinterpret_cast<uint32_t*>(&h23);
+                if (p_bf16) {
+                    __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1), h23 = __floats2bfloat162_rn(p2, p3);
+                    lsum += (__low2float(h01) + __high2float(h01)) + (__low2float(h23) + __high2float(h23));
+                    pk[c >> 1] = *reinterpret_cast<uint32_t*>(&h01);
+                    pk[16 + (c >> 1)] = *reinterpret_cast<uint32_t*>(&h23);
+                } else {
+                    __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+                    lsum += (__low2float(h01) + __high2float(h01)) + (__low2float(h23) + __high2float(h23));
+                    pk[c >> 1] = *reinterpret_cast<uint32_t*>(&h01);
+                    pk[16 + (c >> 1)] = *reinterpret_cast<uint32_t*>(&h23);
+                }
             }
             l += lsum;
             tmem_st_32x32(tmem + lane_addr + TM_S + st * BN, pk);   // P_j (fp16 pairs) over S_j's first 32 columns
@@ -238,13 +247,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
         tc_fence_after();
         const float inv_l = 1.0f / l;
         const bool row_ok = row < len;
-        float* dst = ctx + static_cast<int64_t>(base + row) * ld_ctx + head * DH;
+        float* dst = reinterpret_cast<float*>(ctx) + static_cast<int64_t>(base + row) * ld_ctx + head * DH;
+        uint16_t* dst_h = reinterpret_cast<uint16_t*>(ctx) + static_cast<int64_t>(base + row) * ld_ctx + head * DH;
 #pragma unroll 1
         for (int c = 0; c < DH; c += 32) {
             uint32_t o[32];
             tmem_ld_32x32(tmem + lane_addr + TM_O + c, o);
             tmem_ld_wait();
-            if (row_ok) {
+            if (row_ok && out_dtype != DT_F32) {
+#pragma unroll
+                for (int t = 0; t < 32; t += 8) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        pk[u] = pack_lowp2(__uint_as_float(o[t + 2 * u]) * inv_l, __uint_as_float(o[t + 2 * u + 1]) * inv_l,
+                                           out_dtype);
+                    *reinterpret_cast<uint4*>(dst_h + c + t) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            } else if (row_ok) {
 #pragma unroll
                 for (int t = 0; t < 32; t += 4) {
                     float4 v = make_float4(__uint_as_float(o[t]) * inv_l, __uint_as_float(o[t + 1]) * inv_l,
@@ -267,9 +287,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 // qkv_h: fp16 [rows, 3E] (q | k | v).  Sequences must be contiguous rows (stride 1) and E / H == 256.
-avs_status attention_tc(const void* qkv_h, int64_t rows, int E, int H, const SeqDesc& seqs, float* ctx, int64_t ld_ctx,
-                        int round_tf32, cudaStream_t stream) {
+avs_status attention_tc(const void* qkv_h, int in_dtype, int64_t rows, int E, int H, const SeqDesc& seqs, void* ctx,
+                        int64_t ld_ctx, int out_dtype, int round_tf32, cudaStream_t stream) {
     if (seqs.n_seqs == 0 || seqs.max_len == 0) return AVS_OK;
+    AVS_CHECK(in_dtype == DT_F16 || in_dtype == DT_BF16, AVS_ERR_INVALID, "attention_tc: q|k|v must be fp16 or bf16");
     AVS_CHECK(H > 0 && E == H * DH, AVS_ERR_UNSUPPORTED, "attention_tc: head dim must be 256 (E=%d, heads=%d)", E, H);
     AVS_CHECK(seqs.n_seqs <= 65535, AVS_ERR_UNSUPPORTED, "attention_tc: too many sequences in one launch");
     static EncodeTiledFn encode = nullptr;
@@ -285,7 +306,7 @@ avs_status attention_tc(const void* qkv_h, int64_t rows, int E, int H, const Seq
     cuuint64_t gstr[1] = {static_cast<cuuint64_t>(3 * E) * 2};
     cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(qkv_h), gdim, gstr, box, estr,
+    CUresult r = encode(&tm, in_dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(qkv_h), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AVS_CHECK(r == CUDA_SUCCESS, AVS_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed with CUresult %d", static_cast<int>(r));
@@ -296,7 +317,8 @@ avs_status attention_tc(const void* qkv_h, int64_t rows, int E, int H, const Seq
     }
     dim3 grid((seqs.max_len + BM - 1) / BM, H, seqs.n_seqs);
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
-    attention_tc_kernel<<<grid, ATT_THREADS, SMEM_TOTAL, stream>>>(tm, seqs, E, ctx, ld_ctx, round_tf32, scale_log2);
+    attention_tc_kernel<<<grid, ATT_THREADS, SMEM_TOTAL, stream>>>(tm, seqs, E, in_dtype, ctx, ld_ctx, out_dtype,
+                                                                   round_tf32, scale_log2);
     AVS_LAUNCH_CHECK();
     return AVS_OK;
 }

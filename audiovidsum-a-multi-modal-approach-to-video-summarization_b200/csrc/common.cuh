@@ -48,6 +48,24 @@ void count_launch(int n = 1);
 enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
 static inline int dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 
+#ifdef __CUDACC__
+// fp32 -> 16-bit container (round to nearest; fp16 saturates instead of overflowing to inf)
+// (fminf / fmaxf return the non-NaN operand, so NaN is passed through explicitly)
+__device__ __forceinline__ float sat_f16(float x) { return x != x ? x : fminf(fmaxf(x, -65504.f), 65504.f); }
+__device__ __forceinline__ uint16_t to_lowp_bits(float x, int dt) {
+    if (dt == DT_F16) return __half_as_ushort(__float2half_rn(sat_f16(x)));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ uint32_t pack_lowp2(float a, float b, int dt) {
+    if (dt == DT_F16) {
+        __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+#endif
+
 // ---- GEMM: C[M,N] = act(A[M,K] * W[N,K]^T + bias) ---------------------------
 struct GemmEpilogue {
     const float* bias = nullptr;  // [N] fp32 or null
@@ -87,9 +105,10 @@ struct LstmBatch {            // device arrays, one entry per slot (n_groups * N
 avs_status lstm_recurrence(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
                            float* fused, int round_tf32, void* fused_lowp, int lowp_dtype, cudaStream_t stream);
 
-// tcgen05 version (fp16 operands, fp32 accumulate / state); batch.nb must be 16, 32 or 64.
+// tcgen05 version (16-bit operands: op_dtype = DT_F16 or DT_BF16; fp32 accumulate / state); batch.nb must be
+// 16, 32 or 64.  fused output: fp32 (optionally tf32-rounded), fp16 or bf16 (out_dtype).
 avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
-                              float* fused, int round_tf32, cudaStream_t stream);
+                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream);
 
 // ---- attention core -------------------------------------------------------------
 struct SeqDesc {  // device arrays [n_seqs]
@@ -100,12 +119,12 @@ struct SeqDesc {  // device arrays [n_seqs]
     int max_len;
 };
 // CUDA-core reference implementation (fp32), any sequence layout.
-avs_status attention_simt(const float* qkv, int64_t ld_qkv, int E, int H, const SeqDesc& seqs, float* ctx,
-                          int64_t ld_ctx, int round_tf32, cudaStream_t stream);
+avs_status attention_simt(const float* qkv, int64_t ld_qkv, int E, int H, const SeqDesc& seqs, void* ctx,
+                          int64_t ld_ctx, int out_dtype, int round_tf32, cudaStream_t stream);
 
-// tcgen05 flash-style kernel: fp16 qkv [rows, 3E], contiguous sequences (stride 1), head dim 256.
-avs_status attention_tc(const void* qkv_h, int64_t rows, int E, int H, const SeqDesc& seqs, float* ctx, int64_t ld_ctx,
-                        int round_tf32, cudaStream_t stream);
+// tcgen05 flash-style kernel: fp16 / bf16 (in_dtype) qkv [rows, 3E], contiguous sequences (stride 1), head dim 256.
+avs_status attention_tc(const void* qkv_h, int in_dtype, int64_t rows, int E, int H, const SeqDesc& seqs, void* ctx,
+                        int64_t ld_ctx, int out_dtype, int round_tf32, cudaStream_t stream);
 
 // ---- summary generation -----------------------------------------------------------
 struct SummaryBatch {   // device arrays, [n] unless noted

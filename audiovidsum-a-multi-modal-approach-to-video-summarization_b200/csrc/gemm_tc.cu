@@ -4,9 +4,11 @@
 //
 //     C[M, N] = epilogue(A[M, K] * W[N, K]^T)          (both operands K-major)
 //
-//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier ring)
+// Persistent kernel, one CTA per SM, static round-robin over 128 x BN output tiles:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, 6-8 stage mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32 or kind::f16)
-//   warps 2..5  : epilogue -- tcgen05.ld the fp32 accumulator, fuse bias / ReLU / tf32 rounding /
+//   warps 2..5  : epilogue -- tcgen05.ld the fp32 accumulator (double buffered in TMEM, so it
+//                 overlaps the next tile's main loop), fuse bias / ReLU / tf32 rounding /
 //                 fp16-bf16 cast, or the whole frame-score head (64-wide ReLU, dot with
 //                 scorer.2.weight, sigmoid) and store.
 //
@@ -28,29 +30,32 @@ template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * 128;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 8;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 8;
     static constexpr int TOTAL = 1024 /*alignment slack*/ + TILE_BYTES + BAR_BYTES;
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, + gridDim.x, ...
+// (n fastest, so CTAs that run concurrently share the same A row block in L2).  The TMA and MMA
+// pipelines run straight through tile boundaries; the accumulator is double buffered in TMEM
+// (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i + 1.
 template <int BN, int STAGES, bool TF32>
-__global__ void __launch_bounds__(GEMM_THREADS, (SmemLayout<BN, STAGES>::TOTAL <= 110 * 1024) ? 2 : 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-               int k_blocks, int bk_elems, uint32_t idesc, GemmEpilogue epi) {
+               int k_blocks, int bk_elems, uint32_t idesc, int tiles_n, int num_tiles, GemmEpilogue epi) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + L::TILE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * BM;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -60,11 +65,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full + a, 1);
+            mbar_init(tmem_empty + a, 128);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BN);
+        tmem_alloc(tmem_slot, 2 * BN);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -75,114 +83,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (elect_one()) {
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty + s, ph ^ 1);
-                mbar_expect_tx(full + s, L::STAGE_BYTES);
-                uint8_t* a_dst = tiles + s * L::STAGE_BYTES;
-                tma_load_2d(a_dst, &tmA, full + s, kb * bk_elems, m0);
-                tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, full + s, kb * bk_elems, n0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_expect_tx(full + s, L::STAGE_BYTES);
+                    uint8_t* a_dst = tiles + s * L::STAGE_BYTES;
+                    tma_load_2d(a_dst, &tmA, full + s, kb * bk_elems, m0);
+                    tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, full + s, kb * bk_elems, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (elect_one()) {
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(full + s, ph);
+            uint32_t it = 0, lt = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+                const uint32_t acc = lt & 1;
+                mbar_wait(tmem_empty + acc, ((lt >> 1) & 1) ^ 1);   // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                const uint32_t tmem_acc = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full + s, ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 4 x (K = 32 bytes) per 128-byte swizzled row
-                    const uint64_t ad = umma_desc_sw128_kmajor(a_addr + k * 32);
-                    const uint64_t bd = umma_desc_sw128_kmajor(b_addr + k * 32);
-                    if (TF32)
-                        umma_tf32_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
-                    else
-                        umma_f16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k) {  // 4 x (K = 32 bytes) per 128-byte swizzled row
+                        const uint64_t ad = umma_desc_sw128_kmajor(a_addr + k * 32);
+                        const uint64_t bd = umma_desc_sw128_kmajor(b_addr + k * 32);
+                        if (TF32)
+                            umma_tf32_ss(tmem_acc, ad, bd, idesc, (kb | k) != 0);
+                        else
+                            umma_f16_ss(tmem_acc, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(empty + s);  // smem slot reusable once these MMAs retire
                 }
-                tc_commit(empty + s);  // smem slot reusable once these MMAs retire
+                tc_commit(tmem_full + acc);  // accumulator complete
             }
-            tc_commit(tmem_full);  // accumulator complete
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < M;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        float score_acc = 0.f;
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+            const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+            const uint32_t acc = lt & 1;
+            mbar_wait(tmem_full + acc, (lt >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < M;
+            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+            float score_acc = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c, r);
-            tmem_ld_wait();
-            const int nb = n0 + c;
-            if (nb >= N) continue;
-            float v[32];
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c, r);
+                tmem_ld_wait();
+                const int nb = n0 + c;
+                if (nb >= N) continue;
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(r[j]);
-                if (epi.bias != nullptr && nb + j < N) x += __ldg(epi.bias + nb + j);
-                if (epi.relu) x = fmaxf(x, 0.f);
-                v[j] = x;
-            }
-            if (epi.scores != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (nb + j < N) score_acc = fmaf(v[j], __ldg(epi.score_w2 + nb + j), score_acc);
-                continue;
-            }
-            if (!row_ok) continue;
-            if (epi.out_dtype == DT_F32) {
-                float* dst = reinterpret_cast<float*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (nb + j < N) {
-                        float4 o;
-                        if (epi.round_tf32) {
-                            o = make_float4(to_tf32_rn(v[j]), to_tf32_rn(v[j + 1]), to_tf32_rn(v[j + 2]),
-                                            to_tf32_rn(v[j + 3]));
-                        } else {
-                            o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        }
-                        *reinterpret_cast<float4*>(dst + j) = o;
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    if (epi.bias != nullptr && nb + j < N) x += __ldg(epi.bias + nb + j);
+                    if (epi.relu) x = fmaxf(x, 0.f);
+                    v[j] = x;
                 }
-            } else {
-                uint16_t* dst = reinterpret_cast<uint16_t*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
+                if (epi.scores != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    if (nb + j < N) {
-                        uint32_t pk[4];
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < N) score_acc = fmaf(v[j], __ldg(epi.score_w2 + nb + j), score_acc);
+                    continue;
+                }
+                if (!row_ok) continue;
+                if (epi.out_dtype == DT_F32) {
+                    float* dst = reinterpret_cast<float*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            if (epi.out_dtype == DT_F16) {
-                                __half2 h = __floats2half2_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                                pk[t] = *reinterpret_cast<uint32_t*>(&h);
+                    for (int j = 0; j < 32; j += 4) {
+                        if (nb + j < N) {
+                            float4 o;
+                            if (epi.round_tf32) {
+                                o = make_float4(to_tf32_rn(v[j]), to_tf32_rn(v[j + 1]), to_tf32_rn(v[j + 2]),
+                                                to_tf32_rn(v[j + 3]));
                             } else {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                                pk[t] = *reinterpret_cast<uint32_t*>(&h);
+                                o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                             }
+                            *reinterpret_cast<float4*>(dst + j) = o;
                         }
-                        *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                } else {
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (nb + j < N) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) pk[u] = pack_lowp2(v[j + 2 * u], v[j + 2 * u + 1], epi.out_dtype);
+                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
                     }
                 }
             }
-        }
-        if (epi.scores != nullptr && row_ok) {
-            epi.scores[row] = sigmoidf_acc(score_acc + __ldg(epi.score_b2));
+            // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
+            tc_fence_before();
+            mbar_arrive(tmem_empty + acc);
+            if (epi.scores != nullptr && row_ok) epi.scores[row] = sigmoidf_acc(score_acc + __ldg(epi.score_b2));
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---------------------------------------------------------------- host side
@@ -249,7 +266,17 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     CUtensorMap tmA, tmB;
     AVS_TRY(make_tmap(&tmA, A, in_dtype, M, K, lda, BM));
     AVS_TRY(make_tmap(&tmB, W, in_dtype, N, K, ldw, BN));
-    dim3 grid((N + BN - 1) / BN, static_cast<unsigned>((M + BM - 1) / BM));
+    const int tiles_n = (N + BN - 1) / BN;
+    const int64_t tiles_total = static_cast<int64_t>((M + BM - 1) / BM) * tiles_n;
+    AVS_CHECK(tiles_total < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: too many tiles");
+    const int num_tiles = static_cast<int>(tiles_total);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        AVS_CUDA(cudaGetDevice(&dev));
+        AVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;   // persistent: one CTA per SM
     const uint32_t idesc = umma_idesc(fmt, BM, BN);
 
 #define AVS_GEMM_LAUNCH(BN_, ST_, TF_)                                                                       \
@@ -262,15 +289,15 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
             configured = true;                                                                               \
         }                                                                                                    \
         kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, static_cast<int>(M), N, k_blocks, bk_elems, \
-                                                       idesc, epi);                                          \
+                                                       idesc, tiles_n, num_tiles, epi);                      \
     } while (0)
 
     if (BN == 128) {
-        if (tf32) AVS_GEMM_LAUNCH(128, 3, true);
-        else AVS_GEMM_LAUNCH(128, 3, false);
+        if (tf32) AVS_GEMM_LAUNCH(128, 6, true);
+        else AVS_GEMM_LAUNCH(128, 6, false);
     } else {
-        if (tf32) AVS_GEMM_LAUNCH(64, 4, true);
-        else AVS_GEMM_LAUNCH(64, 4, false);
+        if (tf32) AVS_GEMM_LAUNCH(64, 8, true);
+        else AVS_GEMM_LAUNCH(64, 8, false);
     }
 #undef AVS_GEMM_LAUNCH
     AVS_LAUNCH_CHECK();

@@ -136,7 +136,7 @@ __device__ __forceinline__ float tanh_sfu(float x) {
 template <int NB>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
-               LstmBatch batch, float* __restrict__ fused, int round_tf32) {
+               LstmBatch batch, int op_dtype, void* __restrict__ fused_out, int out_dtype, int round_tf32) {
     using S = Smem<NB>;
     constexpr int NV = NB / 4;  // videos per epilogue thread (four warps share a TMEM lane quarter)
     cg::cluster_group cluster = cg::this_cluster();
@@ -196,9 +196,8 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float4 v = __ldg(src + i);
-            __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-            pk[2 * i] = *reinterpret_cast<uint32_t*>(&lo);
-            pk[2 * i + 1] = *reinterpret_cast<uint32_t*>(&hi);
+            pk[2 * i] = pack_lowp2(v.x, v.y, op_dtype);
+            pk[2 * i + 1] = pack_lowp2(v.z, v.w, op_dtype);
         }
         tmem_st_32x32(tmem_w + (static_cast<uint32_t>(q * 32) << 16) + part * 32, pk);
         tmem_st_wait();
@@ -212,7 +211,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     if (warp == EPI_WARPS) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc(UMMA_FMT_F16, COLS, NB);
+            const uint32_t idesc = umma_idesc(op_dtype == DT_BF16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, COLS, NB);
             for (int s = 0; s < maxlen; ++s) {
                 const int b = s & 1;
                 // arm the barrier that will collect h_{s+1}: 8 peers x SLICE_BYTES, one local arrival
@@ -245,8 +244,10 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         const float act_a = (gate == 2) ? 2.0f : 1.0f;
         const float act_b = (gate == 2) ? -1.0f : 0.0f;
         // this thread's slot in the staged slice: [jj/8][video][jj%8] halfs
-        __half* stage_mine = reinterpret_cast<__half*>(stage16 + (jj >> 3) * S::H_LBO) + (jj & 7);
-        float* const fcol = fused + out_col + jj;
+        uint16_t* stage_mine = reinterpret_cast<uint16_t*>(stage16 + (jj >> 3) * S::H_LBO) + (jj & 7);
+        float* const fcol = reinterpret_cast<float*>(fused_out) + out_col + jj;
+        uint16_t* const fcol_h = reinterpret_cast<uint16_t*>(fused_out) + out_col + jj;
+        const bool op_bf16 = op_dtype == DT_BF16;
         const int rstep = dir ? -1 : 1;
 
         float c_state[NV], xv0[NV], xv1[NV];   // xv0: this step's input projection, xv1: next step's
@@ -287,7 +288,9 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 const float h = a_o * tanh_sfu(cn);
                 c_state[i] = on ? cn : c_state[i];
                 h_out[i] = h;
-                if (on && gate == 0) stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + (v0 + i) * 8] = __float2half_rn(h);
+                if (on && gate == 0)   // |h| < 1: no saturation needed
+                    stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + (v0 + i) * 8] =
+                        op_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(h)) : __half_as_ushort(__float2half_rn(h));
             }
             if (s + 1 < maxlen) {
                 fence_proxy_async();   // staged h (generic proxy) -> visible to the bulk-copy engine
@@ -304,8 +307,12 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const bool on = s < len_r[i];
-                if (on && gate == 0)
-                    fcol[static_cast<size_t>(row_r[i]) * FUSED_LD] = round_tf32 ? to_tf32_rn(h_out[i]) : h_out[i];
+                if (on && gate == 0) {
+                    if (out_dtype != DT_F32)
+                        fcol_h[static_cast<size_t>(row_r[i]) * FUSED_LD] = to_lowp_bits(h_out[i], out_dtype);
+                    else
+                        fcol[static_cast<size_t>(row_r[i]) * FUSED_LD] = round_tf32 ? to_tf32_rn(h_out[i]) : h_out[i];
+                }
                 row_r[i] += on ? rstep : 0;
                 xv0[i] = xv1[i];
                 xv1[i] = xv2[i];
@@ -319,15 +326,16 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
 }
 
 template <int NB>
-avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, float* fused,
-                     int round_tf32, cudaStream_t stream) {
+avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, int op_dtype,
+                     void* fused, int out_dtype, int round_tf32, cudaStream_t stream) {
     auto kern = lstm_tc_kernel<NB>;
     static bool configured = false;
     if (!configured) {
         AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NB>::TOTAL));
         configured = true;
     }
-    kern<<<batch.n_groups * 4 * CL, THREADS, Smem<NB>::TOTAL, stream>>>(xg_v, xg_a, whh, batch, fused, round_tf32);
+    kern<<<batch.n_groups * 4 * CL, THREADS, Smem<NB>::TOTAL, stream>>>(xg_v, xg_a, whh, batch, op_dtype, fused,
+                                                                        out_dtype, round_tf32);
     AVS_LAUNCH_CHECK();
     return AVS_OK;
 }
@@ -335,12 +343,13 @@ avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, con
 }  // namespace
 
 avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
-                              float* fused, int round_tf32, cudaStream_t stream) {
+                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream) {
     if (batch.n_groups == 0) return AVS_OK;
+    AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
     switch (batch.nb) {
-        case 16: return launch_tc<16>(xg_v, xg_a, whh_packed, batch, fused, round_tf32, stream);
-        case 32: return launch_tc<32>(xg_v, xg_a, whh_packed, batch, fused, round_tf32, stream);
-        case 64: return launch_tc<64>(xg_v, xg_a, whh_packed, batch, fused, round_tf32, stream);
+        case 16: return launch_tc<16>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
+        case 32: return launch_tc<32>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
+        case 64: return launch_tc<64>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
         default: set_error("lstm_tc: unsupported videos-per-cluster %d", batch.nb); return AVS_ERR_INVALID;
     }
 }

@@ -294,7 +294,7 @@ def main():
     for name, (ms, calls) in stage_ms.items():
         if calls == 0:
             continue
-        per = ms / calls
+        per = ms / args.steps
         rec = {"ms_per_step": per}
         if name in flops and flops[name] > 0:
             rec["tflops"] = flops[name] * R / (per * 1e-3) / 1e12
