@@ -9,8 +9,10 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32 or kind::f16)
 //   warps 2..5  : epilogue -- tcgen05.ld the fp32 accumulator (double buffered in TMEM, so it
 //                 overlaps the next tile's main loop), fuse bias / ReLU / tf32 rounding /
-//                 fp16-bf16 cast, or the whole frame-score head (64-wide ReLU, dot with
-//                 scorer.2.weight, sigmoid) and store.
+//                 fp16-bf16 cast, stage the warp's 32 rows in 128B-swizzled shared memory and write
+//                 them with TMA stores (cp.async.bulk.tensor ... bulk_group: full-line coalesced
+//                 writes, rows >= M clipped by the tensor map); or the whole frame-score head
+//                 (64-wide ReLU, dot with scorer.2.weight, sigmoid), one float per row.
 //
 // Tile 128 x BN x 128 B of K per stage (32 tf32 or 64 half elements), 4 MMAs (K = 32 B) per stage.
 #include <cuda.h>
@@ -30,11 +32,34 @@ template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * 128;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int OUT_WARP_BYTES = 32 * BN * 4;       // one epilogue warp's 32 rows, fp32 worst case
+    static constexpr int OUT_BYTES = 4 * OUT_WARP_BYTES;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 8;
-    static constexpr int TOTAL = 1024 /*alignment slack*/ + TILE_BYTES + BAR_BYTES;
+    static constexpr int TOTAL = 1024 /*alignment slack*/ + TILE_BYTES + OUT_BYTES + BAR_BYTES;
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// TMA store shared::cta -> global (bulk async group completion).
+__device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most n of this thread's most recent bulk groups still READ their shared-memory source
+__device__ __forceinline__ void bulk_wait_group_read(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, + gridDim.x, ...
 // (n fastest, so CTAs that run concurrently share the same A row block in L2).  The TMA and MMA
@@ -42,13 +67,14 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + e
 // (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i + 1.
 template <int BN, int STAGES, bool TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-               int k_blocks, int bk_elems, uint32_t idesc, int tiles_n, int num_tiles, GemmEpilogue epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int k_blocks, int bk_elems, uint32_t idesc,
+               int tiles_n, int num_tiles, GemmEpilogue epi) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + L::TILE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + L::TILE_BYTES + L::OUT_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;    // [2]
@@ -60,6 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (epi.scores == nullptr) tma_prefetch_desc(&tmC);
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full + s, 1);
@@ -131,70 +158,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        uint32_t lt = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
-            const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
-            const uint32_t acc = lt & 1;
-            mbar_wait(tmem_full + acc, (lt >> 1) & 1);
-            tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
-            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-            float score_acc = 0.f;
+        const uint32_t lane_taddr = static_cast<uint32_t>(q * 32) << 16;
+        if (epi.scores != nullptr) {
+            // fused frame-score head: one float per row, straight from registers
+            uint32_t lt = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+                const uint32_t acc = lt & 1;
+                mbar_wait(tmem_full + acc, (lt >> 1) & 1);
+                tc_fence_after();
+                const int row = m0 + q * 32 + lane;
+                float score_acc = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c, r);
-                tmem_ld_wait();
-                const int nb = n0 + c;
-                if (nb >= N) continue;
-                float v[32];
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + acc * BN + lane_taddr + c, r);
+                    tmem_ld_wait();
+                    const int nb = n0 + c;
+                    if (nb >= N) continue;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (epi.bias != nullptr && nb + j < N) x += __ldg(epi.bias + nb + j);
-                    if (epi.relu) x = fmaxf(x, 0.f);
-                    v[j] = x;
-                }
-                if (epi.scores != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nb + j < N) score_acc = fmaf(v[j], __ldg(epi.score_w2 + nb + j), score_acc);
-                    continue;
-                }
-                if (!row_ok) continue;
-                if (epi.out_dtype == DT_F32) {
-                    float* dst = reinterpret_cast<float*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < 32; ++j) {
                         if (nb + j < N) {
-                            float4 o;
-                            if (epi.round_tf32) {
-                                o = make_float4(to_tf32_rn(v[j]), to_tf32_rn(v[j + 1]), to_tf32_rn(v[j + 2]),
-                                                to_tf32_rn(v[j + 3]));
-                            } else {
-                                o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            }
-                            *reinterpret_cast<float4*>(dst + j) = o;
-                        }
-                    }
-                } else {
-                    uint16_t* dst = reinterpret_cast<uint16_t*>(epi.C) + static_cast<int64_t>(row) * epi.ldc + nb;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (nb + j < N) {
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) pk[u] = pack_lowp2(v[j + 2 * u], v[j + 2 * u + 1], epi.out_dtype);
-                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            float x = __uint_as_float(r[j]);
+                            if (epi.bias != nullptr) x += __ldg(epi.bias + nb + j);
+                            if (epi.relu) x = fmaxf(x, 0.f);
+                            score_acc = fmaf(x, __ldg(epi.score_w2 + nb + j), score_acc);
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(tmem_empty + acc);
+                if (row < M) epi.scores[row] = sigmoidf_acc(score_acc + __ldg(epi.score_b2));
             }
-            // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
-            tc_fence_before();
-            mbar_arrive(tmem_empty + acc);
-            if (epi.scores != nullptr && row_ok) epi.scores[row] = sigmoidf_acc(score_acc + __ldg(epi.score_b2));
+        } else {
+            // stage 32 rows x 128 B boxes (32 fp32 or 64 half columns) in swizzled shared memory, TMA-store each
+            const bool wide = epi.out_dtype != DT_F32;          // 16-bit output: 64 columns per 128-byte box
+            const int box_cols = wide ? 64 : 32;
+            const int n_boxes = BN / box_cols;
+            const uint32_t out_base = smem_u32(tiles + L::TILE_BYTES) + q * L::OUT_WARP_BYTES;
+            const uint32_t my_row = out_base + lane * 128;
+            const uint32_t sw = static_cast<uint32_t>(lane & 7);
+            uint32_t lt = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+                const uint32_t acc = lt & 1;
+                mbar_wait(tmem_full + acc, (lt >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * BN + lane_taddr;
+#pragma unroll 1
+                for (int bx = 0; bx < n_boxes; ++bx) {
+                    const int nb = n0 + bx * box_cols;
+                    // the TMA store that read this box's staging one tile ago must be done reading
+                    if (lt > 0) {
+                        if (lane == 0) bulk_wait_group_read(n_boxes - 1);
+                        __syncwarp();
+                    }
+                    const uint32_t dst = my_row + bx * 4096;
+                    if (!wide) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + bx * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = __uint_as_float(r[j]);
+                            if (epi.bias != nullptr && nb + j < N) x += __ldg(epi.bias + nb + j);
+                            if (epi.relu) x = fmaxf(x, 0.f);
+                            if (epi.round_tf32) x = to_tf32_rn(x);
+                            r[j] = __float_as_uint(x);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), r[4 * j], r[4 * j + 1],
+                                         r[4 * j + 2], r[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t r[32];
+                            tmem_ld_32x32(taddr + bx * 64 + hf * 32, r);
+                            tmem_ld_wait();
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
+                                const int col = nb + hf * 32 + j;
+                                if (epi.bias != nullptr && col < N) {   // N % 16 == 0: col and col + 1 fall together
+                                    x0 += __ldg(epi.bias + col);
+                                    x1 += __ldg(epi.bias + col + 1);
+                                }
+                                if (epi.relu) {
+                                    x0 = fmaxf(x0, 0.f);
+                                    x1 = fmaxf(x1, 0.f);
+                                }
+                                pk[j >> 1] = pack_lowp2(x0, x1, epi.out_dtype);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                st_shared_v4(dst + ((static_cast<uint32_t>(hf * 4 + j) ^ sw) << 4), pk[4 * j],
+                                             pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                    fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (nb < N) tma_store_2d(&tmC, out_base + bx * 4096, nb, m0 + q * 32);
+                        bulk_commit_group();   // (possibly empty) keeps the group count per tile fixed
+                    }
+                }
+                // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
+                tc_fence_before();
+                mbar_arrive(tmem_empty + acc);
+            }
+            if (lane == 0) bulk_wait_group_read(0);   // shared memory must outlive the last stores' reads
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -221,7 +296,8 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D K-major operand [rows, K] with leading dimension ld (elements): box = 128 bytes of K x box_rows.
+// 2-D row-major tensor [rows, K] with leading dimension ld (elements): box = 128 bytes of a row x box_rows,
+// 128-byte swizzle.  Used for the K-major operands (TMA loads) and for the output C (TMA stores).
 avs_status make_tmap(CUtensorMap* tm, const void* ptr, int dtype, int64_t rows, int K, int64_t ld, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     AVS_CHECK(fn != nullptr, AVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -254,8 +330,9 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     if (epi.scores != nullptr)
         AVS_CHECK(N == 64 && epi.score_w2 && epi.score_b2, AVS_ERR_INVALID, "score epilogue needs N == 64");
     else
-        AVS_CHECK(epi.C != nullptr && epi.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0,
-                  AVS_ERR_INVALID, "gemm: output must be 16-byte aligned with ldc %% 4 == 0");
+        AVS_CHECK(epi.C != nullptr && (epi.ldc * dtype_size(epi.out_dtype)) % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0,
+                  AVS_ERR_INVALID, "gemm: output must be 16-byte aligned with a row pitch that is a multiple of 16 B");
     const int esz = dtype_size(in_dtype);
     const int bk_elems = 128 / esz;
     const int k_blocks = (K + bk_elems - 1) / bk_elems;
@@ -263,9 +340,11 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     const uint32_t fmt = tf32 ? UMMA_FMT_TF32 : (in_dtype == DT_F16 ? UMMA_FMT_F16 : UMMA_FMT_BF16);
     const int BN = (N % 128 == 0) ? 128 : 64;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     AVS_TRY(make_tmap(&tmA, A, in_dtype, M, K, lda, BM));
     AVS_TRY(make_tmap(&tmB, W, in_dtype, N, K, ldw, BN));
+    if (epi.scores == nullptr) AVS_TRY(make_tmap(&tmC, epi.C, epi.out_dtype, M, N, epi.ldc, 32));
+    else tmC = tmA;   // unused by the score epilogue
     const int tiles_n = (N + BN - 1) / BN;
     const int64_t tiles_total = static_cast<int64_t>((M + BM - 1) / BM) * tiles_n;
     AVS_CHECK(tiles_total < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: too many tiles");
@@ -288,16 +367,16 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
             AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));     \
             configured = true;                                                                               \
         }                                                                                                    \
-        kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, static_cast<int>(M), N, k_blocks, bk_elems, \
-                                                       idesc, tiles_n, num_tiles, epi);                      \
+        kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, static_cast<int>(M), N, k_blocks,      \
+                                                       bk_elems, idesc, tiles_n, num_tiles, epi);            \
     } while (0)
 
     if (BN == 128) {
-        if (tf32) AVS_GEMM_LAUNCH(128, 6, true);
-        else AVS_GEMM_LAUNCH(128, 6, false);
+        if (tf32) AVS_GEMM_LAUNCH(128, 4, true);
+        else AVS_GEMM_LAUNCH(128, 4, false);
     } else {
-        if (tf32) AVS_GEMM_LAUNCH(64, 8, true);
-        else AVS_GEMM_LAUNCH(64, 8, false);
+        if (tf32) AVS_GEMM_LAUNCH(64, 6, true);
+        else AVS_GEMM_LAUNCH(64, 6, false);
     }
 #undef AVS_GEMM_LAUNCH
     AVS_LAUNCH_CHECK();

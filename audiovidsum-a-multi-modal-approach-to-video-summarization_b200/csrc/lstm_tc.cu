@@ -248,6 +248,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         float* const fcol = reinterpret_cast<float*>(fused_out) + out_col + jj;
         uint16_t* const fcol_h = reinterpret_cast<uint16_t*>(fused_out) + out_col + jj;
         const bool op_bf16 = op_dtype == DT_BF16;
+        const bool lowp_out = out_dtype == op_dtype;   // fused output straight from the staged operand slice
         const int rstep = dir ? -1 : 1;
 
         float c_state[NV], xv0[NV], xv1[NV];   // xv0: this step's input projection, xv1: next step's
@@ -292,22 +293,37 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                     stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + (v0 + i) * 8] =
                         op_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(h)) : __half_as_ushort(__float2half_rn(h));
             }
-            if (s + 1 < maxlen) {
-                fence_proxy_async();   // staged h (generic proxy) -> visible to the bulk-copy engine
-                tc_fence_before();
-                epi_bar_sync();        // whole slice staged; all TMEM reads of this step done
-                if (tid < CL) {
-                    const int nb = (s + 1) & 1;
-                    const uint32_t dst = smem_u32(h_sm + nb * S::H_BYTES) + r * S::SLICE_BYTES;
-                    bulk_copy_to_peer(mapa(dst, tid), smem_u32(stage16) + (s & 1) * S::SLICE_BYTES, S::SLICE_BYTES,
-                                      mapa(smem_u32(bar_h + nb), tid));
+            fence_proxy_async();   // staged h (generic proxy) -> visible to the bulk-copy engine
+            tc_fence_before();
+            epi_bar_sync();        // whole slice staged; all TMEM reads of this step done
+            if (s + 1 < maxlen && tid < CL) {
+                const int nb = (s + 1) & 1;
+                const uint32_t dst = smem_u32(h_sm + nb * S::H_BYTES) + r * S::SLICE_BYTES;
+                bulk_copy_to_peer(mapa(dst, tid), smem_u32(stage16) + (s & 1) * S::SLICE_BYTES, S::SLICE_BYTES,
+                                  mapa(smem_u32(bar_h + nb), tid));
+            }
+            // h -> global fused output (off the critical path)
+            if (lowp_out) {
+                // 16-bit output in the operand format: the staged slice already holds it.  One 16-byte store
+                // per (video, 8 hidden units): 4 lanes cover this CTA's 64 contiguous bytes of a fused row.
+                // (slot s&1 is rewritten at step s+2, which every thread reaches only after the step s+1
+                // barrier, i.e. after these reads)
+                if (tid < NB * 4) {
+                    const int v = tid >> 2, ch = tid & 3;
+                    const int len = s_len[v];
+                    if (s < len) {
+                        const uint4 hv = *reinterpret_cast<const uint4*>(stage16 + (s & 1) * S::SLICE_BYTES +
+                                                                         ch * S::H_LBO + v * 16);
+                        const int row = s_row[v] + (dir ? len - 1 - s : s);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(fused_out) +
+                                                  static_cast<size_t>(row) * FUSED_LD + out_col + ch * 8) = hv;
+                    }
                 }
             }
-            // h -> global fused output (off the critical path), advance the per-video cursors
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const bool on = s < len_r[i];
-                if (on && gate == 0) {
+                if (!lowp_out && on && gate == 0) {
                     if (out_dtype != DT_F32)
                         fcol_h[static_cast<size_t>(row_r[i]) * FUSED_LD] = to_lowp_bits(h_out[i], out_dtype);
                     else

@@ -41,7 +41,8 @@ def native(cuda_ready):
 # ------------------------------------------------------------------ K1/K3/K5: nn.Linear
 @pytest.mark.parametrize("prec", ["tf32", "fp32_simt", "bf16"])
 @pytest.mark.parametrize("shape", [(128, 128, 32), (300, 512, 128), (1000, 2048, 512), (500, 64, 1024),
-                                   (320, 512, 296), (77, 1024, 1024), (1, 512, 4096), (129, 3072, 1024)])
+                                   (320, 512, 296), (77, 1024, 1024), (1, 512, 4096), (129, 3072, 1024),
+                                   (200, 16, 64), (333, 48, 256), (4097, 192, 64)])
 def test_linear_matches_torch(cuda_ready, prec, shape):
     M, N, K = shape
     g = torch.Generator().manual_seed(M * 7 + N)
