@@ -57,6 +57,31 @@ __device__ __forceinline__ void bulk_wait_group_read(int n) {
         default: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
     }
 }
+// 32 consecutive bias values for columns [nb, nb + 32) as independent vector loads (every lane reads the same
+// addresses: one broadcast transaction each).  N % 16 == 0, so validity is decided per 16 columns.
+__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int nb, int N, bool vec_ok, float (&bv)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (bias != nullptr && nb + 16 * h < N) {
+            if (vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(bias + nb + 16 * h) + j);
+                    bv[16 * h + 4 * j] = v.x;
+                    bv[16 * h + 4 * j + 1] = v.y;
+                    bv[16 * h + 4 * j + 2] = v.z;
+                    bv[16 * h + 4 * j + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bv[16 * h + j] = __ldg(bias + nb + 16 * h + j);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bv[16 * h + j] = 0.f;
+        }
+    }
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -161,6 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t lane_taddr = static_cast<uint32_t>(q * 32) << 16;
         if (epi.scores != nullptr) {
             // fused frame-score head: one float per row, straight from registers
+            const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
+            const bool w2_vec = (reinterpret_cast<uintptr_t>(epi.score_w2) & 15) == 0;
             uint32_t lt = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
                 const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
@@ -172,18 +199,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 32) {
                     uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + acc * BN + lane_taddr + c, r);
-                    tmem_ld_wait();
+                    float bv[32], wv[32];
                     const int nb = n0 + c;
-                    if (nb >= N) continue;
+                    tmem_ld_32x32(tmem_base + acc * BN + lane_taddr + c, r);
+                    load_bias32(epi.bias, nb, N, bias_vec, bv);
+                    load_bias32(epi.score_w2, nb, N, w2_vec, wv);   // zero beyond N: those columns drop out
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (nb + j < N) {
-                            float x = __uint_as_float(r[j]);
-                            if (epi.bias != nullptr) x += __ldg(epi.bias + nb + j);
-                            if (epi.relu) x = fmaxf(x, 0.f);
-                            score_acc = fmaf(x, __ldg(epi.score_w2 + nb + j), score_acc);
-                        }
+                        float x = __uint_as_float(r[j]) + bv[j];
+                        if (epi.relu) x = fmaxf(x, 0.f);
+                        score_acc = fmaf(x, wv[j], score_acc);
                     }
                 }
                 tc_fence_before();
@@ -198,6 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t out_base = smem_u32(tiles + L::TILE_BYTES) + q * L::OUT_WARP_BYTES;
             const uint32_t my_row = out_base + lane * 128;
             const uint32_t sw = static_cast<uint32_t>(lane & 7);
+            const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
             uint32_t lt = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
                 const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
@@ -216,12 +243,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t dst = my_row + bx * 4096;
                     if (!wide) {
                         uint32_t r[32];
+                        float bv[32];
                         tmem_ld_32x32(taddr + bx * 32, r);
+                        load_bias32(epi.bias, nb, N, bias_vec, bv);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            float x = __uint_as_float(r[j]);
-                            if (epi.bias != nullptr && nb + j < N) x += __ldg(epi.bias + nb + j);
+                            float x = __uint_as_float(r[j]) + bv[j];
                             if (epi.relu) x = fmaxf(x, 0.f);
                             if (epi.round_tf32) x = to_tf32_rn(x);
                             r[j] = __float_as_uint(x);
@@ -234,17 +262,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
                             uint32_t r[32];
+                            float bv[32];
                             tmem_ld_32x32(taddr + bx * 64 + hf * 32, r);
+                            load_bias32(epi.bias, nb + hf * 32, N, bias_vec, bv);
                             tmem_ld_wait();
                             uint32_t pk[16];
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
-                                float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
-                                const int col = nb + hf * 32 + j;
-                                if (epi.bias != nullptr && col < N) {   // N % 16 == 0: col and col + 1 fall together
-                                    x0 += __ldg(epi.bias + col);
-                                    x1 += __ldg(epi.bias + col + 1);
-                                }
+                                float x0 = __uint_as_float(r[j]) + bv[j], x1 = __uint_as_float(r[j + 1]) + bv[j + 1];
                                 if (epi.relu) {
                                     x0 = fmaxf(x0, 0.f);
                                     x1 = fmaxf(x1, 0.f);

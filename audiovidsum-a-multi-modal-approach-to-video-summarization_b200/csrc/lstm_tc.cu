@@ -11,11 +11,13 @@
 //       128 lanes x 128 columns), so a step never re-streams the 64 KB slice through shared memory
 //     - h_prev: fp16, shared memory (no-swizzle K-major), rewritten every step by all 8 CTAs
 //     - accumulator: tensor memory, NB columns
-//   16 epilogue warps: tcgen05.ld -> + x W_ih^T (precomputed by the GEMM, fp32) -> SFU sigmoid/tanh ->
-//     quad shuffles -> c, h update in fp32 registers -> h to global (fp32) and, as fp16, staged in the
-//     destination layout; 8 threads then push the CTA's contiguous NB*64-byte slice into every peer's
+//   16 epilogue warps: tcgen05.ld -> 4x4 quad shuffle transpose (every thread then owns all four gates of
+//     one (hidden unit, video)) -> + x W_ih^T (precomputed by the GEMM, fp32, one float4) -> cell update on
+//     the SFU with shared denominators (5 ex2 + 2 rcp per cell) in fp32 registers -> h staged as fp16 in
+//     the destination layout; 8 threads then push the CTA's contiguous NB*64-byte slice into every peer's
 //     next-step buffer with cp.async.bulk (DSMEM, async proxy) which complete_tx's the peer's
-//     mbarrier.  No cluster-wide barrier, no generic-proxy remote stores, no fences at cluster scope.
+//     mbarrier, and 4*NB threads write the slice to the fused output with 16-byte stores.
+//     No cluster-wide barrier, no generic-proxy remote stores, no fences at cluster scope.
 //
 // fp16 operands have the same 11-bit significand as tf32 and |h| < 1, so the recurrent matmul
 // carries tf32-level rounding (measured contribution to the final scores: < 3e-5 relative);
@@ -230,67 +232,93 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps
+        // TMEM lane p = 4*jj + gate holds one gate of hidden unit jj for NV videos (columns).  The four
+        // lanes of a quad exchange their values with a 4x4 shuffle transpose, after which lane g owns ALL
+        // four gates of unit jj for video v0 + 4k + g: the cell update runs once per (unit, video) with
+        // no redundant lanes, and the input projection arrives as one float4 per owned video.
         const int q = warp & 3;              // TMEM lane quarter
         const int part = warp >> 2;          // which quarter of the videos
         const int p = q * 32 + lane;         // gate column inside the slice: 4*jj + gate
-        const int gate = p & 3;
+        const int g = p & 3;                 // gate held in TMEM == video-in-block owned after the transpose
         const int jj = p >> 2;
         const int v0 = part * NV;
-        const float* xg = ((ld >> 1) ? xg_a : xg_v) + dir * (4 * HC) + r * COLS + p;
+        const float4* xg4 = reinterpret_cast<const float4*>(((ld >> 1) ? xg_a : xg_v) + dir * (4 * HC) + r * COLS + 4 * jj);
+        constexpr int XG_LD4 = XG_LD / 4;
         const int out_col = ld * HC + r * UNITS;
         const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + v0;
-        const int qbase = lane & ~3;
-        const float act_k = (gate == 2) ? -2.885390082f : -1.442695041f;   // -k * log2(e)
-        const float act_a = (gate == 2) ? 2.0f : 1.0f;
-        const float act_b = (gate == 2) ? -1.0f : 0.0f;
-        // this thread's slot in the staged slice: [jj/8][video][jj%8] halfs
+        const bool par1 = (lane & 1) != 0, par2 = (lane & 2) != 0;
+        // this thread's slot in the staged slice: [jj/8][video][jj%8] 16-bit values
         uint16_t* stage_mine = reinterpret_cast<uint16_t*>(stage16 + (jj >> 3) * S::H_LBO) + (jj & 7);
         float* const fcol = reinterpret_cast<float*>(fused_out) + out_col + jj;
         uint16_t* const fcol_h = reinterpret_cast<uint16_t*>(fused_out) + out_col + jj;
         const bool op_bf16 = op_dtype == DT_BF16;
         const bool lowp_out = out_dtype == op_dtype;   // fused output straight from the staged operand slice
         const int rstep = dir ? -1 : 1;
+        constexpr int NP = NV / 4;             // (unit, video) pairs owned by this thread
+        constexpr float LOG2E = 1.4426950408889634f;
 
-        float c_state[NV], xv0[NV], xv1[NV];   // xv0: this step's input projection, xv1: next step's
-        int len_r[NV], row_r[NV];              // row_r: global row of the frame consumed at step s
+        float c_state[NP];
+        float4 xv0[NP], xv1[NP];               // xv0: this step's input projection, xv1: next step's
+        int len_r[NP], row_r[NP], vid_r[NP];   // row_r: global row of the frame consumed at step s
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            c_state[i] = 0.f;
-            const int len = s_len[v0 + i];
-            len_r[i] = len;
-            row_r[i] = s_row[v0 + i] + (dir ? (len > 0 ? len - 1 : 0) : 0);
-            xv0[i] = len > 0 ? __ldg(xg + static_cast<size_t>(row_r[i]) * XG_LD) : 0.f;
-            xv1[i] = len > 1 ? __ldg(xg + static_cast<size_t>(row_r[i] + rstep) * XG_LD) : 0.f;
+        for (int k = 0; k < NP; ++k) {
+            c_state[k] = 0.f;
+            vid_r[k] = v0 + 4 * k + g;
+            const int len = s_len[vid_r[k]];
+            len_r[k] = len;
+            row_r[k] = s_row[vid_r[k]] + (dir ? (len > 0 ? len - 1 : 0) : 0);
+            xv0[k] = len > 0 ? __ldg(xg4 + static_cast<size_t>(row_r[k]) * XG_LD4) : zero4;
+            xv1[k] = len > 1 ? __ldg(xg4 + static_cast<size_t>(row_r[k] + rstep) * XG_LD4) : zero4;
         }
 
         for (int s = 0; s < maxlen; ++s) {
             // two-step-deep register prefetch of the input projections (DRAM latency >> one step)
-            float xv2[NV];
+            float4 xv2[NP];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                xv2[i] = 0.f;
-                if (s + 2 < len_r[i]) xv2[i] = __ldg(xg + static_cast<size_t>(row_r[i] + 2 * rstep) * XG_LD);
+            for (int k = 0; k < NP; ++k) {
+                xv2[k] = zero4;
+                if (s + 2 < len_r[k]) xv2[k] = __ldg(xg4 + static_cast<size_t>(row_r[k] + 2 * rstep) * XG_LD4);
             }
             mbar_wait(bar_mma, s & 1);
             tc_fence_after();
             uint32_t acc[NV];
             tmem_ld_cols<NV>(taddr, acc);
             tmem_ld_wait();
-            float h_out[NV];
+            float h_out[NP];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const float act = gate_act(__uint_as_float(acc[i]) + xv0[i], act_k, act_a, act_b);
-                const float a_i = __shfl_sync(0xffffffffu, act, qbase + 0);
-                const float a_f = __shfl_sync(0xffffffffu, act, qbase + 1);
-                const float a_g = __shfl_sync(0xffffffffu, act, qbase + 2);
-                const float a_o = __shfl_sync(0xffffffffu, act, qbase + 3);
-                const bool on = s < len_r[i];
-                const float cn = fmaf(a_f, c_state[i], a_i * a_g);
-                const float h = a_o * tanh_sfu(cn);
-                c_state[i] = on ? cn : c_state[i];
-                h_out[i] = h;
-                if (on && gate == 0)   // |h| < 1: no saturation needed
-                    stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + (v0 + i) * 8] =
+            for (int k = 0; k < NP; ++k) {
+                // ---- quad transpose: in a[j] = (gate g, video 4k + j)  ->  out t_j = (gate j, video 4k + g)
+                const float a0 = __uint_as_float(acc[4 * k]), a1 = __uint_as_float(acc[4 * k + 1]);
+                const float a2 = __uint_as_float(acc[4 * k + 2]), a3 = __uint_as_float(acc[4 * k + 3]);
+                const float r0 = __shfl_xor_sync(0xffffffffu, par1 ? a0 : a1, 1);
+                const float r1 = __shfl_xor_sync(0xffffffffu, par1 ? a2 : a3, 1);
+                const float n0 = par1 ? r0 : a0, n1 = par1 ? a1 : r0, n2 = par1 ? r1 : a2, n3 = par1 ? a3 : r1;
+                const float u0 = __shfl_xor_sync(0xffffffffu, par2 ? n0 : n2, 2);
+                const float u1 = __shfl_xor_sync(0xffffffffu, par2 ? n1 : n3, 2);
+                const float t_i = (par2 ? u0 : n0) + xv0[k].x;
+                const float t_f = (par2 ? u1 : n1) + xv0[k].y;
+                const float t_g = (par2 ? n2 : u0) + xv0[k].z;
+                const float t_o = (par2 ? n3 : u1) + xv0[k].w;
+                // ---- LSTM cell on the SFU with shared denominators (5 ex2 + 2 rcp per cell):
+                //   sigmoid(x) = 1 / (1 + e^-x),  tanh(x) = (1 - e^-2x) / (1 + e^-2x)
+                //   c' = sig(f) c + sig(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ei)(1+eg)(1+ef)]
+                //   h  = sig(o) tanh(c')           = (1-ec) / [(1+eo)(1+ec)]
+                // arguments clamped so that the products stay far inside fp32 (sigmoid(-25) = 1.4e-11).
+                const float ei = ex2_approx(fminf(fmaxf(t_i, -25.f), 25.f) * -LOG2E);
+                const float ef = ex2_approx(fminf(fmaxf(t_f, -25.f), 25.f) * -LOG2E);
+                const float eg = ex2_approx(fminf(fmaxf(t_g, -12.5f), 12.5f) * (-2.f * LOG2E));
+                const float eo = ex2_approx(fminf(fmaxf(t_o, -25.f), 25.f) * -LOG2E);
+                const float A = (1.f + ei) * (1.f + eg);
+                const float opf = 1.f + ef;
+                const float cn = fmaf(c_state[k], A, (1.f - eg) * opf) * rcp_approx(A * opf);
+                const float ec = ex2_approx(fminf(fmaxf(cn, -12.5f), 12.5f) * (-2.f * LOG2E));
+                const float h = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));
+                const bool on = s < len_r[k];
+                c_state[k] = on ? cn : c_state[k];
+                h_out[k] = h;
+                if (on)   // |h| < 1: no saturation needed
+                    stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + vid_r[k] * 8] =
                         op_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(h)) : __half_as_ushort(__float2half_rn(h));
             }
             fence_proxy_async();   // staged h (generic proxy) -> visible to the bulk-copy engine
@@ -321,17 +349,17 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 }
             }
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const bool on = s < len_r[i];
-                if (!lowp_out && on && gate == 0) {
+            for (int k = 0; k < NP; ++k) {
+                const bool on = s < len_r[k];
+                if (!lowp_out && on) {
                     if (out_dtype != DT_F32)
-                        fcol_h[static_cast<size_t>(row_r[i]) * FUSED_LD] = to_lowp_bits(h_out[i], out_dtype);
+                        fcol_h[static_cast<size_t>(row_r[k]) * FUSED_LD] = to_lowp_bits(h_out[k], out_dtype);
                     else
-                        fcol[static_cast<size_t>(row_r[i]) * FUSED_LD] = round_tf32 ? to_tf32_rn(h_out[i]) : h_out[i];
+                        fcol[static_cast<size_t>(row_r[k]) * FUSED_LD] = round_tf32 ? to_tf32_rn(h_out[k]) : h_out[k];
                 }
-                row_r[i] += on ? rstep : 0;
-                xv0[i] = xv1[i];
-                xv1[i] = xv2[i];
+                row_r[k] += on ? rstep : 0;
+                xv0[k] = xv1[k];
+                xv1[k] = xv2[k];
             }
         }
     }
