@@ -26,7 +26,7 @@ EXPORTS = [
     "avs_last_error", "avs_version", "avs_device_ok", "avs_model_create", "avs_model_update",
     "avs_model_destroy", "avs_forward", "avs_summarize", "avs_linear", "avs_bilstm_pair",
     "avs_attention", "avs_temporal_f1", "avs_launch_count", "avs_profile", "avs_profile_stages",
-    "avs_profile_stage_name", "avs_profile_read",
+    "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace",
 ]
 
 

@@ -311,12 +311,13 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
     LstmPlan p;
     const int B = static_cast<int>(order.size());
     if (B == 0) return p;
-    // one wave = 16 clusters of 8 CTAs (4 recurrences x 4 groups); the tensor-core kernel pads the
-    // video dimension of its MMA to 16 / 32 / 64
+    // one wave = 16 clusters of 8 CTAs (4 recurrences x 4 groups) with one CTA per SM; the tensor-core kernel
+    // also has an 8-slot variant whose CTAs are small enough for two per SM (32 clusters per wave), so that
+    // one cluster's DSMEM exchange overlaps another's MMA + cell math on the same SM
     if (tensor_core) {
         p.nb = 64;
-        for (int nb : {16, 32, 64}) {
-            if (((B + nb - 1) / nb) * 4 <= 16) { p.nb = nb; break; }
+        for (int nb : {8, 16, 32, 64}) {
+            if (((B + nb - 1) / nb) * 4 <= (nb == 8 ? 32 : 16)) { p.nb = nb; break; }
         }
     } else {
         p.nb = 16;
@@ -389,6 +390,15 @@ void avs_profile_read(double* ms, int64_t* calls) {
         if (ms) ms[i] = g_prof.ms[i];
         if (calls) calls[i] = g_prof.calls[i];
     }
+}
+
+/* Debugging aid (not part of the reference surface): with AVS_LSTM_TRACE=1 in the environment the NB=16
+ * recurrence kernel accumulates clock64 deltas of its per-step dependency chain on cluster 0 / CTA 0:
+ * [0] h landed -> MMAs issued, [1] -> epilogue awake, [2] tcgen05.ld, [3] cell math + staging,
+ * [4] fence + barrier, [5] bulk-copy issue, [6] copies issued -> next h landed, [7] steps. */
+avs_status avs_debug_lstm_trace(uint64_t* out8) {
+    AVS_CHECK(out8 != nullptr, AVS_ERR_INVALID, "null pointer");
+    return lstm_trace_read(reinterpret_cast<unsigned long long*>(out8));
 }
 
 int avs_device_ok(void) {

@@ -106,9 +106,11 @@ avs_status lstm_recurrence(const float* xg_v, const float* xg_a, const float* wh
                            float* fused, int round_tf32, void* fused_lowp, int lowp_dtype, cudaStream_t stream);
 
 // tcgen05 version (16-bit operands: op_dtype = DT_F16 or DT_BF16; fp32 accumulate / state); batch.nb must be
-// 16, 32 or 64.  fused output: fp32 (optionally tf32-rounded), fp16 or bf16 (out_dtype).
+// 8 (two CTAs per SM), 16, 32 or 64.  fused output: fp32 (optionally tf32-rounded), fp16 or bf16 (out_dtype).
 avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
                               int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream);
+
+avs_status lstm_trace_read(unsigned long long* out8);   // AVS_LSTM_TRACE=1 debugging aid
 
 // ---- attention core -------------------------------------------------------------
 struct SeqDesc {  // device arrays [n_seqs]

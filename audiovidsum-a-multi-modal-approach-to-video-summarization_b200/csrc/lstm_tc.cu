@@ -23,6 +23,7 @@
 // carries tf32-level rounding (measured contribution to the final scores: < 3e-5 relative);
 // cell state, gate math and accumulation stay fp32.  Latency bound: ~T dependent steps.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -39,9 +40,10 @@ constexpr int UNITS = HC / CL;      // 32 hidden units per CTA
 constexpr int COLS = 4 * UNITS;     // 128 gate columns per CTA
 constexpr int XG_LD = 2 * 4 * HC;   // 2048
 constexpr int FUSED_LD = 4 * HC;    // 1024
-constexpr int EPI_WARPS = 16;       // 4 warps per TMEM lane quarter, each owning NB/4 videos
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = EPI_THREADS + 32;  // + one MMA-issuing warp
+// Epilogue warps come in "parts" of 4 (one warp per TMEM lane quarter); every part owns NB/4 video slots.
+// PARTS = 4: all NB slots are real videos, one CTA per SM.  PARTS = 2 (NB = 16 only): 8 real videos per
+// cluster (the other 8 MMA columns are padding), 9 warps and 256 TMEM columns per CTA, so TWO CTAs of
+// different clusters share an SM and one cluster's DSMEM exchange overlaps the other's MMA + cell math.
 constexpr int W_TMEM_COLS = HC / 2;        // W_hh slice as packed fp16 pairs: 128 columns
 
 template <int NB>
@@ -75,7 +77,35 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uin
         "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
         : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+// 16-byte store into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16) (release at
+// cluster scope) when the data has landed.
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, const uint4& v, uint32_t mbar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     dst_cluster_addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster_addr)
+                 : "memory");
+}
+// mbarrier wait with acquire at cluster scope (pairs with the release of remote st.async complete_tx)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > AVS_SPIN_LIMIT) {
+            printf("avsum_b200: lstm h-exchange wait timed out (block %d parity %u)\n", blockIdx.x, parity);
+            __trap();
+        }
+    }
+}
 
 // K-major, no swizzle: start address, LBO = K-direction core-matrix stride, SBO = 8-row-group stride.
 __device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -135,12 +165,24 @@ __device__ __forceinline__ float tanh_sfu(float x) {
     return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(x * -2.885390082f)), -1.0f);
 }
 
-template <int NB>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+// Optional phase trace (AVS_LSTM_TRACE=1, debugging aid): cluster 0 / CTA 0 accumulates clock64 deltas of the
+// per-step dependency chain; read back with avs_debug_lstm_trace().
+__device__ unsigned long long g_lstm_trace[8];
+__device__ __forceinline__ long long clk64() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
+
+template <int NB, int PARTS, bool TRACE>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PARTS * 128 + 32, PARTS == 2 ? 2 : 1)
 lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
                LstmBatch batch, int op_dtype, void* __restrict__ fused_out, int out_dtype, int round_tf32) {
     using S = Smem<NB>;
-    constexpr int NV = NB / 4;  // videos per epilogue thread (four warps share a TMEM lane quarter)
+    constexpr int NV = NB / 4;             // video slots per part
+    constexpr int SLOTS = NV * PARTS;      // real video slots of this cluster (batch.nb)
+    constexpr int EPI_WARPS = 4 * PARTS;
+    constexpr int THREADS = EPI_WARPS * 32 + 32;   // + one MMA-issuing warp
     cg::cluster_group cluster = cg::this_cluster();
     const int r = static_cast<int>(cluster.block_rank());
     const int cid = blockIdx.x / CL;
@@ -161,11 +203,14 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     uint64_t* bar_h = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);  // [2]
     uint64_t* bar_mma = bar_h + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    __shared__ volatile long long tr_ts[2];   // [0] MMA commit issued, [1] bulk copies issued (TRACE only)
+    const bool tracing = TRACE && blockIdx.x == 0;
+    long long tr_acc[7] = {0, 0, 0, 0, 0, 0, 0};
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid < NB) {
-        s_len[tid] = batch.slot_len[grp * NB + tid];
-        s_row[tid] = batch.slot_row_start[grp * NB + tid];
+        s_len[tid] = tid < SLOTS ? batch.slot_len[grp * SLOTS + tid] : 0;
+        s_row[tid] = tid < SLOTS ? batch.slot_row_start[grp * SLOTS + tid] : 0;
     }
     for (int i = tid; i < (2 * S::H_BYTES + 2 * S::SLICE_BYTES) / 16; i += THREADS)
         reinterpret_cast<uint4*>(h_sm)[i] = make_uint4(0, 0, 0, 0);   // h buffers + stage (contiguous)
@@ -190,18 +235,21 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     if (warp < EPI_WARPS) {
         // W_hh slice -> tensor memory, resident for the whole kernel.  A-operand layout of
         // kind::f16 with M = 128: lane = row (gate column), 32-bit column c holds k = 2c, 2c+1.
-        const int q = warp & 3, part = warp >> 2;          // lane quarter, 32-column part of the row
+        const int q = warp & 3;                            // lane quarter
         const int row = q * 32 + lane;
-        const float4* src = reinterpret_cast<const float4*>(
-            whh + (static_cast<size_t>(ld) * 4 * HC + r * COLS + row) * HC + part * 64);
-        uint32_t pk[32];
+#pragma unroll 1
+        for (int cpart = warp >> 2; cpart < 4; cpart += PARTS) {   // 32-column (64 k) part of the row
+            const float4* src = reinterpret_cast<const float4*>(
+                whh + (static_cast<size_t>(ld) * 4 * HC + r * COLS + row) * HC + cpart * 64);
+            uint32_t pk[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 v = __ldg(src + i);
-            pk[2 * i] = pack_lowp2(v.x, v.y, op_dtype);
-            pk[2 * i + 1] = pack_lowp2(v.z, v.w, op_dtype);
+            for (int i = 0; i < 16; ++i) {
+                const float4 v = __ldg(src + i);
+                pk[2 * i] = pack_lowp2(v.x, v.y, op_dtype);
+                pk[2 * i + 1] = pack_lowp2(v.z, v.w, op_dtype);
+            }
+            tmem_st_32x32(tmem_w + (static_cast<uint32_t>(q * 32) << 16) + cpart * 32, pk);
         }
-        tmem_st_32x32(tmem_w + (static_cast<uint32_t>(q * 32) << 16) + part * 32, pk);
         tmem_st_wait();
     }
     tc_fence_before();
@@ -217,9 +265,17 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
             for (int s = 0; s < maxlen; ++s) {
                 const int b = s & 1;
                 // arm the barrier that will collect h_{s+1}: 8 peers x SLICE_BYTES, one local arrival
-                if (s + 1 < maxlen) mbar_expect_tx(bar_h + (b ^ 1), CL * S::SLICE_BYTES);
-                if (s > 0) mbar_wait(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
+                if (s + 1 < maxlen) mbar_expect_tx(bar_h + (b ^ 1), CL * SLOTS * 64);   // 8 peers x 64 B per real video slot
+                if (s > 0) {
+                    mbar_wait_cluster(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
+                    fence_proxy_async();   // peers' st.async (generic proxy) -> visible to the tensor core's reads
+                }
                 tc_fence_after();
+                long long tA = 0;
+                if (tracing) {
+                    tA = clk64();
+                    if (s > 0) tr_acc[6] += tA - tr_ts[1];   // copies issued -> all 8 slices of h landed
+                }
                 const uint32_t h_addr = smem_u32(h_sm + b * S::H_BYTES);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {  // K = 256 = 16 x 16; A from TMEM (8 columns per K step)
@@ -227,6 +283,16 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                     umma_f16_ts(tmem_d, tmem_w + k * 8, bd, idesc, k != 0);
                 }
                 tc_commit(bar_mma);
+                if (tracing) {
+                    const long long tB = clk64();
+                    tr_ts[0] = tB;
+                    tr_acc[0] += tB - tA;                     // h landed -> 16 MMAs + commit issued
+                }
+            }
+            if (tracing) {
+                g_lstm_trace[0] = tr_acc[0];
+                g_lstm_trace[6] = tr_acc[6];
+                g_lstm_trace[7] = maxlen;
             }
         }
         __syncwarp();
@@ -256,6 +322,13 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         const int rstep = dir ? -1 : 1;
         constexpr int NP = NV / 4;             // (unit, video) pairs owned by this thread
         constexpr float LOG2E = 1.4426950408889634f;
+        // h exchange, warp-local: this warp produces the 16-byte chunks (8 hidden units of chunk q) of videos
+        // v0 .. v0+NV-1.  After a __syncwarp lane l sends chunk (video v0 + 4k + (l >> 3)) to peer CTA (l & 7)
+        // with one st.async: 4 videos x 8 peers = 32 lanes.  No CTA-wide barrier, no bulk-copy engine.
+        const uint32_t peer = lane & 7, cvid = lane >> 3;
+        const uint32_t stage_rd = smem_u32(stage16) + q * S::H_LBO + (v0 + cvid) * 16;     // + k*64, + slot
+        const uint32_t remote_h = mapa(smem_u32(h_sm) + (r * 4 + q) * S::H_LBO + (v0 + cvid) * 16, peer);
+        const uint32_t remote_bar = mapa(smem_u32(bar_h), peer);
 
         float c_state[NP];
         float4 xv0[NP], xv1[NP];               // xv0: this step's input projection, xv1: next step's
@@ -282,9 +355,18 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
             }
             mbar_wait(bar_mma, s & 1);
             tc_fence_after();
+            long long tC = 0, tD = 0;
+            if (tracing && tid == 0) {
+                tC = clk64();
+                tr_acc[1] += tC - tr_ts[0];                   // commit issued -> epilogue awake (MMA latency)
+            }
             uint32_t acc[NV];
             tmem_ld_cols<NV>(taddr, acc);
             tmem_ld_wait();
+            if (tracing && tid == 0) {
+                tD = clk64();
+                tr_acc[2] += tD - tC;                         // tcgen05.ld
+            }
             float h_out[NP];
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
@@ -321,30 +403,44 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                     stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + vid_r[k] * 8] =
                         op_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(h)) : __half_as_ushort(__float2half_rn(h));
             }
-            fence_proxy_async();   // staged h (generic proxy) -> visible to the bulk-copy engine
-            tc_fence_before();
-            epi_bar_sync();        // whole slice staged; all TMEM reads of this step done
-            if (s + 1 < maxlen && tid < CL) {
-                const int nb = (s + 1) & 1;
-                const uint32_t dst = smem_u32(h_sm + nb * S::H_BYTES) + r * S::SLICE_BYTES;
-                bulk_copy_to_peer(mapa(dst, tid), smem_u32(stage16) + (s & 1) * S::SLICE_BYTES, S::SLICE_BYTES,
-                                  mapa(smem_u32(bar_h + nb), tid));
+            long long tE = 0, tF = 0;
+            if (tracing && tid == 0) {
+                tE = clk64();
+                tr_acc[3] += tE - tD;                         // transpose + cell math + stage write
             }
-            // h -> global fused output (off the critical path)
-            if (lowp_out) {
-                // 16-bit output in the operand format: the staged slice already holds it.  One 16-byte store
-                // per (video, 8 hidden units): 4 lanes cover this CTA's 64 contiguous bytes of a fused row.
-                // (slot s&1 is rewritten at step s+2, which every thread reaches only after the step s+1
-                // barrier, i.e. after these reads)
-                if (tid < NB * 4) {
-                    const int v = tid >> 2, ch = tid & 3;
+            tc_fence_before();     // this warp's TMEM reads of the step are complete
+            __syncwarp();          // the warp's chunks are staged
+            if (tracing && tid == 0) {
+                tF = clk64();
+                tr_acc[4] += tF - tE;                         // warp sync
+            }
+            uint4 hv[NP];
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(hv[k].x), "=r"(hv[k].y), "=r"(hv[k].z), "=r"(hv[k].w)
+                             : "r"(stage_rd + (s & 1) * S::SLICE_BYTES + k * 64));
+                if (s + 1 < maxlen) {
+                    const uint32_t nb = (s + 1) & 1;
+                    st_async_v4(remote_h + nb * S::H_BYTES + k * 64, hv[k], remote_bar + nb * 8);
+                }
+            }
+            if (tracing && tid == 0) {
+                const long long tG = clk64();
+                tr_ts[1] = tG;
+                tr_acc[5] += tG - tF;                         // ld.shared + st.async issue
+            }
+            // h -> global fused output (off the critical path).  16-bit output in the operand format: the chunk
+            // this lane just read is exactly 16 contiguous bytes of a fused row; the lanes with peer == 0 store it.
+            if (lowp_out && peer == 0) {
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const int v = v0 + 4 * k + cvid;
                     const int len = s_len[v];
                     if (s < len) {
-                        const uint4 hv = *reinterpret_cast<const uint4*>(stage16 + (s & 1) * S::SLICE_BYTES +
-                                                                         ch * S::H_LBO + v * 16);
                         const int row = s_row[v] + (dir ? len - 1 - s : s);
                         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(fused_out) +
-                                                  static_cast<size_t>(row) * FUSED_LD + out_col + ch * 8) = hv;
+                                                  static_cast<size_t>(row) * FUSED_LD + out_col + q * 8) = hv[k];
                     }
                 }
             }
@@ -362,6 +458,8 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 xv1[k] = xv2[k];
             }
         }
+        if (tracing && tid == 0)
+            for (int i = 1; i <= 5; ++i) g_lstm_trace[i] = tr_acc[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -369,31 +467,40 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
-template <int NB>
+template <int NB, int PARTS>
 avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, int op_dtype,
                      void* fused, int out_dtype, int round_tf32, cudaStream_t stream) {
-    auto kern = lstm_tc_kernel<NB>;
+    static const bool trace = getenv("AVS_LSTM_TRACE") != nullptr;
+    auto kern = trace ? lstm_tc_kernel<NB, PARTS, NB == 16> : lstm_tc_kernel<NB, PARTS, false>;
     static bool configured = false;
     if (!configured) {
         AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NB>::TOTAL));
         configured = true;
     }
-    kern<<<batch.n_groups * 4 * CL, THREADS, Smem<NB>::TOTAL, stream>>>(xg_v, xg_a, whh, batch, op_dtype, fused,
-                                                                        out_dtype, round_tf32);
+    kern<<<batch.n_groups * 4 * CL, PARTS * 128 + 32, Smem<NB>::TOTAL, stream>>>(xg_v, xg_a, whh, batch, op_dtype,
+                                                                                 fused, out_dtype, round_tf32);
     AVS_LAUNCH_CHECK();
     return AVS_OK;
 }
 
 }  // namespace
 
+// debugging aid: the phase trace of the last traced launch (8 values, see g_lstm_trace)
+avs_status lstm_trace_read(unsigned long long* out8) {
+    AVS_CUDA(cudaDeviceSynchronize());
+    AVS_CUDA(cudaMemcpyFromSymbol(out8, g_lstm_trace, 8 * sizeof(unsigned long long)));
+    return AVS_OK;
+}
+
 avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
                               int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream) {
     if (batch.n_groups == 0) return AVS_OK;
     AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
-    switch (batch.nb) {
-        case 16: return launch_tc<16>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
-        case 32: return launch_tc<32>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
-        case 64: return launch_tc<64>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
+    switch (batch.nb) {   // video slots per cluster
+        case 8: return launch_tc<16, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
+        case 16: return launch_tc<16, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
+        case 32: return launch_tc<32, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
+        case 64: return launch_tc<64, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
         default: set_error("lstm_tc: unsupported videos-per-cluster %d", batch.nb); return AVS_ERR_INVALID;
     }
 }

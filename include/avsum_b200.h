@@ -154,6 +154,12 @@ int avs_profile_stages(void);
 const char* avs_profile_stage_name(int stage);
 void avs_profile_read(double* ms, int64_t* calls);
 
+/* Debugging aid (no reference counterpart): phase trace of the tensor-core LSTM recurrence, filled when the
+ * environment variable AVS_LSTM_TRACE is set.  out8[0..6] = summed clock64 deltas of the per-step chain
+ * (h landed -> MMAs issued -> epilogue awake -> tcgen05.ld -> cell math -> fence+barrier -> copies issued ->
+ * next h landed), out8[7] = number of steps. */
+avs_status avs_debug_lstm_trace(uint64_t* out8);
+
 #ifdef __cplusplus
 }
 #endif
