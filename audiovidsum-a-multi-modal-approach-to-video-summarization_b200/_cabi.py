@@ -27,6 +27,7 @@ EXPORTS = [
     "avs_model_destroy", "avs_forward", "avs_summarize", "avs_linear", "avs_bilstm_pair",
     "avs_attention", "avs_temporal_f1", "avs_launch_count", "avs_profile", "avs_profile_stages",
     "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace",
+    "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
 ]
 
 
@@ -102,6 +103,16 @@ def lib() -> C.CDLL:
     L.avs_attention.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, C.c_int, vp, vp]
     L.avs_temporal_f1.restype = C.c_int
     L.avs_temporal_f1.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    L.avs_eval_metrics.restype = C.c_int
+    L.avs_eval_metrics.argtypes = [vp, vp, C.c_int, i32, vp, vp, vp, vp, C.c_int, vp]
+    L.avs_cdist.restype = C.c_int
+    L.avs_cdist.argtypes = [vp, vp, i32, i32, i32, vp, C.c_int, vp]
+    L.avs_interpolate.restype = C.c_int
+    L.avs_interpolate.argtypes = [vp, i64, i32, vp, vp, i32, vp, C.c_int, vp]
+    L.avs_dtw_path.restype = C.c_int
+    L.avs_dtw_path.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.avs_debug_lstm_trace.restype = C.c_int
+    L.avs_debug_lstm_trace.argtypes = [vp]
     L.avs_profile.restype = None
     L.avs_profile.argtypes = [C.c_int]
     L.avs_profile_stages.restype = C.c_int

@@ -991,4 +991,167 @@ avs_status avs_temporal_f1(const int32_t* pred, const int32_t* pred_start, const
     return s;
 }
 
+// ---- scripts/evaluate.py:25-36 metric block for a batch of videos ----------------------------------
+avs_status avs_eval_metrics(const float* pred, const void* target, int target_is_f64, int32_t n_videos,
+                            const int32_t* row_start, const int32_t* lengths, double* metrics, int64_t* counts,
+                            int space, void* cuda_stream) {
+    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
+    AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
+    if (n_videos == 0) return AVS_OK;
+    AVS_CHECK(pred && target && row_start && lengths && metrics && counts, AVS_ERR_INVALID,
+              "avs_eval_metrics: null pointer");
+    int64_t rows = 0;
+    for (int v = 0; v < n_videos; ++v) {
+        AVS_CHECK(row_start[v] >= 0 && lengths[v] >= 0, AVS_ERR_INVALID, "video %d: bad row range", v);
+        rows = std::max<int64_t>(rows, static_cast<int64_t>(row_start[v]) + lengths[v]);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t tsz = target_is_f64 ? 8 : 4;
+    const size_t n = static_cast<size_t>(n_videos);
+    // one async allocation: descriptors | (host space: pred, target copies, outputs)
+    size_t bytes = align_up(2 * n * 4, 256);
+    const size_t off_pred = bytes;
+    if (space == AVS_HOST) bytes += align_up(rows * 4, 256);
+    const size_t off_tgt = bytes;
+    if (space == AVS_HOST) bytes += align_up(rows * tsz, 256);
+    const size_t off_f = bytes;
+    if (space == AVS_HOST) bytes += align_up(n * 4 * 8, 256);
+    const size_t off_i = bytes;
+    if (space == AVS_HOST) bytes += align_up(n * 8 * 8, 256);
+    char* dev = nullptr;
+    AVS_CUDA(cudaMallocAsync(&dev, bytes, st));
+    int32_t* desc = reinterpret_cast<int32_t*>(dev);
+    avs_status s = AVS_OK;
+    auto fail = [&](cudaError_t e) {
+        if (e != cudaSuccess && s == AVS_OK) {
+            set_error("avs_eval_metrics: %s", cudaGetErrorString(e));
+            s = AVS_ERR_CUDA;
+        }
+    };
+    fail(cudaMemcpyAsync(desc, row_start, n * 4, cudaMemcpyHostToDevice, st));
+    fail(cudaMemcpyAsync(desc + n, lengths, n * 4, cudaMemcpyHostToDevice, st));
+    const float* p_dev = pred;
+    const void* t_dev = target;
+    double* f_dev = metrics;
+    long long* i_dev = reinterpret_cast<long long*>(counts);
+    if (space == AVS_HOST) {
+        fail(cudaMemcpyAsync(dev + off_pred, pred, rows * 4, cudaMemcpyHostToDevice, st));
+        fail(cudaMemcpyAsync(dev + off_tgt, target, rows * tsz, cudaMemcpyHostToDevice, st));
+        p_dev = reinterpret_cast<const float*>(dev + off_pred);
+        t_dev = dev + off_tgt;
+        f_dev = reinterpret_cast<double*>(dev + off_f);
+        i_dev = reinterpret_cast<long long*>(dev + off_i);
+    }
+    if (s == AVS_OK) s = eval_metrics_device(p_dev, t_dev, target_is_f64, desc, desc + n, n_videos, f_dev, i_dev, st);
+    if (s == AVS_OK && space == AVS_HOST) {
+        fail(cudaMemcpyAsync(metrics, f_dev, n * 4 * 8, cudaMemcpyDeviceToHost, st));
+        fail(cudaMemcpyAsync(counts, i_dev, n * 8 * 8, cudaMemcpyDeviceToHost, st));
+        fail(cudaStreamSynchronize(st));
+    }
+    cudaFreeAsync(dev, st);
+    return s;
+}
+
+// ---- features/fusion.py helpers -------------------------------------------------------------------
+avs_status avs_cdist(const float* a, const float* b, int32_t na, int32_t nb, int32_t D, double* out, int space,
+                     void* cuda_stream) {
+    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
+    AVS_CHECK(na >= 0 && nb >= 0 && D >= 0, AVS_ERR_INVALID, "avs_cdist: negative size");
+    if (na == 0 || nb == 0) return AVS_OK;
+    AVS_CHECK(a && b && out, AVS_ERR_INVALID, "avs_cdist: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (space == AVS_DEVICE) return cdist_device(a, b, na, nb, D, out, st);
+    const size_t ba = align_up(static_cast<size_t>(na) * D * 4, 256), bb = align_up(static_cast<size_t>(nb) * D * 4, 256);
+    const size_t bo = static_cast<size_t>(na) * nb * 8;
+    char* dev = nullptr;
+    AVS_CUDA(cudaMallocAsync(&dev, ba + bb + bo + 256, st));
+    avs_status s = AVS_OK;
+    cudaError_t e = cudaMemcpyAsync(dev, a, static_cast<size_t>(na) * D * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dev + ba, b, static_cast<size_t>(nb) * D * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        s = cdist_device(reinterpret_cast<float*>(dev), reinterpret_cast<float*>(dev + ba), na, nb, D,
+                         reinterpret_cast<double*>(dev + ba + bb), st);
+    if (e == cudaSuccess && s == AVS_OK) e = cudaMemcpyAsync(out, dev + ba + bb, bo, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && s == AVS_OK) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        set_error("avs_cdist: %s", cudaGetErrorString(e));
+        s = AVS_ERR_CUDA;
+    }
+    cudaFreeAsync(dev, st);
+    return s;
+}
+
+avs_status avs_interpolate(const float* features, int64_t n_rows, int32_t D, const int32_t* idx, const float* weights,
+                           int32_t U, float* out, int space, void* cuda_stream) {
+    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
+    AVS_CHECK(n_rows >= 0 && D >= 0 && U >= 0, AVS_ERR_INVALID, "avs_interpolate: negative size");
+    if (U == 0 || D == 0) return AVS_OK;
+    AVS_CHECK(features && idx && weights && out, AVS_ERR_INVALID, "avs_interpolate: null pointer");
+    for (int k = 0; k < U; ++k)
+        AVS_CHECK(idx[k] >= 0 && idx[k] < n_rows, AVS_ERR_INVALID, "avs_interpolate: index %d = %d outside [0, %lld)", k,
+                  idx[k], static_cast<long long>(n_rows));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t b_idx = align_up(static_cast<size_t>(U) * 4, 256);
+    const size_t b_feat = space == AVS_HOST ? align_up(static_cast<size_t>(n_rows) * D * 4, 256) : 0;
+    const size_t b_out = space == AVS_HOST ? static_cast<size_t>(U) * D * 4 : 0;
+    char* dev = nullptr;
+    AVS_CUDA(cudaMallocAsync(&dev, 2 * b_idx + b_feat + b_out + 256, st));
+    avs_status s = AVS_OK;
+    cudaError_t e = cudaMemcpyAsync(dev, idx, static_cast<size_t>(U) * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dev + b_idx, weights, static_cast<size_t>(U) * 4, cudaMemcpyHostToDevice, st);
+    const float* f_dev = features;
+    float* o_dev = out;
+    if (space == AVS_HOST) {
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dev + 2 * b_idx, features, static_cast<size_t>(n_rows) * D * 4, cudaMemcpyHostToDevice, st);
+        f_dev = reinterpret_cast<float*>(dev + 2 * b_idx);
+        o_dev = reinterpret_cast<float*>(dev + 2 * b_idx + b_feat);
+    }
+    if (e == cudaSuccess)
+        s = gather_scale_device(f_dev, reinterpret_cast<int32_t*>(dev), reinterpret_cast<float*>(dev + b_idx), U, D, o_dev, st);
+    if (space == AVS_HOST && e == cudaSuccess && s == AVS_OK) {
+        e = cudaMemcpyAsync(out, o_dev, b_out, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) {
+        set_error("avs_interpolate: %s", cudaGetErrorString(e));
+        s = AVS_ERR_CUDA;
+    }
+    cudaFreeAsync(dev, st);
+    return s;
+}
+
+avs_status avs_dtw_path(const double* cost, int32_t n, int32_t m, int32_t* path, int32_t* path_len, double* total,
+                        void* cuda_stream) {
+    AVS_CHECK(cost && path && path_len && total, AVS_ERR_INVALID, "avs_dtw_path: null pointer");
+    AVS_CHECK(n > 0 && m > 0, AVS_ERR_INVALID, "avs_dtw_path: the cost matrix must be non-empty (got %d x %d)", n, m);
+    AVS_CHECK(static_cast<int64_t>(n) * m < (1ll << 31), AVS_ERR_UNSUPPORTED, "avs_dtw_path: matrix too large");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t cells = static_cast<size_t>(n) * m;
+    const size_t b_cost = align_up(cells * 8, 256), b_choice = align_up(cells, 256);
+    const size_t b_path = align_up(static_cast<size_t>(n + m) * 2 * 4, 256);
+    char* dev = nullptr;
+    AVS_CUDA(cudaMallocAsync(&dev, 2 * b_cost + b_choice + b_path + 512, st));
+    double* d_cost = reinterpret_cast<double*>(dev);
+    double* d_acc = reinterpret_cast<double*>(dev + b_cost);
+    uint8_t* d_choice = reinterpret_cast<uint8_t*>(dev + 2 * b_cost);
+    int32_t* d_path = reinterpret_cast<int32_t*>(dev + 2 * b_cost + b_choice);
+    int32_t* d_len = reinterpret_cast<int32_t*>(dev + 2 * b_cost + b_choice + b_path);
+    double* d_total = reinterpret_cast<double*>(dev + 2 * b_cost + b_choice + b_path + 256);
+    avs_status s = AVS_OK;
+    cudaError_t e = cudaMemcpyAsync(d_cost, cost, cells * 8, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) s = dtw_device(d_cost, n, m, d_acc, d_choice, d_path, d_len, d_total, st);
+    if (e == cudaSuccess && s == AVS_OK) e = cudaMemcpyAsync(path_len, d_len, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && s == AVS_OK) e = cudaMemcpyAsync(total, d_total, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && s == AVS_OK)
+        e = cudaMemcpyAsync(path, d_path, static_cast<size_t>(n + m - 1) * 2 * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && s == AVS_OK) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        set_error("avs_dtw_path: %s", cudaGetErrorString(e));
+        s = AVS_ERR_CUDA;
+    }
+    cudaFreeAsync(dev, st);
+    return s;
+}
+
 }  // extern "C"

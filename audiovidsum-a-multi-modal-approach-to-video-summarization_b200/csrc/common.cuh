@@ -150,4 +150,14 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
 avs_status temporal_f1_device(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
                               const int32_t* gt_start, int n, double* f1_dev, cudaStream_t stream);
 
+// ---- evaluation metrics / fusion helpers (metrics.cu) -------------------------------------------
+avs_status eval_metrics_device(const float* pred, const void* target, int tgt_f64, const int32_t* row_start,
+                               const int32_t* lengths, int n_videos, double* out_f, long long* out_i,
+                               cudaStream_t stream);
+avs_status cdist_device(const float* a, const float* b, int na, int nb, int D, double* out, cudaStream_t stream);
+avs_status gather_scale_device(const float* feat, const int32_t* idx, const float* w, int U, int D, float* out,
+                               cudaStream_t stream);
+avs_status dtw_device(const double* cost, int n, int m, double* acc, uint8_t* choice, int32_t* path, int32_t* path_len,
+                      double* total, cudaStream_t stream);
+
 }  // namespace avs

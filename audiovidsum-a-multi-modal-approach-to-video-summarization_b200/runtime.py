@@ -210,3 +210,89 @@ def temporal_f1_batch(pred_lists: Sequence[Sequence[Tuple[int, int]]], gt_lists:
     _cabi.check(_cabi.lib().avs_temporal_f1(_cabi.np_ptr(pred), _cabi.np_ptr(ps), _cabi.np_ptr(gt), _cabi.np_ptr(gs),
                                             n, _cabi.np_ptr(out), _stream_ptr(dev)))
     return out
+
+
+# ---- evaluate() metric block and features/fusion.py helpers -------------------------------------
+
+def eval_metrics_rows(pred: torch.Tensor, target: torch.Tensor, row_start, lengths):
+    """Batched scripts/evaluate.py:25-36 on the GPU.
+
+    pred fp32 [rows], target fp32 / fp64 [rows] -- both on the GPU or both on the host -- and the usual
+    (row_start, lengths) descriptors.  Returns (metrics float64 [n, 4] = f1, spearman, kendall, mean(pred);
+    counts int64 [n, 8]) as numpy arrays.
+    """
+    _require_cuda()
+    rs, ln = _i32(row_start), _i32(lengths)
+    n = int(rs.size)
+    if pred.device != target.device:
+        raise ValueError("pred and target must live on the same device")
+    pred = pred.to(torch.float32).contiguous()
+    if target.dtype not in (torch.float32, torch.float64):
+        target = target.to(torch.float64)       # integer annotations compare like float64 in numpy
+    target = target.contiguous()
+    if pred.numel() != target.numel():
+        raise ValueError("pred and target must have the same number of rows")
+    on_gpu = pred.is_cuda
+    dev = pred.device if on_gpu else torch.device("cuda", torch.cuda.current_device())
+    metrics = torch.empty(n, 4, dtype=torch.float64, device=pred.device)
+    counts = torch.empty(n, 8, dtype=torch.int64, device=pred.device)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().avs_eval_metrics(
+            C.c_void_p(pred.data_ptr()), C.c_void_p(target.data_ptr()), int(target.dtype == torch.float64), n,
+            _cabi.np_ptr(rs), _cabi.np_ptr(ln), C.c_void_p(metrics.data_ptr()), C.c_void_p(counts.data_ptr()),
+            _cabi.AVS_DEVICE if on_gpu else _cabi.AVS_HOST, _stream_ptr(dev)))
+    return metrics.cpu().numpy(), counts.cpu().numpy()
+
+
+def cdist_euclidean(a: torch.Tensor, b: torch.Tensor) -> np.ndarray:
+    """scipy.spatial.distance.cdist(a, b, 'euclidean') -> float64 numpy [na, nb] (bit-exact), on the GPU."""
+    _require_cuda()
+    a = a.detach().to(torch.float32).contiguous()
+    b = b.detach().to(torch.float32).contiguous()
+    on_gpu = a.is_cuda
+    if b.is_cuda != on_gpu:
+        raise ValueError("both inputs must live on the same device")
+    dev = a.device if on_gpu else torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float64, device=a.device)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().avs_cdist(
+            C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), int(a.shape[0]), int(b.shape[0]), int(a.shape[1]),
+            C.c_void_p(out.data_ptr()), _cabi.AVS_DEVICE if on_gpu else _cabi.AVS_HOST, _stream_ptr(dev)))
+    return out.cpu().numpy()
+
+
+def gather_scale(features: torch.Tensor, idx, weights) -> torch.Tensor:
+    """out[k, :] = features[idx[k], :] * float32(weights[k]) on the GPU; result in the memory space of features."""
+    _require_cuda()
+    f = features.detach().to(torch.float32).contiguous()
+    ix = _i32(idx)
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.float32))
+    on_gpu = f.is_cuda
+    dev = f.device if on_gpu else torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(int(ix.size), f.shape[1], dtype=torch.float32, device=f.device)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().avs_interpolate(
+            C.c_void_p(f.data_ptr()), int(f.shape[0]), int(f.shape[1]), _cabi.np_ptr(ix), _cabi.np_ptr(w),
+            int(ix.size), C.c_void_p(out.data_ptr()), _cabi.AVS_DEVICE if on_gpu else _cabi.AVS_HOST, _stream_ptr(dev)))
+    return out
+
+
+def dtw_path(cost) -> Tuple[float, np.ndarray]:
+    """Exact DTW through a float64 cost matrix (numpy or torch, host or device) -> (total cost, path int [P, 2])."""
+    _require_cuda()
+    if isinstance(cost, torch.Tensor):
+        c = cost.detach().to(torch.float64).contiguous()
+        ptr, keep = c.data_ptr(), c
+        n, m = int(c.shape[0]), int(c.shape[1])
+    else:
+        c = np.ascontiguousarray(np.asarray(cost, dtype=np.float64))
+        ptr, keep = c.ctypes.data, c
+        n, m = int(c.shape[0]), int(c.shape[1])
+    path = np.zeros((max(n + m - 1, 1), 2), dtype=np.int32)
+    plen = np.zeros(1, dtype=np.int32)
+    total = np.zeros(1, dtype=np.float64)
+    dev = torch.cuda.current_device()
+    _cabi.check(_cabi.lib().avs_dtw_path(C.c_void_p(ptr), n, m, _cabi.np_ptr(path), _cabi.np_ptr(plen),
+                                         _cabi.np_ptr(total), _stream_ptr(dev)))
+    del keep
+    return float(total[0]), path[:int(plen[0])].astype(np.int64)

@@ -1,0 +1,50 @@
+"""Drop-in for the reference's ``scripts/evaluate.py`` -- ``evaluate(model, dataset)``.
+
+The reference (/root/reference/scripts/evaluate.py:6-42) scores one video at a time (B = 1, a synchronous
+``.cuda()`` / ``.cpu()`` pair per video) and then computes, per video on the host, the mean-threshold F1,
+Spearman's rho and Kendall's tau, returning their means.  Here the whole dataset is ONE packed
+variable-length batch: one ``avs_forward`` (each video treated as its own B = 1 call, i.e. the reference's
+semantics) and one ``avs_eval_metrics`` launch that evaluates the metric block for every video on the GPU;
+only 3 doubles per video come back.  Return value: the same ``{"f1", "spearman", "kendall"}`` dict.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def evaluate(model, dataset, return_per_video: bool = False):
+    model.eval()
+    visuals, audios, targets = [], [], []
+    for features, scores in dataset:
+        visuals.append(torch.as_tensor(features["visual"]))
+        audios.append(torch.as_tensor(features["audio"]))
+        targets.append(torch.as_tensor(scores).reshape(-1))
+    if not visuals:
+        nan = float("nan")   # np.mean([]) in the reference
+        return {"f1": nan, "spearman": nan, "kendall": nan}
+    lens = [int(v.shape[0]) for v in visuals]
+    for n, t in zip(lens, targets):
+        if int(t.numel()) != n:
+            raise ValueError("every video needs one target score per frame")
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    dev = next(model.parameters()).device
+    with torch.no_grad():
+        axis = "literal_b1" if model.attn_axis == "literal" else model.attn_axis
+        pred = model.native().forward_rows(torch.cat(visuals).to(dev), torch.cat(audios).to(dev), starts, lens, axis,
+                                           model.precision)
+    tgt_dtype = torch.float64 if any(t.dtype == torch.float64 for t in targets) else torch.float32
+    target = torch.cat([t.to(tgt_dtype) for t in targets]).to(dev)
+    from .. import runtime
+    metrics, counts = runtime.eval_metrics_rows(pred, target, starts, lens)
+    # scipy.stats.kendalltau returns the correlation in the dtype of its inputs when both are float32
+    # (float64 arithmetic, rounded once), spearmanr always float64; np.mean then follows those dtypes
+    kendalls = metrics[:, 2].astype(np.float32) if tgt_dtype == torch.float32 else metrics[:, 2]
+    out = {
+        "f1": np.mean(metrics[:, 0]),
+        "spearman": np.mean(metrics[:, 1]),
+        "kendall": np.mean(kendalls),
+    }
+    if return_per_video:
+        return out, metrics, counts
+    return out

@@ -143,6 +143,35 @@ avs_status avs_attention(const float* qkv, int64_t rows, int32_t E, int32_t num_
 avs_status avs_temporal_f1(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
                            const int32_t* gt_start, int32_t n_videos, double* f1_host, void* cuda_stream);
 
+/* The metric block of scripts/evaluate.py:25-36 for a batch of videos (the caller right after the forward):
+ *   binary_pred = pred > np.mean(pred), binary_target = target > np.mean(target)   (np.mean's pairwise
+ *   summation restated exactly), tp / precision / recall / F1 with the 1e-8 guard, scipy.stats.spearmanr
+ *   (Pearson correlation of average ranks) and scipy.stats.kendalltau (tau-b) per video.
+ * pred fp32 [rows]; target fp32 or fp64 (target_is_f64) [rows]; same (row_start, lengths) indexing as avs_forward.
+ * metrics double [n, 4] = f1, spearman, kendall, np.mean(pred);  counts int64 [n, 8] = tp, sum(binary_pred),
+ * sum(binary_target), discordant pairs, x ties, y ties, joint ties, n.  `space` applies to pred / target /
+ * metrics / counts.  F1 and tau are bit-exact against numpy / scipy; rho to ~1e-15 (exact integer moments). */
+avs_status avs_eval_metrics(const float* pred, const void* target, int target_is_f64, int32_t n_videos,
+                            const int32_t* row_start, const int32_t* lengths, double* metrics, int64_t* counts,
+                            int space, void* cuda_stream);
+
+/* features/fusion.py:7-12 compute_dtw: scipy cdist(a, b, "euclidean") -- a [na, D], b [nb, D] fp32, out [na, nb]
+ * float64, summed in scipy's order (bit-exact). */
+avs_status avs_cdist(const float* a, const float* b, int32_t na, int32_t nb, int32_t D, double* out, int space,
+                     void* cuda_stream);
+
+/* features/fusion.py:21-32 interpolate_features: out[k, :] = features[idx[k], :] * weights[k]  (fp32 multiply).
+ * idx / weights: host arrays [U] (np.unique of the path's first column and counts / counts.sum()). */
+avs_status avs_interpolate(const float* features, int64_t n_rows, int32_t D, const int32_t* idx, const float* weights,
+                           int32_t U, float* out, int space, void* cuda_stream);
+
+/* Exact dynamic-time-warping path through a cost matrix [n, m] (float64, host or device; results to host):
+ * fastdtw's published recurrence D[i,j] = c[i,j] + min(D[i-1,j], D[i,j-1], D[i-1,j-1]) with its tie order.
+ * This is what features/fusion.py:15-18 evidently intends; the reference's own call raises TypeError.
+ * path int32 [(n + m - 1), 2] (first *path_len rows valid), total = accumulated cost. */
+avs_status avs_dtw_path(const double* cost, int32_t n, int32_t m, int32_t* path, int32_t* path_len, double* total,
+                        void* cuda_stream);
+
 /* Counters: number of kernel launches issued by this library since load (gpu_launches in bench.py). */
 int64_t avs_launch_count(void);
 

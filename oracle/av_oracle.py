@@ -311,3 +311,108 @@ def threshold_f1(pred, target):
     precision = tp / bp.sum()
     recall = tp / bt.sum()
     return 2 * (precision * recall) / (precision + recall + 1e-8)
+
+
+def eval_metrics(pred, target):
+    """Metric block of scripts/evaluate.py:25-36 for one video, with the SAME library calls the reference
+    makes (numpy + scipy.stats): returns (f1, spearman, kendall)."""
+    from scipy.stats import kendalltau, spearmanr
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with np.errstate(all="ignore"):
+            f1 = threshold_f1(pred, target)
+            return float(f1), float(spearmanr(pred, target).correlation), float(kendalltau(pred, target).correlation)
+
+
+def np_mean_pairwise(a):
+    """numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src) restated, then / n in the array's
+    dtype -- what np.mean(a) computes for a contiguous 1-D float array.  Used to pin the CUDA restatement."""
+    a = np.ascontiguousarray(a)
+    T = a.dtype.type
+
+    def block(x):
+        n = x.shape[0]
+        if n < 8:
+            res = T(0)
+            for v in x:
+                res = T(res + v)
+            return res
+        r = [T(v) for v in x[:8]]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = T(r[j] + x[i + j])
+            i += 8
+        res = T(T(T(r[0] + r[1]) + T(r[2] + r[3])) + T(T(r[4] + r[5]) + T(r[6] + r[7])))
+        while i < n:
+            res = T(res + x[i])
+            i += 1
+        return res
+
+    def rec(x):
+        n = x.shape[0]
+        if n <= 128:
+            return block(x)
+        n2 = n // 2
+        n2 -= n2 % 8
+        return T(rec(x[:n2]) + rec(x[n2:]))
+
+    return T(rec(a) / T(a.shape[0]))
+
+
+def kendall_counts(x, y):
+    """Integer ingredients of scipy.stats.kendalltau (tau-b) by brute force: (dis, xtie, ytie, ntie, tot)."""
+    x = np.asarray(x)
+    y = np.asarray(y)
+    n = x.shape[0]
+    dx = np.sign(x[:, None] - x[None, :])
+    dy = np.sign(y[:, None] - y[None, :])
+    iu = np.triu_indices(n, 1)
+    dis = int(np.sum((dx * dy)[iu] < 0))
+    xtie = int(np.sum(dx[iu] == 0))
+    ytie = int(np.sum(dy[iu] == 0))
+    ntie = int(np.sum((dx[iu] == 0) & (dy[iu] == 0)))
+    return dis, xtie, ytie, ntie, n * (n - 1) // 2
+
+
+def cdist_euclidean(a, b):
+    """scipy cdist(a, b, 'euclidean') restated (features/fusion.py:11): float64, the feature loop summed
+    sequentially (np.cumsum accumulates left to right), square root at the end."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = a[:, None, :] - b[None, :, :]
+    return np.sqrt(np.cumsum(d * d, axis=-1)[..., -1])
+
+
+def interpolate_features(features, path, target_length):
+    """features/fusion.py:21-32 on numpy arrays (float32 rows scaled by float32(count / total))."""
+    path = np.asarray(path)
+    u, c = np.unique(path[:, 0], return_counts=True)
+    w = c / c.sum()
+    f = np.asarray(features, dtype=F32)
+    return np.stack([f[i] * F32(wt) for i, wt in zip(u, w)])[:target_length]
+
+
+def dtw_path(cost):
+    """Exact DTW through a cost matrix: fastdtw's published `__dtw` (fastdtw 0.3.x, fastdtw.py) with the full
+    window -- D[i, j] = min((D[i-1, j] + c, ...), (D[i, j-1] + c, ...), (D[i-1, j-1] + c, ...)) keyed on the sum,
+    first minimum wins; D = inf outside, D[0, 0] = 0 (1-based).  PARITY UNPINNED: fastdtw is absent from this
+    image and the reference's own call site (features/fusion.py:17) raises TypeError."""
+    cost = np.asarray(cost, dtype=np.float64)
+    n, m = cost.shape
+    inf = float("inf")
+    D = {(0, 0): (0.0, 0, 0)}
+    get = lambda i, j: D.get((i, j), (inf,))
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            dt = float(cost[i - 1, j - 1])
+            D[i, j] = min((get(i - 1, j)[0] + dt, i - 1, j), (get(i, j - 1)[0] + dt, i, j - 1),
+                          (get(i - 1, j - 1)[0] + dt, i - 1, j - 1), key=lambda a: a[0])
+    path = []
+    i, j = n, m
+    while not (i == j == 0):
+        path.append((i - 1, j - 1))
+        i, j = D[i, j][1], D[i, j][2]
+    path.reverse()
+    return D[n, m][0], np.asarray(path, dtype=np.int64)

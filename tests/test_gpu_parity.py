@@ -356,3 +356,111 @@ def test_empty_and_zero_length_videos(native):
     assert torch.equal(got[:4], a1) and torch.equal(got[4:], a2)
     with pytest.raises(ValueError):
         native.forward_rows(v, a, [0, 8], [4, 6], "temporal")      # rows outside the buffer
+
+
+# ------------------------------------------------------------------ evaluate() metric block (a13)
+def _metric_case(rng, n, kind, tgt_dtype):
+    if kind == "ties":
+        pred = rng.integers(0, 6, n).astype(np.float32) / 5
+        target = rng.integers(0, 4, n).astype(tgt_dtype) / 3
+    elif kind == "constant":
+        pred = np.full(n, 0.5, np.float32)
+        target = rng.random(n).astype(tgt_dtype)
+    elif kind == "nan":
+        pred = rng.random(n).astype(np.float32)
+        target = rng.random(n).astype(tgt_dtype)
+        if n:
+            pred[n // 2] = np.nan
+    else:
+        pred = rng.random(n).astype(np.float32)
+        target = (0.3 * pred + rng.random(n)).astype(tgt_dtype)
+    return pred, target
+
+
+@pytest.mark.parametrize("space", ["cuda", "cpu"])
+@pytest.mark.parametrize("tgt_dtype", [np.float32, np.float64])
+def test_eval_metrics_match_numpy_scipy(cuda_ready, space, tgt_dtype):
+    """scripts/evaluate.py:25-36 per video: F1 and Kendall's tau bit-exact against numpy / scipy (the calls the
+    reference makes), Spearman's rho to 1e-13, integer pair counts exact, np.mean(pred) bit-exact."""
+    rng = np.random.default_rng(7)
+    cases = [(320, "random"), (700, "random"), (57, "ties"), (129, "ties"), (1, "random"), (2, "random"),
+             (40, "constant"), (33, "nan"), (2049, "random"), (0, "random")]
+    preds, targets = zip(*[_metric_case(rng, n, k, tgt_dtype) for n, k in cases])
+    lens = [len(p) for p in preds]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    metrics, counts = runtime.eval_metrics_rows(torch.from_numpy(np.concatenate(preds)).to(space),
+                                                torch.from_numpy(np.concatenate(targets)).to(space), starts, lens)
+    same = lambda a, b: (a == b) or (np.isnan(a) and np.isnan(b))
+    for i, (p, t) in enumerate(zip(preds, targets)):
+        if len(p) == 0:
+            assert np.isnan(metrics[i, 0]) and counts[i, 7] == 0
+            continue
+        f1, rho, tau = av_oracle.eval_metrics(p, t)
+        assert same(metrics[i, 0], f1), (i, metrics[i, 0], f1)
+        tau_gpu = np.float32(metrics[i, 2]) if tgt_dtype == np.float32 else metrics[i, 2]
+        assert same(tau_gpu, tau), (i, tau_gpu, tau)     # scipy rounds once to float32 for float32 inputs
+        assert same(metrics[i, 1], rho) or abs(metrics[i, 1] - rho) < 1e-13, (i, metrics[i, 1], rho)
+        assert np.float32(metrics[i, 3]) == np.mean(p) or np.isnan(np.mean(p))
+        if not np.isnan(p).any():
+            dis, xt, yt, nt, tot = av_oracle.kendall_counts(p, t)
+            assert list(counts[i, 3:8]) == [dis, xt, yt, nt, len(p)]
+            assert counts[i, 1] == int((p > np.mean(p)).sum()) and counts[i, 2] == int((t > np.mean(t)).sum())
+
+
+def test_evaluate_drop_in_matches_reference_loop(cuda_ready):
+    """evaluate(model, dataset) (scripts/evaluate.py:6-42) as one packed batch == the reference's per-video loop
+    applied to the same scores."""
+    from avsum_b200.scripts.evaluate import evaluate
+    vids = synth.config2()[:9]
+    rng = np.random.default_rng(5)
+    dataset = [({"visual": v.visual, "audio": v.audio}, torch.from_numpy(rng.random(v.T).astype(np.float32)))
+               for v in vids]
+    m = make_model(spread=True)
+    got, metrics, _ = evaluate(m, dataset, return_per_video=True)
+    scores = m.score_videos([(v.visual.cuda(), v.audio.cuda()) for v in vids])
+    f1s, rhos, taus = zip(*[av_oracle.eval_metrics(s.cpu().numpy(), t.numpy()) for s, (_, t) in zip(scores, dataset)])
+    from scipy.stats import kendalltau
+    taus32 = [kendalltau(s.cpu().numpy(), t.numpy()).correlation for s, (_, t) in zip(scores, dataset)]
+    assert got["f1"] == np.mean(f1s)
+    assert got["kendall"] == np.mean(taus32) and got["kendall"].dtype == np.float32
+    assert abs(got["spearman"] - np.mean(rhos)) < 1e-13
+    assert set(got) == {"f1", "spearman", "kendall"}
+    # and against the reference scores (CPU port): same metrics within the score tolerance
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
+    port.load_state_dict(synth.seeded_state_dict(spread=True))
+    ref_scores = av_oracle_torch.run_videos(port, [(v.visual, v.audio) for v in vids])
+    ref = [av_oracle.eval_metrics(s.numpy(), t.numpy()) for s, (_, t) in zip(ref_scores, dataset)]
+    assert abs(got["spearman"] - np.mean([r[1] for r in ref])) < 5e-3
+    assert abs(float(got["kendall"]) - np.mean([r[2] for r in ref])) < 5e-3
+
+
+# ------------------------------------------------------------------ features/fusion.py helpers (a9-a11)
+def test_fusion_helpers_match_reference(cuda_ready, golden_dir):
+    from avsum_b200.features import fusion
+    g = np.load(os.path.join(golden_dir, "helpers.npz"))
+    gen = torch.Generator().manual_seed(11)
+    fv, fa = torch.randn(23, 64, generator=gen), torch.randn(31, 64, generator=gen)
+    for dev in ("cpu", "cuda"):
+        dtw = fusion.compute_dtw(fv.to(dev), fa.to(dev)) if dev == "cpu" else runtime.cdist_euclidean(fv.cuda(), fa.cuda())
+        assert dtw.dtype == np.float64 and np.array_equal(dtw, g["dtw"])          # bit-exact vs the reference
+        interp = fusion.interpolate_features(fv.to(dev), g["path"], 20)
+        assert isinstance(interp, torch.Tensor) and np.array_equal(interp.cpu().numpy(), g["interp"])
+    with pytest.raises(ValueError):                                               # 1024-d vs 128-d (SURVEY a9)
+        fusion.compute_dtw(torch.randn(5, 1024), torch.randn(5, 128))
+    with pytest.raises(TypeError):                                                # the reference's broken call (a10)
+        fusion.compute_optimal_path(g["dtw"])
+    # larger, odd-sized case against the oracle restatement (summation order matters at D = 1000)
+    a, b = torch.randn(70, 1000, generator=gen), torch.randn(33, 1000, generator=gen)
+    assert np.array_equal(fusion.compute_dtw(a, b), av_oracle.cdist_euclidean(a.numpy(), b.numpy()))
+
+
+def test_exact_dtw_path_matches_oracle(cuda_ready):
+    from avsum_b200.features import fusion
+    rng = np.random.default_rng(4)
+    for n, m, ties in [(1, 1, False), (1, 9, False), (8, 1, False), (23, 31, False), (40, 40, True), (130, 77, True)]:
+        cost = rng.integers(0, 5, (n, m)).astype(np.float64) if ties else rng.random((n, m))
+        total, path = av_oracle.dtw_path(cost)
+        got = fusion.compute_optimal_path(cost, exact=True)
+        assert np.array_equal(got, path), (n, m)
+        t2, _ = runtime.dtw_path(torch.from_numpy(cost).cuda())
+        assert t2 == total
