@@ -1,0 +1,89 @@
+"""On-disk feature contract of the reference (``data/dataset.py:8-32``; written by ``scripts/preprocess.py:74-81``):
+
+    <feature_dir>/<video_id>/{visual.npy, audio.npy, scores.npy}      (float32 arrays, one row per sampled frame)
+
+``BaseDataset`` keeps the reference's constructor and item type -- ``(features: {"visual", "audio"}, scores)`` as
+torch tensors -- so ``scripts/evaluate.evaluate(model, dataset)`` works unchanged.  ``packed_batches`` is the
+feeding side the reference lacks: it turns a dataset into length-bucketed, PACKED batches in pinned host
+memory (one row per frame plus ``row_start`` / ``lengths`` descriptors), the layout ``avs_forward`` consumes, so
+that the per-video ``.cuda()`` / ``.cpu()`` synchronisation of ``scripts/evaluate.py:13-15`` disappears.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+class BaseDataset(torch.utils.data.Dataset):
+    def __init__(self, feature_dir, annotation_path=None):
+        self.feature_dir = feature_dir
+        self.video_ids = sorted(os.listdir(feature_dir))   # sorted: deterministic order (os.listdir is not)
+        if annotation_path is not None:
+            raise NotImplementedError(
+                "annotation files are not part of the feature contract: the reference's BaseDataset._load_annotations "
+                "is itself undefined (data/dataset.py:12-14); scores come from <video>/scores.npy")
+        self.annotations = None
+
+    def __len__(self):
+        return len(self.video_ids)
+
+    def __getitem__(self, idx):
+        vid = self.video_ids[idx]
+        features = {
+            "visual": torch.from_numpy(np.load(os.path.join(self.feature_dir, vid, "visual.npy"))),
+            "audio": torch.from_numpy(np.load(os.path.join(self.feature_dir, vid, "audio.npy"))),
+        }
+        scores = torch.from_numpy(np.load(os.path.join(self.feature_dir, vid, "scores.npy")))
+        return features, scores
+
+
+class PackedBatch:
+    """Packed variable-length batch in pinned host memory."""
+
+    def __init__(self, indices, visual, audio, scores, row_start, lengths):
+        self.indices = indices          # dataset indices of the videos, in batch order
+        self.visual = visual            # fp32 [sum T, Dv] pinned
+        self.audio = audio              # fp32 [sum T, Da] pinned
+        self.scores = scores            # [sum T] pinned (dtype of scores.npy)
+        self.row_start = row_start      # int32 [n]
+        self.lengths = lengths          # int32 [n]
+
+
+def packed_batches(dataset, max_frames: int = 32768, max_videos: int = 64, bucket: bool = True,
+                   pin: Optional[bool] = None) -> Iterator[PackedBatch]:
+    """Yield PackedBatch objects covering the dataset once.
+
+    Videos are sorted by length (longest first) when ``bucket`` is set, so that the videos of one batch -- which
+    share LSTM clusters whose run time is set by their longest member -- have similar lengths; a batch closes
+    when adding a video would exceed ``max_frames`` rows or ``max_videos`` videos.
+    """
+    pin = torch.cuda.is_available() if pin is None else pin
+    items = [dataset[i] for i in range(len(dataset))]
+    order = list(range(len(items)))
+    if bucket:
+        order.sort(key=lambda i: -int(items[i][0]["visual"].shape[0]))
+    cur: List[int] = []
+    rows = 0
+
+    def flush(idxs):
+        lens = np.asarray([int(items[i][0]["visual"].shape[0]) for i in idxs], dtype=np.int32)
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+        visual = torch.cat([items[i][0]["visual"].to(torch.float32) for i in idxs])
+        audio = torch.cat([items[i][0]["audio"].to(torch.float32) for i in idxs])
+        scores = torch.cat([items[i][1].reshape(-1) for i in idxs])
+        if pin:
+            visual, audio, scores = visual.pin_memory(), audio.pin_memory(), scores.pin_memory()
+        return PackedBatch(list(idxs), visual, audio, scores, starts, lens)
+
+    for i in order:
+        t = int(items[i][0]["visual"].shape[0])
+        if cur and (rows + t > max_frames or len(cur) >= max_videos):
+            yield flush(cur)
+            cur, rows = [], 0
+        cur.append(i)
+        rows += t
+    if cur:
+        yield flush(cur)

@@ -72,3 +72,31 @@ def test_alignment_and_overlap_helpers(golden_dir):
     pred = [tuple(int(x) for x in p) for p in g["pred"]]
     gt = [tuple(int(x) for x in p) for p in g["gt"]]
     assert calculate_overlap(pred, gt) == int(g["overlap"])
+
+
+def test_feature_dir_dataset_and_packed_batches(tmp_path):
+    """data/dataset.py:8-32 contract: <dir>/<vid>/{visual,audio,scores}.npy -> (features dict, scores)."""
+    import numpy as np
+    import torch
+    from avsum_b200.data.dataset import BaseDataset, packed_batches
+    rng = np.random.default_rng(0)
+    lens = {"vid_b": 7, "vid_a": 19, "vid_c": 3, "vid_d": 12}
+    for name, t in lens.items():
+        d = tmp_path / name
+        d.mkdir()
+        np.save(d / "visual.npy", rng.random((t, 16)).astype(np.float32))
+        np.save(d / "audio.npy", rng.random((t, 4)).astype(np.float32))
+        np.save(d / "scores.npy", rng.random(t).astype(np.float32))
+    ds = BaseDataset(str(tmp_path))
+    assert len(ds) == 4 and ds.video_ids == sorted(lens)
+    feats, scores = ds[0]
+    assert set(feats) == {"visual", "audio"} and feats["visual"].shape == (19, 16) and scores.shape == (19,)
+    batches = list(packed_batches(ds, max_frames=30, pin=False))
+    seen = sorted(i for b in batches for i in b.indices)
+    assert seen == [0, 1, 2, 3]
+    for b in batches:
+        assert int(b.lengths.sum()) == b.visual.shape[0] == b.audio.shape[0] == b.scores.shape[0] <= 30
+        assert list(b.lengths) == sorted(b.lengths, reverse=True)          # bucketed: longest first
+        for k, i in enumerate(b.indices):
+            s, n = int(b.row_start[k]), int(b.lengths[k])
+            assert torch.equal(b.visual[s:s + n], ds[i][0]["visual"]) and torch.equal(b.scores[s:s + n], ds[i][1])
