@@ -28,6 +28,7 @@ EXPORTS = [
     "avs_attention", "avs_temporal_f1", "avs_launch_count", "avs_profile", "avs_profile_stages",
     "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace",
     "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
+    "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd",
 ]
 
 
@@ -111,6 +112,12 @@ def lib() -> C.CDLL:
     L.avs_interpolate.argtypes = [vp, i64, i32, vp, vp, i32, vp, C.c_int, vp]
     L.avs_dtw_path.restype = C.c_int
     L.avs_dtw_path.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.avs_bilstm_pair_train.restype = C.c_int
+    L.avs_bilstm_pair_train.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]
+    L.avs_bilstm_pair_bwd.restype = C.c_int
+    L.avs_bilstm_pair_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.avs_linear_bwd.restype = C.c_int
+    L.avs_linear_bwd.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     L.avs_debug_lstm_trace.restype = C.c_int
     L.avs_debug_lstm_trace.argtypes = [vp]
     L.avs_profile.restype = None

@@ -869,9 +869,9 @@ avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t
     return s;
 }
 
-avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows, int32_t n_videos,
-                           const int32_t* row_start, const int32_t* lengths, int precision, float* fused,
-                           void* cuda_stream) {
+static avs_status bilstm_pair_impl(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows,
+                                   int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int precision,
+                                   float* fused, void* save_pre, float* save_c, void* cuda_stream) {
     AVS_CHECK(m && v_emb && a_emb && fused, AVS_ERR_INVALID, "avs_bilstm_pair: null pointer");
     AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
     int max_len = 0;
@@ -910,8 +910,178 @@ avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb,
     AVS_TRY(run_gemm(precision, xa, act, H, w_ih_a, 0, H, R, 2 * G4, H, e2, st));
     const int slots = plan.n_groups * plan.nb;
     LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
-    if (!simt) return lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, act, fused, DT_F32, 0, st);
+    if (!simt) return lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, act, fused, DT_F32, 0, st, save_pre, save_c);
+    AVS_CHECK(save_pre == nullptr, AVS_ERR_UNSUPPORTED, "the training forward needs a tensor-core precision");
     return lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, 0, nullptr, 0, st);
+}
+
+avs_status avs_bilstm_pair(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows, int32_t n_videos,
+                           const int32_t* row_start, const int32_t* lengths, int precision, float* fused,
+                           void* cuda_stream) {
+    return bilstm_pair_impl(m, v_emb, a_emb, total_rows, n_videos, row_start, lengths, precision, fused, nullptr, nullptr,
+                            cuda_stream);
+}
+
+// ---- training step building blocks (scripts/train_av_model.py:86-96) ---------------------------------
+avs_status avs_bilstm_pair_train(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows,
+                                 int32_t n_videos, const int32_t* row_start, const int32_t* lengths, float* fused,
+                                 float* save_pre, float* save_c, void* cuda_stream) {
+    AVS_CHECK(save_pre && save_c, AVS_ERR_INVALID, "avs_bilstm_pair_train: null save buffer");
+    return bilstm_pair_impl(m, v_emb, a_emb, total_rows, n_videos, row_start, lengths, AVS_PREC_TF32, fused, save_pre,
+                            save_c, cuda_stream);
+}
+
+namespace {
+// C[M, N] = A[M, K] * Wt[N, K]^T on the tensor cores (kind::tf32), all operands pre-rounded fp32
+avs_status gemm_nt_tf32(const float* A, int64_t lda, const float* Wt, int64_t ldw, int64_t M, int N, int K, float* C,
+                        int64_t ldc, cudaStream_t st) {
+    GemmEpilogue e;
+    e.C = C;
+    e.ldc = ldc;
+    return gemm_tc(A, lda, Wt, ldw, DT_F32, M, N, K, e, st);
+}
+int64_t pad4(int64_t x) { return (x + 3) / 4 * 4; }
+}  // namespace
+
+avs_status avs_linear_bwd(const float* dY, const float* X, const float* W, int64_t M, int32_t N, int32_t K, float* dX,
+                          float* dW, float* db, void* cuda_stream) {
+    AVS_CHECK(dY != nullptr && M >= 0 && N > 0 && K > 0, AVS_ERR_INVALID, "avs_linear_bwd: bad arguments");
+    AVS_CHECK(M < (1ll << 31), AVS_ERR_UNSUPPORTED, "avs_linear_bwd: too many rows");
+    AVS_CHECK((dX == nullptr || W != nullptr) && (dW == nullptr || X != nullptr), AVS_ERR_INVALID,
+              "avs_linear_bwd: dX needs W and dW needs X");
+    AVS_CHECK(N % 4 == 0 && K % 4 == 0, AVS_ERR_UNSUPPORTED,
+              "avs_linear_bwd: N=%d and K=%d must be multiples of 4 (16-byte TMA row pitch)", N, K);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (M == 0) {
+        if (dW) AVS_CUDA(cudaMemsetAsync(dW, 0, static_cast<size_t>(N) * K * 4, st));
+        if (db) AVS_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(N) * 4, st));
+        return AVS_OK;
+    }
+    const int64_t Mp = pad4(M);
+    size_t bytes = 0;
+    const size_t o_dyr = bytes;  bytes += dX ? align_up(static_cast<size_t>(M) * N * 4, 256) : 0;
+    const size_t o_wt = bytes;   bytes += dX ? align_up(static_cast<size_t>(K) * N * 4, 256) : 0;
+    const size_t o_dyt = bytes;  bytes += dW ? align_up(static_cast<size_t>(N) * Mp * 4, 256) : 0;
+    const size_t o_xt = bytes;   bytes += dW ? align_up(static_cast<size_t>(K) * Mp * 4, 256) : 0;
+    char* ws = nullptr;
+    if (bytes) AVS_CUDA(cudaMallocAsync(&ws, bytes, st));
+    avs_status s = AVS_OK;
+    if (dX) {   // dX[M, K] = dY[M, N] * W[N, K]  ==  dY * (W^T)^T
+        float* dyr = reinterpret_cast<float*>(ws + o_dyr);
+        float* wt = reinterpret_cast<float*>(ws + o_wt);
+        if (s == AVS_OK) s = convert_f32(dY, dyr, M * N, DT_F32, 1, st);
+        if (s == AVS_OK) s = transpose_f32(W, K, N, K, wt, N, 0, 1, st);
+        if (s == AVS_OK) s = gemm_nt_tf32(dyr, N, wt, N, M, K, N, dX, K, st);
+    }
+    if (dW) {   // dW[N, K] = dY^T[N, M] * X[M, K]  ==  (dY^T) * (X^T)^T
+        float* dyt = reinterpret_cast<float*>(ws + o_dyt);
+        float* xt = reinterpret_cast<float*>(ws + o_xt);
+        if (s == AVS_OK) s = transpose_f32(dY, N, static_cast<int>(M), N, dyt, Mp, 0, 1, st);
+        if (s == AVS_OK) s = transpose_f32(X, K, static_cast<int>(M), K, xt, Mp, 0, 1, st);
+        if (s == AVS_OK) s = gemm_nt_tf32(dyt, Mp, xt, Mp, N, K, static_cast<int>(M), dW, K, st);
+    }
+    if (db && s == AVS_OK) s = colsum_f32(dY, N, static_cast<int>(M), N, db, 0, st);
+    if (ws) cudaFreeAsync(ws, st);
+    return s;
+}
+
+avs_status avs_bilstm_pair_bwd(avs_model* m, const float* d_fused, const float* save_pre, const float* save_c,
+                               const float* fused, const float* v_emb, const float* a_emb, int64_t total_rows,
+                               int32_t n_videos, const int32_t* row_start, const int32_t* lengths, float* d_v_emb,
+                               float* d_a_emb, float* const* dW_ih, float* const* dW_hh, float* const* db,
+                               void* cuda_stream) {
+    AVS_CHECK(m && d_fused && save_pre && save_c && fused && v_emb && a_emb && d_v_emb && d_a_emb && dW_ih && dW_hh && db,
+              AVS_ERR_INVALID, "avs_bilstm_pair_bwd: null pointer");
+    for (int i = 0; i < 4; ++i)
+        AVS_CHECK(dW_ih[i] && dW_hh[i] && db[i], AVS_ERR_INVALID, "avs_bilstm_pair_bwd: null gradient pointer");
+    int max_len = 0;
+    AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int64_t R = total_rows;
+    const size_t uR = static_cast<size_t>(R);
+    if (R == 0 || max_len == 0) {
+        for (int i = 0; i < 4; ++i) {
+            AVS_CUDA(cudaMemsetAsync(dW_ih[i], 0, static_cast<size_t>(G4) * H * 4, st));
+            AVS_CUDA(cudaMemsetAsync(dW_hh[i], 0, static_cast<size_t>(G4) * HC * 4, st));
+            AVS_CUDA(cudaMemsetAsync(db[i], 0, static_cast<size_t>(G4) * 4, st));
+        }
+        return AVS_OK;
+    }
+    // ---- plan: up to 8 videos per cluster, longest first (any number of groups: clusters are independent)
+    std::vector<int> order;
+    for (int b = 0; b < n_videos; ++b)
+        if (lengths[b] > 0) order.push_back(b);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lengths[a] > lengths[b]; });
+    const int B = static_cast<int>(order.size());
+    int nb = 8;
+    for (int c : {1, 2, 4, 8})
+        if (B <= c) { nb = c; break; }
+    const int n_groups = (B + nb - 1) / nb;
+    const int slots = n_groups * nb;
+    std::vector<int32_t> plan(2 * slots + n_groups + 2 * static_cast<size_t>(n_videos), 0);
+    for (int i = 0; i < B; ++i) {
+        plan[i] = row_start[order[i]];
+        plan[slots + i] = lengths[order[i]];
+    }
+    for (int gidx = 0; gidx < n_groups; ++gidx) plan[2 * slots + gidx] = lengths[order[gidx * nb]];
+    const size_t desc_off = 2 * slots + n_groups;
+    for (int b = 0; b < n_videos; ++b) {
+        plan[desc_off + b] = row_start[b];
+        plan[desc_off + n_videos + b] = lengths[b];
+    }
+    // ---- workspace
+    const int64_t Rp = pad4(R);
+    const size_t need = 2 * uR * 2 * G4 * 4      /* d_xg_v, d_xg_a */
+                        + uR * 2 * G4 * 4          /* rounded copy of one d_xg */
+                        + uR * E * 4               /* hprev */
+                        + 2ull * G4 * Rp * 4       /* d_xg^T (un-permuted rows) */
+                        + static_cast<size_t>(E) * Rp * 4  /* hprev^T */
+                        + static_cast<size_t>(H) * Rp * 4  /* emb^T */
+                        + static_cast<size_t>(H) * 2 * G4 * 4 /* W_ih^T */
+                        + 2 * G4 * 4 + plan.size() * 4 + 32 * 256;
+    AVS_TRY(m->ws.reserve(need));
+    m->ws.reset();
+    float* d_xg_v = m->ws.take<float>(uR * 2 * G4);
+    float* d_xg_a = m->ws.take<float>(uR * 2 * G4);
+    float* d_xg_r = m->ws.take<float>(uR * 2 * G4);
+    float* hprev = m->ws.take<float>(uR * E);
+    float* dxg_t = m->ws.take<float>(2ull * G4 * Rp);
+    float* hprev_t = m->ws.take<float>(static_cast<size_t>(E) * Rp);
+    float* emb_t = m->ws.take<float>(static_cast<size_t>(H) * Rp);
+    float* wih_t = m->ws.take<float>(static_cast<size_t>(H) * 2 * G4);
+    float* db_tmp = m->ws.take<float>(2 * G4);
+    int32_t* plan_dev = m->ws.take<int32_t>(plan.size());
+    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice, st));
+    AVS_CUDA(cudaMemsetAsync(d_xg_v, 0, 2 * uR * 2 * G4 * 4 + 256, st));   // rows no video owns contribute nothing
+
+    LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, n_groups, nb};
+    AVS_TRY(lstm_backward(d_fused, save_pre, save_c, m->whh, lb, d_xg_v, d_xg_a, st));
+    AVS_TRY(shift_h(fused, plan_dev + desc_off, plan_dev + desc_off + n_videos, n_videos, max_len, hprev, st));
+    AVS_TRY(transpose_f32(hprev, E, static_cast<int>(R), E, hprev_t, Rp, 0, 1, st));
+    for (int mod = 0; mod < 2; ++mod) {
+        const float* d_xg = mod ? d_xg_a : d_xg_v;
+        const float* emb = mod ? a_emb : v_emb;
+        const float* wih = mod ? m->ih_a_x : m->ih_v_x;      // packed [2048, 512], exact fp32
+        float* d_emb = mod ? d_a_emb : d_v_emb;
+        // d_emb[R, 512] = d_xg[R, 2048] * W_ih_packed[2048, 512]  (both directions at once)
+        AVS_TRY(convert_f32(d_xg, d_xg_r, R * 2 * G4, DT_F32, 1, st));
+        AVS_TRY(transpose_f32(wih, H, 2 * G4, H, wih_t, 2 * G4, 0, 1, st));
+        AVS_TRY(gemm_nt_tf32(d_xg_r, 2 * G4, wih_t, 2 * G4, R, H, 2 * G4, d_emb, H, st));
+        // weight gradients in the reference's row order: rows of d_xg^T are un-permuted on the way
+        AVS_TRY(transpose_f32(d_xg, 2 * G4, static_cast<int>(R), 2 * G4, dxg_t, Rp, 1, 1, st));
+        AVS_TRY(transpose_f32(emb, H, static_cast<int>(R), H, emb_t, Rp, 0, 1, st));
+        AVS_TRY(colsum_f32(d_xg, 2 * G4, static_cast<int>(R), 2 * G4, db_tmp, 1, st));
+        for (int dir = 0; dir < 2; ++dir) {
+            const int ld = mod * 2 + dir;
+            const float* a_t = dxg_t + static_cast<size_t>(dir) * G4 * Rp;
+            AVS_TRY(gemm_nt_tf32(a_t, Rp, emb_t, Rp, G4, H, static_cast<int>(R), dW_ih[ld], H, st));
+            AVS_TRY(gemm_nt_tf32(a_t, Rp, hprev_t + static_cast<size_t>(ld) * HC * Rp, Rp, G4, HC, static_cast<int>(R),
+                                 dW_hh[ld], HC, st));
+            AVS_CUDA(cudaMemcpyAsync(db[ld], db_tmp + dir * G4, G4 * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return AVS_OK;
 }
 
 avs_status avs_attention(const float* qkv, int64_t rows, int32_t E_, int32_t num_heads, int32_t n_seqs,

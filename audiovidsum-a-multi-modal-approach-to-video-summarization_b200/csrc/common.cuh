@@ -107,8 +107,16 @@ avs_status lstm_recurrence(const float* xg_v, const float* xg_a, const float* wh
 
 // tcgen05 version (16-bit operands: op_dtype = DT_F16 or DT_BF16; fp32 accumulate / state); batch.nb must be
 // 8 (two CTAs per SM), 16, 32 or 64.  fused output: fp32 (optionally tf32-rounded), fp16 or bf16 (out_dtype).
+// save_pre (float4 [rows, 4, 256]: i, f, g, o pre-activations) / save_c (float [rows, 4, 256]: new cell state) are
+// written when non-null (training forward; consumed by lstm_backward).
 avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
-                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream);
+                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream,
+                              void* save_pre = nullptr, float* save_c = nullptr);
+
+// BPTT through the four recurrences (CUDA-core fp32, cluster of 8 CTAs, DSMEM reduce-scatter of dh):
+// d_fused [rows, 1024] -> d_xg_v / d_xg_a [rows, 2048] (gate gradients in the packed column order of xg).
+avs_status lstm_backward(const float* d_fused, const void* save_pre, const float* save_c, const float* whh_packed,
+                         const LstmBatch& batch, float* d_xg_v, float* d_xg_a, cudaStream_t stream);
 
 avs_status lstm_trace_read(unsigned long long* out8);   // AVS_LSTM_TRACE=1 debugging aid
 
@@ -149,6 +157,14 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
                            cudaStream_t stream);
 avs_status temporal_f1_device(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
                               const int32_t* gt_start, int n, double* f1_dev, cudaStream_t stream);
+
+// ---- training helpers (train.cu) -------------------------------------------------------------
+// dst[map(c)][r] = src[r][c] (optionally tf32-rounded); perm 1 = LSTM gate-row un-permutation per 1024-column block
+avs_status transpose_f32(const float* src, int64_t ld_src, int R, int C, float* dst, int64_t ld_dst, int perm, int round,
+                         cudaStream_t stream);
+avs_status colsum_f32(const float* src, int64_t ld_src, int R, int C, float* out, int perm, cudaStream_t stream);
+avs_status shift_h(const float* fused, const int32_t* row_start, const int32_t* lengths, int n_videos, int max_len,
+                   float* hprev, cudaStream_t stream);
 
 // ---- evaluation metrics / fusion helpers (metrics.cu) -------------------------------------------
 avs_status eval_metrics_device(const float* pred, const void* target, int tgt_f64, const int32_t* row_start,

@@ -351,7 +351,10 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     if (M == 0) return AVS_OK;
     AVS_CHECK(M > 0 && N > 0 && K > 0, AVS_ERR_INVALID, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
     AVS_CHECK(M < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: M too large");
-    AVS_CHECK(N % 16 == 0, AVS_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 16", N);
+    // the bias / score epilogues read 16 columns at a time; a plain store only needs a 16-byte row pitch
+    // (columns >= N are computed from zero-filled operand rows and clipped by the TMA store)
+    AVS_CHECK(N % 16 == 0 || (epi.bias == nullptr && epi.scores == nullptr && (N * dtype_size(epi.out_dtype)) % 16 == 0),
+              AVS_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 16 (or of 4 without a bias, fp32 output)", N);
     if (epi.scores != nullptr)
         AVS_CHECK(N == 64 && epi.score_w2 && epi.score_b2, AVS_ERR_INVALID, "score epilogue needs N == 64");
     else

@@ -177,7 +177,8 @@ __device__ __forceinline__ long long clk64() {
 template <int NB, int PARTS, bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PARTS * 128 + 32, PARTS == 2 ? 2 : 1)
 lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
-               LstmBatch batch, int op_dtype, void* __restrict__ fused_out, int out_dtype, int round_tf32) {
+               LstmBatch batch, int op_dtype, void* __restrict__ fused_out, int out_dtype, int round_tf32,
+               float4* __restrict__ save_pre, float* __restrict__ save_c) {
     using S = Smem<NB>;
     constexpr int NV = NB / 4;             // video slots per part
     constexpr int SLOTS = NV * PARTS;      // real video slots of this cluster (batch.nb)
@@ -399,6 +400,11 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 const bool on = s < len_r[k];
                 c_state[k] = on ? cn : c_state[k];
                 h_out[k] = h;
+                if (save_pre != nullptr && on) {   // training: gate pre-activations and the new cell state
+                    const size_t o = (static_cast<size_t>(row_r[k]) * 4 + ld) * HC + r * UNITS + jj;
+                    save_pre[o] = make_float4(t_i, t_f, t_g, t_o);
+                    save_c[o] = cn;
+                }
                 if (on)   // |h| < 1: no saturation needed
                     stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + vid_r[k] * 8] =
                         op_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(h)) : __half_as_ushort(__float2half_rn(h));
@@ -469,7 +475,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
 
 template <int NB, int PARTS>
 avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, int op_dtype,
-                     void* fused, int out_dtype, int round_tf32, cudaStream_t stream) {
+                     void* fused, int out_dtype, int round_tf32, float4* save_pre, float* save_c, cudaStream_t stream) {
     static const bool trace = getenv("AVS_LSTM_TRACE") != nullptr;
     auto kern = trace ? lstm_tc_kernel<NB, PARTS, NB == 16> : lstm_tc_kernel<NB, PARTS, false>;
     static bool configured = false;
@@ -477,8 +483,8 @@ avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, con
         AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NB>::TOTAL));
         configured = true;
     }
-    kern<<<batch.n_groups * 4 * CL, PARTS * 128 + 32, Smem<NB>::TOTAL, stream>>>(xg_v, xg_a, whh, batch, op_dtype,
-                                                                                 fused, out_dtype, round_tf32);
+    kern<<<batch.n_groups * 4 * CL, PARTS * 128 + 32, Smem<NB>::TOTAL, stream>>>(
+        xg_v, xg_a, whh, batch, op_dtype, fused, out_dtype, round_tf32, save_pre, save_c);
     AVS_LAUNCH_CHECK();
     return AVS_OK;
 }
@@ -493,14 +499,19 @@ avs_status lstm_trace_read(unsigned long long* out8) {
 }
 
 avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
-                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream) {
+                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream,
+                              void* save_pre, float* save_c) {
     if (batch.n_groups == 0) return AVS_OK;
     AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
     switch (batch.nb) {   // video slots per cluster
-        case 8: return launch_tc<16, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
-        case 16: return launch_tc<16, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
-        case 32: return launch_tc<32, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
-        case 64: return launch_tc<64, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream);
+        case 8: return launch_tc<16, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+                                                static_cast<float4*>(save_pre), save_c, stream);
+        case 16: return launch_tc<16, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+                                                static_cast<float4*>(save_pre), save_c, stream);
+        case 32: return launch_tc<32, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+                                                static_cast<float4*>(save_pre), save_c, stream);
+        case 64: return launch_tc<64, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+                                                static_cast<float4*>(save_pre), save_c, stream);
         default: set_error("lstm_tc: unsupported videos-per-cluster %d", batch.nb); return AVS_ERR_INVALID;
     }
 }

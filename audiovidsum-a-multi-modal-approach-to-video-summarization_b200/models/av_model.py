@@ -45,6 +45,7 @@ class AVBiLSTMModel(nn.Module):
         self.precision = precision
         self._native: Optional[NativeModel] = None
         self._native_key = None
+        self._train_in_eval = False   # set to differentiate through an eval-mode (dropout-free) forward
 
     # ------------------------------------------------------------------ native handle
     def _weights_key(self):
@@ -76,11 +77,10 @@ class AVBiLSTMModel(nn.Module):
         Unbatched [T, Dv] / [T, Da] inputs follow torch's unbatched semantics in the
         reference: the attention then runs over the T frames of the single video.
         """
-        if self.training:
-            raise NotImplementedError(
-                "avsum_b200 implements the inference hot path (model.eval()); the training step of "
-                "scripts/train_av_model.py:86-96 (dropout + backward) is outside this build's scope")
         axis = attn_axis or self.attn_axis
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+                             and (visual.requires_grad or self._train_in_eval)):
+            return self._forward_train(visual, audio, lengths, axis)
         nat = self.native()
         if visual.dim() == 2 and audio.dim() == 2:
             T = visual.shape[0]
@@ -105,6 +105,53 @@ class AVBiLSTMModel(nn.Module):
         if lengths is not None:
             mask = torch.arange(T, device=out.device)[None, :] < torch.as_tensor(lens, device=out.device)[:, None]
             out = torch.where(mask[..., None], out, torch.zeros((), dtype=out.dtype, device=out.device))
+        return out.squeeze()
+
+    # ------------------------------------------------------------------ training forward (autograd)
+    def _forward_train(self, visual, audio, lengths, axis):
+        """The forward of scripts/train_av_model.py:88 with a backward: same layer chain as av_model.py:33-46,
+        every GEMM and both BiLSTMs as native kernels with native backward kernels (avsum_b200/training.py).
+
+        Attention: the reference's training loop feeds ONE video per step (``unsqueeze(0)``, B = 1), where
+        nn.MultiheadAttention over dim 0 degenerates to softmax weight 1 -- context == value projection and the
+        q / k thirds of in_proj receive zero gradient.  A batch here is therefore a set of independent B = 1
+        samples ("literal_b1"); a literal batch with B > 1 (cross-video mixing) or temporal attention has no
+        backward in this build.
+        """
+        from .. import training as T_
+        if visual.dim() == 2:
+            raise NotImplementedError("training with unbatched [T, D] inputs (temporal attention) has no backward here")
+        B, T, _ = visual.shape
+        if axis == "temporal" or (axis == "literal" and B > 1):
+            raise NotImplementedError(
+                "the training path differentiates the reference's own training semantics (B = 1 per sample: "
+                "attn_axis 'literal' with B == 1, or 'literal_b1'); temporal / cross-video attention has no backward")
+        if not visual.is_cuda:
+            raise RuntimeError("AVBiLSTMModel (avsum_b200) trains only on a CUDA sm_100 device; there is no CPU fallback")
+        lens = [T] * B if lengths is None else [int(x) for x in lengths]
+        starts = [b * T for b in range(B)]
+        nat = self.native()
+        xv = visual.reshape(B * T, -1).to(torch.float32)
+        xa = audio.reshape(B * T, -1).to(torch.float32)
+        relu, drop = torch.relu, torch.nn.functional.dropout
+        v = drop(relu(T_.linear(xv, self.visual_fc[0].weight, self.visual_fc[0].bias)), self.visual_fc[2].p, self.training)
+        a = drop(relu(T_.linear(xa, self.audio_fc[0].weight, self.audio_fc[0].bias)), self.audio_fc[2].p, self.training)
+        lw = []
+        for mod in (self.visual_bilstm, self.audio_bilstm):
+            for suf in ("", "_reverse"):
+                lw += [getattr(mod, f"weight_ih_l0{suf}"), getattr(mod, f"weight_hh_l0{suf}"),
+                       getattr(mod, f"bias_ih_l0{suf}"), getattr(mod, f"bias_hh_l0{suf}")]
+        fused = T_.bilstm_pair(v, a, nat, starts, lens, lw)
+        E = self.hidden_dim * 2
+        ctx = T_.linear(fused, self.attention.in_proj_weight[2 * E:], self.attention.in_proj_bias[2 * E:])
+        y = T_.linear(ctx, self.attention.out_proj.weight, self.attention.out_proj.bias)
+        h1 = relu(T_.linear(y, self.scorer[0].weight, self.scorer[0].bias))
+        # Linear(64, 1) + Sigmoid: 128 FLOP / frame, left to torch's elementwise autograd
+        s = torch.sigmoid(torch.nn.functional.linear(h1, self.scorer[2].weight, self.scorer[2].bias))
+        out = s.reshape(B, T, 1)
+        if lengths is not None:
+            mask = torch.arange(T, device=out.device)[None, :] < torch.as_tensor(lens, device=out.device)[:, None]
+            out = out * mask[..., None]
         return out.squeeze()
 
     @torch.no_grad()

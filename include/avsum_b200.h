@@ -143,6 +143,32 @@ avs_status avs_attention(const float* qkv, int64_t rows, int32_t E, int32_t num_
 avs_status avs_temporal_f1(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
                            const int32_t* gt_start, int32_t n_videos, double* f1_host, void* cuda_stream);
 
+/* ---- training step building blocks (scripts/train_av_model.py:86-96: forward in train mode, loss.backward()).
+ * The reference trains through torch autograd; these are the backward kernels an autograd.Function around the
+ * forward building blocks calls (device pointers, fp32).  Optimiser and loss stay the caller's (torch.optim.AdamW,
+ * F.mse_loss -- train_av_model.py:68,91); gradients are all-reduced by the caller (NCCL) in data-parallel runs. */
+
+/* avs_bilstm_pair (tensor-core mode) that also saves what BPTT needs:
+ * save_pre float [rows, 4, 256, 4] = gate pre-activations (i, f, g, o) per (frame, recurrence, hidden unit),
+ * save_c   float [rows, 4, 256]    = cell state after the step; recurrence order as lstm_* in avs_weights. */
+avs_status avs_bilstm_pair_train(avs_model* m, const float* v_emb, const float* a_emb, int64_t total_rows,
+                                 int32_t n_videos, const int32_t* row_start, const int32_t* lengths, float* fused,
+                                 float* save_pre, float* save_c, void* cuda_stream);
+
+/* Backward of avs_bilstm_pair: d_fused [rows, 1024] -> d_v_emb, d_a_emb [rows, 512] and, per recurrence i (order of
+ * avs_weights.lstm_*), dW_ih[i] [1024, 512], dW_hh[i] [1024, 256], db[i] [1024] (= grad of b_ih = grad of b_hh) in the
+ * reference's gate-row order.  `fused`, `v_emb`, `a_emb` are the forward's output / inputs. */
+avs_status avs_bilstm_pair_bwd(avs_model* m, const float* d_fused, const float* save_pre, const float* save_c,
+                               const float* fused, const float* v_emb, const float* a_emb, int64_t total_rows,
+                               int32_t n_videos, const int32_t* row_start, const int32_t* lengths, float* d_v_emb,
+                               float* d_a_emb, float* const* dW_ih, float* const* dW_hh, float* const* db,
+                               void* cuda_stream);
+
+/* Backward of nn.Linear y = x W^T + b:  dX[M, K] = dY W,  dW[N, K] = dY^T X,  db[N] = column sums of dY; any of
+ * dX / dW / db may be NULL.  tcgen05 kind::tf32 GEMMs on round-to-nearest operands; N % 4 == 0 and K % 4 == 0. */
+avs_status avs_linear_bwd(const float* dY, const float* X, const float* W, int64_t M, int32_t N, int32_t K, float* dX,
+                          float* dW, float* db, void* cuda_stream);
+
 /* The metric block of scripts/evaluate.py:25-36 for a batch of videos (the caller right after the forward):
  *   binary_pred = pred > np.mean(pred), binary_target = target > np.mean(target)   (np.mean's pairwise
  *   summation restated exactly), tp / precision / recall / F1 with the 1e-8 guard, scipy.stats.spearmanr

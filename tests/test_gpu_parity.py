@@ -464,3 +464,130 @@ def test_exact_dtw_path_matches_oracle(cuda_ready):
         assert np.array_equal(got, path), (n, m)
         t2, _ = runtime.dtw_path(torch.from_numpy(cost).cuda())
         assert t2 == total
+
+
+# ------------------------------------------------------------------ training step (BASELINE configs[4])
+def _grad_err(got, want):
+    return float((got.double().cpu() - want.double()).abs().max() / want.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("shape", [(300, 512, 128), (2560, 1024, 1024), (77, 64, 1024), (129, 2048, 512), (40, 512, 296)])
+def test_linear_backward_matches_autograd(cuda_ready, shape):
+    from avsum_b200 import training
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(N, K, generator=g, dtype=torch.float64) / K ** 0.5).requires_grad_()
+    b = torch.randn(N, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(M, N, generator=g, dtype=torch.float64)
+    torch.nn.functional.linear(x, w, b).backward(dy)
+    xc, wc, bc = (t.detach().float().cuda().requires_grad_() for t in (x, w, b))
+    y = training.linear(xc, wc, bc)
+    y.backward(dy.float().cuda())
+    assert _grad_err(xc.grad, x.grad) < 3e-3 and _grad_err(wc.grad, w.grad) < 3e-3 and _grad_err(bc.grad, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize("lens", [[37], [5, 64, 1, 33], [20] * 11])
+def test_bilstm_pair_backward_matches_torch_lstm(native, lens):
+    """BPTT kernel + GEMMs vs torch.nn.LSTM autograd on the CPU (fp32): d_emb, dW_ih, dW_hh, db per recurrence."""
+    from avsum_b200 import training
+    sd = synth.seeded_state_dict()
+    R = sum(lens)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    g = torch.Generator().manual_seed(len(lens) + 100)
+    v = torch.randn(R, 512, generator=g).requires_grad_()
+    a = torch.randn(R, 512, generator=g).requires_grad_()
+    dfused = torch.randn(R, 1024, generator=g)
+    lv = torch.nn.LSTM(512, 256, bidirectional=True, batch_first=True)
+    la = torch.nn.LSTM(512, 256, bidirectional=True, batch_first=True)
+    lv.load_state_dict({k.split(".", 1)[1]: t for k, t in sd.items() if k.startswith("visual_bilstm")})
+    la.load_state_dict({k.split(".", 1)[1]: t for k, t in sd.items() if k.startswith("audio_bilstm")})
+    outs = []
+    for s, n in zip(starts, lens):
+        outs.append(torch.cat([lv(v[None, s:s + n])[0][0], la(a[None, s:s + n])[0][0]], dim=1))
+    torch.cat(outs).backward(dfused)
+    vc, ac = v.detach().cuda().requires_grad_(), a.detach().cuda().requires_grad_()
+    weights = []
+    for mod in (lv, la):
+        for suf in ("", "_reverse"):
+            weights += [getattr(mod, f"{n}_l0{suf}").detach().cuda().requires_grad_()
+                        for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    fused = training.bilstm_pair(vc, ac, native, starts, lens, weights)
+    assert float((fused.cpu() - torch.cat(outs).detach()).abs().max()) < 3e-3
+    fused.backward(dfused.cuda())
+    assert _grad_err(vc.grad, v.grad) < 1e-2 and _grad_err(ac.grad, a.grad) < 1e-2
+    i = 0
+    for mod in (lv, la):
+        for suf in ("", "_reverse"):
+            for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                want = getattr(mod, f"{n}_l0{suf}").grad
+                assert _grad_err(weights[i].grad, want) < 1e-2, (n, suf, _grad_err(weights[i].grad, want))
+                i += 1
+
+
+def test_training_step_matches_reference_autograd(cuda_ready):
+    """One step of scripts/train_av_model.py:86-96 on a batch of B = 1 samples: loss, all 28 gradients and the
+    AdamW update vs the reference's torch CPU path (dropout p = 0 so both sides are deterministic)."""
+    vids = [synth.make_video(t, 1024, 128, 4000 + i) for i, t in enumerate([48, 48, 48])]
+    visual = torch.stack([v.visual for v in vids])
+    audio = torch.stack([v.audio for v in vids])
+    target = torch.rand(3, 48, generator=torch.Generator().manual_seed(1))
+    sd = synth.seeded_state_dict(spread=True)
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).train()
+    port.load_state_dict(sd)
+    for seq in (port.visual_fc, port.audio_fc):
+        seq[2].p = 0.0
+    opt_ref = torch.optim.AdamW(port.parameters(), lr=1e-4)
+    preds = torch.stack([port(visual[b:b + 1], audio[b:b + 1], "literal") for b in range(3)])   # B = 1 per sample
+    loss_ref = torch.nn.functional.mse_loss(preds, target)
+    opt_ref.zero_grad()
+    loss_ref.backward()
+
+    m = make_model(spread=True, attn_axis="literal_b1").train()
+    m.visual_fc[2].p = 0.0
+    m.audio_fc[2].p = 0.0
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
+    out = m(visual.cuda(), audio.cuda())
+    assert out.shape == (3, 48) and out.requires_grad
+    loss = torch.nn.functional.mse_loss(out, target.cuda())
+    opt.zero_grad()
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < 1e-3 * abs(float(loss_ref))
+    ref_grads = dict(port.named_parameters())
+    worst = {}
+    for name, p in m.named_parameters():
+        want = ref_grads[name].grad
+        assert p.grad is not None and p.grad.shape == want.shape, name
+        if float(want.abs().max()) == 0.0:
+            assert float(p.grad.abs().max()) == 0.0, name      # q / k thirds of in_proj get exactly zero
+            continue
+        if name.startswith("attention.in_proj"):
+            E = 1024
+            assert float(p.grad[:2 * E].abs().max()) == 0.0
+        l2 = float((p.grad.double().cpu() - want.double()).norm() / want.double().norm())
+        worst[name] = (round(_grad_err(p.grad, want), 4), round(l2, 4))
+    print(worst)
+    # Stated tolerance: the forward runs on 11-bit-significand operands (tf32 / fp16), so a handful of ReLU
+    # pre-activations that the fp32 reference has within ~1e-3 of zero land on the other side; each such unit
+    # switches a whole gradient path on or off (the x50 "spread" head makes those paths large).  The per-layer
+    # backward kernels are checked tightly above (3e-3 linear, 1e-2 BiLSTM); end to end we require 6 % in the
+    # max norm and 4 % in the L2 norm for every one of the 28 gradients.
+    assert max(v[0] for v in worst.values()) < 6e-2 and max(v[1] for v in worst.values()) < 4e-2, worst
+    opt.step()
+    opt_ref.step()
+    for name, p in m.named_parameters():
+        assert float((p.detach().cpu() - ref_grads[name].detach()).abs().max()) < 2.5e-4, name   # lr-sized updates
+    # the updated parameters are re-packed for the next forward
+    out2 = m(visual.cuda(), audio.cuda())
+    assert float((out2 - out).abs().max()) > 0
+
+
+def test_training_rejects_unsupported_attention(cuda_ready):
+    m = make_model(attn_axis="temporal").train()
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(2, 8, 1024).cuda(), torch.randn(2, 8, 128).cuda())
+    m = make_model(attn_axis="literal").train()
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(2, 8, 1024).cuda(), torch.randn(2, 8, 128).cuda())
+    out = m(torch.randn(1, 8, 1024).cuda(), torch.randn(1, 8, 128).cuda())      # the reference's B = 1 step
+    assert out.shape == (8,) and out.requires_grad

@@ -53,3 +53,28 @@ def test_two_rank_gather_equals_single_process():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, lengths, n_segs, ret), nprocs=2, join=True)
     assert ret[0] == want and ret[1] == want
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from avsum_b200.training import allreduce_gradients
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    for i, p in enumerate(lin.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = allreduce_gradients(lin.parameters())
+    ret[rank] = (n, [float(p.grad.flatten()[0]) for p in lin.parameters()])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_averages_one_flat_bucket():
+    """Data-parallel training (BASELINE configs[4]): one flat bucket, sum over ranks, divided by world."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    want = [1.5 * (i + 1) for i in range(4)]          # mean of (1, 2) * (i + 1)
+    assert ret[0][0] == ret[1][0] == 5 * 3 + 3 + 3 * 2 + 2
+    assert ret[0][1] == want and ret[1][1] == want
