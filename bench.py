@@ -311,14 +311,21 @@ def main():
         kernels[name] = rec
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     drec = kernels[dom]
+    # DRAM traffic per launch of the dominant kernel, from the committed ncu --set full capture of this workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    if world == 1 and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
     if "tflops" in drec:
         roofline = {"kernel": dom, "bound": "tensor", "achieved": drec["tflops"], "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": drec["tflops"] / peaks["tflops"], "traffic": None,
+                    "frac": drec["tflops"] / peaks["tflops"], "traffic": traffic,
                     "peak_source": peaks["source"] + " bf16 sustained (MEASURED_PEAKS.json)",
-                    "share_of_step": drec["ms_per_step"] / ms_per_step}
+                    "share_of_step": drec["ms_per_step"] / ms_per_step,
+                    "note": "the LSTM recurrence is a chain of max(T) dependent steps (latency bound, SURVEY 8d); "
+                            "see kernels{} for the GEMM / attention tensor-pipe fractions"}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": drec.get("gbs"), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": (drec.get("gbs") or 0) / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "frac": (drec.get("gbs") or 0) / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
                     "share_of_step": drec["ms_per_step"] / ms_per_step}
 
     line = {
