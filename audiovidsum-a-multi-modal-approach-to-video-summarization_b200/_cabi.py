@@ -28,7 +28,7 @@ EXPORTS = [
     "avs_attention", "avs_temporal_f1", "avs_launch_count", "avs_profile", "avs_profile_stages",
     "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace",
     "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
-    "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd",
+    "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
 ]
 
 
@@ -96,6 +96,9 @@ def lib() -> C.CDLL:
     L.avs_forward.argtypes = [vp, vp, vp, i64, i32, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
     L.avs_summarize.restype = C.c_int
     L.avs_summarize.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, C.c_int, vp]
+    L.avs_forward_summarize.restype = C.c_int
+    L.avs_forward_summarize.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, C.c_int, C.c_int, vp, vp, vp, i32, i32,
+                                        vp, vp, vp, vp, vp, C.c_int, vp]
     L.avs_linear.restype = C.c_int
     L.avs_linear.argtypes = [vp, vp, vp, i64, i32, i32, C.c_int, C.c_int, vp, vp]
     L.avs_bilstm_pair.restype = C.c_int

@@ -132,6 +132,14 @@ __global__ void permute_gate_rows_kernel(const float* __restrict__ src, float* _
         dst[static_cast<size_t>(p) * cols + k] = round_tf32 ? to_tf32_rn(v) : v;
     }
 }
+// Small host arrays (launch plans, sequence descriptors) travel to the device INSIDE kernel parameters instead of
+// through cudaMemcpyAsync: a pageable-memory copy would queue on the H2D copy engine behind the multi-megabyte
+// feature transfers of the next video group and stall the pipeline.
+struct UploadPayload { uint32_t w[896]; };   // 3,584 bytes, inside the 4 KB kernel-parameter limit
+__global__ void upload_kernel(UploadPayload p, uint32_t* __restrict__ dst, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = p.w[i];
+}
+
 __global__ void permute_gate_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                          float* __restrict__ dst) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,6 +170,10 @@ struct avs_model {
     uint16_t *fc_v_w_l[2], *fc_a_w_l[2], *ih_v_l[2], *ih_a_l[2], *in_w_l[2], *out_w_l[2], *sc0_w_l[2];
     Arena ws;       // activations
     Arena staging;  // raw weights during packing
+    Arena host_in;  // device copies of host-space inputs when a call is pipelined by video group
+    Arena ws_grp[3];                 // activations of groups 1..3 (group 0 uses ws): the groups run concurrently
+    cudaStream_t grp_stream[3] = {}; // compute streams of groups 1..3 (group 0 runs on the caller's stream)
+    cudaEvent_t ev_grp[3] = {};
     // host-space calls: H2D copies run on their own stream, chunked, so that the row-parallel
     // front of the pipeline (tf32 rounding, fc and LSTM-input GEMMs) overlaps the PCIe transfer
     static constexpr int MAX_CHUNKS = 4;
@@ -265,6 +277,24 @@ avs_status pack_weights(avs_model* m, const avs_weights* w) {
         AVS_TRY(convert_f32(m->ih_a_x, m->ih_a_l[l], 2ll * G4 * H, dt, 0, st));
     }
     AVS_CUDA(cudaStreamSynchronize(st));
+    return AVS_OK;
+}
+
+avs_status upload_small(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st) {
+    AVS_CHECK(bytes % 4 == 0, AVS_ERR_INVALID, "upload_small: size must be a multiple of 4");
+    const uint32_t* src = static_cast<const uint32_t*>(src_host);
+    uint32_t* dst = static_cast<uint32_t*>(dst_dev);
+    size_t words = bytes / 4;
+    while (words > 0) {
+        UploadPayload p;
+        const int n = static_cast<int>(std::min<size_t>(words, 896));
+        std::memcpy(p.w, src, static_cast<size_t>(n) * 4);
+        upload_kernel<<<1, 256, 0, st>>>(p, dst, n);
+        AVS_CUDA(cudaGetLastError());
+        src += n;
+        dst += n;
+        words -= n;
+    }
     return AVS_OK;
 }
 
@@ -468,6 +498,10 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming);
         for (int i = 0; i < avs_model::MAX_CHUNKS && ce == cudaSuccess; ++i)
             ce = cudaEventCreateWithFlags(&m->ev_chunk[i], cudaEventDisableTiming);
+        for (int i = 0; i < 3 && ce == cudaSuccess; ++i) {
+            ce = cudaStreamCreateWithFlags(&m->grp_stream[i], cudaStreamNonBlocking);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_grp[i], cudaEventDisableTiming);
+        }
         if (ce != cudaSuccess) {
             set_error("creating the copy stream / events failed: %s", cudaGetErrorString(ce));
             s = AVS_ERR_CUDA;
@@ -497,6 +531,12 @@ void avs_model_destroy(avs_model* m) {
     cudaDeviceSynchronize();
     m->ws.release();
     m->staging.release();
+    m->host_in.release();
+    for (int i = 0; i < 3; ++i) {
+        m->ws_grp[i].release();
+        if (m->grp_stream[i]) cudaStreamDestroy(m->grp_stream[i]);
+        if (m->ev_grp[i]) cudaEventDestroy(m->ev_grp[i]);
+    }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     for (cudaEvent_t e : m->ev_chunk)
@@ -505,10 +545,139 @@ void avs_model_destroy(avs_model* m) {
     delete m;
 }
 
+static avs_status forward_impl(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
+                               int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int attn_axis,
+                               int precision, float* scores, int space, void* cuda_stream, Arena* arena = nullptr);
+
+// scores_dev_out != nullptr (host space only): leave the scores on the device (pointer returned), skip the D2H copy
+// and the final synchronisation -- the caller continues on the stream (avs_forward_summarize).
+static avs_status forward_entry(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
+                                int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int attn_axis,
+                                int precision, float* scores, int space, void* cuda_stream, float** scores_dev_out,
+                                const int32_t* positions_host, int32_t** positions_dev_out) {
+    // Host-space calls on large packed batches are pipelined by VIDEO GROUP: all H2D copies are queued on the
+    // copy stream up front, and the complete forward of group g (GEMMs, recurrences, attention, score head) runs
+    // on the caller's stream as soon as its rows have landed -- i.e. while group g+1 is still crossing PCIe.
+    // The recurrence of a group lasts as long as its longest video, so callers that order the batch longest
+    // video first (data/dataset.py packed_batches does) hide most of the compute behind the transfer.
+    const bool per_video = attn_axis == AVS_ATTN_TEMPORAL || attn_axis == AVS_ATTN_LITERAL_B1;
+    int n_groups = 1;
+    if (m != nullptr && space == AVS_HOST && per_video && visual && audio && (scores || scores_dev_out) && row_start &&
+        lengths &&
+        n_videos >= 2 && total_rows >= 4096 && total_rows < (1ll << 31)) {
+        bool ordered = true;   // groups must be contiguous, disjoint row ranges
+        for (int b = 0; b < n_videos && ordered; ++b) {
+            ordered = lengths[b] >= 0 && row_start[b] >= 0 &&
+                      static_cast<int64_t>(row_start[b]) + lengths[b] <= total_rows &&
+                      (b == 0 || row_start[b] >= row_start[b - 1] + lengths[b - 1]);
+        }
+        if (ordered) n_groups = (total_rows >= 16384 && n_videos >= 12) ? 4 : ((total_rows >= 8192 && n_videos >= 6) ? 3 : 2);
+    }
+    if (n_groups == 1) {
+        if (scores_dev_out == nullptr)
+            return forward_impl(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, scores,
+                                space, cuda_stream);
+        // small / unsplittable host batch, scores wanted on the device: stage the inputs, run in device space
+        AVS_CHECK(m && visual && audio && total_rows >= 0, AVS_ERR_INVALID, "avs_forward_summarize: bad arguments");
+        Guard g1(m->device);
+        cudaStream_t s1 = static_cast<cudaStream_t>(cuda_stream);
+        const size_t r1 = static_cast<size_t>(total_rows);
+        AVS_TRY(m->host_in.reserve(r1 * (m->Dv + m->Da + 2) * 4 + 5 * 256));
+        m->host_in.reset();
+        float* v1 = m->host_in.take<float>(r1 * m->Dv);
+        float* a1 = m->host_in.take<float>(r1 * m->Da);
+        float* sc1 = m->host_in.take<float>(r1);
+        int32_t* p1 = m->host_in.take<int32_t>(r1);
+        AVS_CUDA(cudaMemcpyAsync(v1, visual, r1 * m->Dv * 4, cudaMemcpyHostToDevice, s1));
+        AVS_CUDA(cudaMemcpyAsync(a1, audio, r1 * m->Da * 4, cudaMemcpyHostToDevice, s1));
+        if (positions_host) AVS_CUDA(cudaMemcpyAsync(p1, positions_host, r1 * 4, cudaMemcpyHostToDevice, s1));
+        *scores_dev_out = sc1;
+        if (positions_dev_out) *positions_dev_out = p1;
+        return forward_impl(m, v1, a1, total_rows, n_videos, row_start, lengths, attn_axis, precision, sc1, AVS_DEVICE,
+                            cuda_stream);
+    }
+
+    AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int Dv = m->Dv, Da = m->Da;
+    const size_t uR = static_cast<size_t>(total_rows);
+    AVS_TRY(m->host_in.reserve(uR * (Dv + Da + 2) * 4 + 5 * 256));
+    m->host_in.reset();
+    float* in_v = m->host_in.take<float>(uR * Dv);
+    float* in_a = m->host_in.take<float>(uR * Da);
+    float* sc_dev = m->host_in.take<float>(uR);
+    int32_t* pos_dev = m->host_in.take<int32_t>(uR);
+    // group boundaries at video boundaries.  Shares shrink towards the end: what remains after the last byte has
+    // crossed PCIe is the last group's compute, so it should be the smallest (and, for a longest-first batch, the
+    // one with the shortest recurrence).
+    static const int kShare[5][4] = {{0, 0, 0, 0}, {100, 0, 0, 0}, {60, 100, 0, 0}, {45, 80, 100, 0}, {40, 70, 90, 100}};
+    int first[avs_model::MAX_CHUNKS + 1];
+    first[0] = 0;
+    for (int gi = 1; gi < n_groups; ++gi) {
+        const int64_t want = total_rows * kShare[n_groups][gi - 1] / 100;
+        int b = first[gi - 1] + 1;
+        while (b < n_videos - (n_groups - gi) && row_start[b] < want) ++b;
+        first[gi] = b;
+    }
+    first[n_groups] = n_videos;
+    AVS_CUDA(cudaEventRecord(m->ev_start, st));                 // staging is free once prior work on st is done
+    AVS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
+    if (positions_host)   // summary input, a few KB: goes first so it never waits behind the features
+        AVS_CUDA(cudaMemcpyAsync(pos_dev, positions_host, uR * 4, cudaMemcpyHostToDevice, m->copy_stream));
+    int64_t lo[avs_model::MAX_CHUNKS], hi[avs_model::MAX_CHUNKS];
+    for (int gi = 0; gi < n_groups; ++gi) {
+        lo[gi] = row_start[first[gi]];
+        hi[gi] = static_cast<int64_t>(row_start[first[gi + 1] - 1]) + lengths[first[gi + 1] - 1];
+        const size_t rows = static_cast<size_t>(hi[gi] - lo[gi]);
+        if (rows) {
+            AVS_CUDA(cudaMemcpyAsync(in_v + lo[gi] * Dv, visual + lo[gi] * Dv, rows * Dv * 4, cudaMemcpyHostToDevice,
+                                     m->copy_stream));
+            AVS_CUDA(cudaMemcpyAsync(in_a + lo[gi] * Da, audio + lo[gi] * Da, rows * Da * 4, cudaMemcpyHostToDevice,
+                                     m->copy_stream));
+        }
+        AVS_CUDA(cudaEventRecord(m->ev_chunk[gi], m->copy_stream));
+    }
+    // every group on its own stream and workspace: the recurrence of group g (a chain of max(T_g) dependent steps
+    // that leaves most of the chip idle) keeps running while group g+1 starts
+    std::vector<int32_t> rs;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const int nv = first[gi + 1] - first[gi];
+        rs.assign(nv, 0);
+        for (int b = 0; b < nv; ++b) rs[b] = row_start[first[gi] + b] - static_cast<int32_t>(lo[gi]);
+        cudaStream_t gs = gi == 0 ? st : m->grp_stream[gi - 1];
+        if (gi > 0) AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_start, 0));   // not before earlier work on st is done
+        AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_chunk[gi], 0));
+        AVS_TRY(forward_impl(m, in_v + lo[gi] * Dv, in_a + lo[gi] * Da, hi[gi] - lo[gi], nv, rs.data(),
+                             lengths + first[gi], attn_axis, precision, sc_dev + lo[gi], AVS_DEVICE, gs,
+                             gi == 0 ? nullptr : &m->ws_grp[gi - 1]));
+        if (gi > 0) {
+            AVS_CUDA(cudaEventRecord(m->ev_grp[gi - 1], gs));
+            AVS_CUDA(cudaStreamWaitEvent(st, m->ev_grp[gi - 1], 0));
+        }
+    }
+    if (scores_dev_out != nullptr) {   // the caller continues on the stream with the scores still on the device
+        *scores_dev_out = sc_dev;
+        if (positions_dev_out) *positions_dev_out = pos_dev;
+        return AVS_OK;
+    }
+    AVS_CUDA(cudaMemcpyAsync(scores, sc_dev, uR * 4, cudaMemcpyDeviceToHost, st));
+    AVS_CUDA(cudaStreamSynchronize(st));
+    return AVS_OK;
+}
+
 avs_status avs_forward(avs_model* m, const float* visual, const float* audio, int64_t total_rows, int32_t n_videos,
                        const int32_t* row_start, const int32_t* lengths, int attn_axis, int precision, float* scores,
                        int space, void* cuda_stream) {
+    return forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, scores, space,
+                         cuda_stream, nullptr, nullptr, nullptr);
+}
+
+static avs_status forward_impl(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
+                               int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int attn_axis,
+                               int precision, float* scores, int space, void* cuda_stream, Arena* arena) {
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    Arena& WS = arena ? *arena : m->ws;
     AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
     AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
     AVS_CHECK(attn_axis == AVS_ATTN_LITERAL || attn_axis == AVS_ATTN_TEMPORAL || attn_axis == AVS_ATTN_LITERAL_B1,
@@ -548,23 +717,23 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     const size_t bytes = uR * (Dv + Da) * 4 + (bf16 ? uR * (Dv + Da) * 2 : 0) + 2 * uR * H * asz + 2 * uR * 2 * G4 * 4 +
                          3 * uR * E * asz + (literal_rows ? 0 : uR * 3 * E * dtype_size(qkv_dt)) + uR * 4 +
                          (plan.host.size() + 3 * static_cast<size_t>(n_seqs)) * 4 + 64 * 256;
-    AVS_TRY(m->ws.reserve(bytes));
-    m->ws.reset();
-    float* in_v = m->ws.take<float>(uR * Dv);
-    float* in_a = m->ws.take<float>(uR * Da);
-    uint16_t* in_v16 = bf16 ? m->ws.take<uint16_t>(uR * Dv) : nullptr;
-    uint16_t* in_a16 = bf16 ? m->ws.take<uint16_t>(uR * Da) : nullptr;
-    char* v_emb = m->ws.take<char>(uR * H * asz);
-    char* a_emb = m->ws.take<char>(uR * H * asz);
-    float* xg_v = m->ws.take<float>(uR * 2 * G4);
-    float* xg_a = m->ws.take<float>(uR * 2 * G4);
-    char* fused = m->ws.take<char>(uR * E * asz);
-    char* qkv = literal_rows ? nullptr : m->ws.take<char>(uR * 3 * E * dtype_size(qkv_dt));
-    char* ctx = m->ws.take<char>(uR * E * asz);
-    char* attn_out = m->ws.take<char>(uR * E * asz);
-    float* scores_dev = space == AVS_DEVICE ? scores : m->ws.take<float>(uR);
-    int32_t* plan_dev = m->ws.take<int32_t>(plan.host.size());
-    int32_t* seq_dev = m->ws.take<int32_t>(3 * static_cast<size_t>(std::max(n_seqs, 1)));
+    AVS_TRY(WS.reserve(bytes));
+    WS.reset();
+    float* in_v = WS.take<float>(uR * Dv);
+    float* in_a = WS.take<float>(uR * Da);
+    uint16_t* in_v16 = bf16 ? WS.take<uint16_t>(uR * Dv) : nullptr;
+    uint16_t* in_a16 = bf16 ? WS.take<uint16_t>(uR * Da) : nullptr;
+    char* v_emb = WS.take<char>(uR * H * asz);
+    char* a_emb = WS.take<char>(uR * H * asz);
+    float* xg_v = WS.take<float>(uR * 2 * G4);
+    float* xg_a = WS.take<float>(uR * 2 * G4);
+    char* fused = WS.take<char>(uR * E * asz);
+    char* qkv = literal_rows ? nullptr : WS.take<char>(uR * 3 * E * dtype_size(qkv_dt));
+    char* ctx = WS.take<char>(uR * E * asz);
+    char* attn_out = WS.take<char>(uR * E * asz);
+    float* scores_dev = space == AVS_DEVICE ? scores : WS.take<float>(uR);
+    int32_t* plan_dev = WS.take<int32_t>(plan.host.size());
+    int32_t* seq_dev = WS.take<int32_t>(3 * static_cast<size_t>(std::max(n_seqs, 1)));
 
     const GemmW w_fc_v{m->fc_v_w_x, m->fc_v_w_t, m->fc_v_w_l}, w_fc_a{m->fc_a_w_x, m->fc_a_w_t, m->fc_a_w_l};
     const GemmW w_ih_v{m->ih_v_x, m->ih_v_t, m->ih_v_l}, w_ih_a{m->ih_a_x, m->ih_a_t, m->ih_a_l};
@@ -575,7 +744,7 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     // user features -> K1 visual_fc / audio_fc (Linear + ReLU; Dropout is identity in eval, av_model.py:35-36)
     // -> K2a LSTM input projections for both directions (av_model.py:39-40).  In host space chunk c+1 is in
     // flight on the copy stream while chunk c is being computed.
-    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
+    AVS_TRY(upload_small(plan_dev, plan.host.data(), plan.host.size() * 4, st));
     const int n_chunks = (space == AVS_HOST && R >= 2048) ? avs_model::MAX_CHUNKS : 1;
     const int64_t chunk_rows = ((R + n_chunks - 1) / n_chunks + 127) / 128 * 128;
     if (space == AVS_HOST) {
@@ -685,7 +854,7 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
             }
             seq_max = n_videos;
         }
-        AVS_CUDA(cudaMemcpyAsync(seq_dev, sd.data(), sd.size() * 4, cudaMemcpyHostToDevice, st));
+        AVS_TRY(upload_small(seq_dev, sd.data(), sd.size() * 4, st));
         SeqDesc seqs{seq_dev, seq_dev + n_seqs, seq_dev + 2 * n_seqs, n_seqs, seq_max};
         StageTimer tm(ST_ATTENTION, st);
         if (tc_attn) AVS_TRY(attention_tc(qkv, act, R, E, m->heads, seqs, ctx, E, act, 0, st));
@@ -722,11 +891,12 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
     return AVS_OK;
 }
 
-avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* positions, int32_t n_videos,
-                         const int32_t* row_start, const int32_t* lengths, const int32_t* n_frames, const int32_t* cps,
-                         const int32_t* cps_start, int32_t prop_num, int32_t prop_den, uint8_t* picks,
-                         int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start, int space,
-                         void* cuda_stream) {
+static avs_status summarize_impl(avs_model* m, const float* scores, const int32_t* positions, int32_t n_videos,
+                                 const int32_t* row_start, const int32_t* lengths, const int32_t* n_frames,
+                                 const int32_t* cps, const int32_t* cps_start, int32_t prop_num, int32_t prop_den,
+                                 uint8_t* picks, int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start,
+                                 int in_space, int space, void* cuda_stream) {
+    // in_space: where scores / positions live; space: where picks / seg_mean / summary go
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
     AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
     AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
@@ -784,7 +954,8 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
 
     size_t need = desc.size() * 4 + off64.size() * 8 + static_cast<size_t>(total_S) * (8 + 8 + 1) +
                   static_cast<size_t>(keep_words) * 4 + static_cast<size_t>(dp_elems) * 8 + 64 * 256;
-    if (space == AVS_HOST) need += static_cast<size_t>(rows) * 8 + static_cast<size_t>(sum_bytes);
+    if (in_space == AVS_HOST) need += static_cast<size_t>(rows) * 8 + 512;
+    if (space == AVS_HOST) need += static_cast<size_t>(sum_bytes) + static_cast<size_t>(total_S) + 512;
     AVS_TRY(m->ws.reserve(need));
     m->ws.reset();
     int64_t* off_dev = m->ws.take<int64_t>(off64.size());
@@ -797,13 +968,15 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
     const int32_t* pos = positions;
     uint8_t* picks_dev = picks;
     uint8_t* summary_dev = summary;
-    if (space == AVS_HOST) {
+    if (in_space == AVS_HOST) {
         float* s2 = m->ws.take<float>(rows);
         int32_t* p2 = m->ws.take<int32_t>(rows);
         AVS_CUDA(cudaMemcpyAsync(s2, scores, rows * 4, cudaMemcpyHostToDevice, st));
         AVS_CUDA(cudaMemcpyAsync(p2, positions, rows * 4, cudaMemcpyHostToDevice, st));
         sc = s2;
         pos = p2;
+    }
+    if (space == AVS_HOST) {
         picks_dev = m->ws.take<uint8_t>(std::max(total_S, 1));
         if (summary) summary_dev = m->ws.take<uint8_t>(sum_bytes);
     }
@@ -842,6 +1015,49 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
         AVS_CUDA(cudaStreamSynchronize(st));
     }
     return AVS_OK;
+}
+
+avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* positions, int32_t n_videos,
+                         const int32_t* row_start, const int32_t* lengths, const int32_t* n_frames, const int32_t* cps,
+                         const int32_t* cps_start, int32_t prop_num, int32_t prop_den, uint8_t* picks,
+                         int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start, int space,
+                         void* cuda_stream) {
+    return summarize_impl(m, scores, positions, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
+                          prop_den, picks, seg_mean, summary, summary_start, space, space, cuda_stream);
+}
+
+avs_status avs_forward_summarize(avs_model* m, const float* visual, const float* audio, const int32_t* positions,
+                                 int64_t total_rows, int32_t n_videos, const int32_t* row_start,
+                                 const int32_t* lengths, int attn_axis, int precision, const int32_t* n_frames,
+                                 const int32_t* cps, const int32_t* cps_start, int32_t prop_num, int32_t prop_den,
+                                 float* scores, uint8_t* picks, int64_t* seg_mean, uint8_t* summary,
+                                 const int64_t* summary_start, int space, void* cuda_stream) {
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
+    AVS_CHECK(positions != nullptr && scores != nullptr, AVS_ERR_INVALID, "positions / scores pointer is null");
+    if (space == AVS_DEVICE) {
+        AVS_TRY(forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, scores,
+                              AVS_DEVICE, cuda_stream, nullptr, nullptr, nullptr));
+        return summarize_impl(m, scores, positions, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
+                              prop_den, picks, seg_mean, summary, summary_start, AVS_DEVICE, AVS_DEVICE, cuda_stream);
+    }
+    // host space: features in, scores stay on the device for pooling + knapsack, everything comes back with ONE
+    // synchronisation at the end (no D2H -> H2D round trip of the scores between the two halves)
+    int max_len = 0;
+    AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
+    if (total_rows == 0 || n_videos == 0 || max_len == 0)
+        return summarize_impl(m, scores, positions, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
+                              prop_den, picks, seg_mean, summary, summary_start, AVS_HOST, AVS_HOST, cuda_stream);
+    float* sc_dev = nullptr;
+    int32_t* pos_dev = nullptr;
+    AVS_TRY(forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, nullptr,
+                          AVS_HOST, cuda_stream, &sc_dev, positions, &pos_dev));
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[0], 0));   // positions travelled on the copy stream (grouped path)
+    AVS_CUDA(cudaMemcpyAsync(scores, sc_dev, static_cast<size_t>(total_rows) * 4, cudaMemcpyDeviceToHost, st));
+    return summarize_impl(m, sc_dev, pos_dev, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num, prop_den,
+                          picks, seg_mean, summary, summary_start, AVS_DEVICE, AVS_HOST, cuda_stream);
 }
 
 avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t M, int32_t N, int32_t K, int relu,

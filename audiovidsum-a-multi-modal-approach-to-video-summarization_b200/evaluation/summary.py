@@ -52,12 +52,17 @@ def summarize_videos(model, videos, proportion=0.15, attn_axis: Optional[str] = 
     visual = torch.cat([v.visual for v in videos], dim=0)
     audio = torch.cat([v.audio for v in videos], dim=0)
     axis = attn_axis or ("literal_b1" if model.attn_axis == "literal" else model.attn_axis)
-    scores = nat.forward_rows(visual, audio, starts, lens, axis, model.precision)
     positions = torch.as_tensor(np.concatenate([np.asarray(v.positions, dtype=np.int32) for v in videos]))
-    if scores.is_cuda:
-        positions = positions.to(scores.device)
-    picks, seg_mean, summary, cps_start, sum_start = nat.summarize_rows(
-        scores, positions, starts, lens, [v.n_frames for v in videos], [v.cps for v in videos], proportion)
+    if visual.is_cuda:
+        positions = positions.to(visual.device)
+    if axis == "literal":     # cross-video mixing cannot be pipelined by video group: two calls
+        scores = nat.forward_rows(visual, audio, starts, lens, axis, model.precision)
+        picks, seg_mean, summary, cps_start, sum_start = nat.summarize_rows(
+            scores, positions, starts, lens, [v.n_frames for v in videos], [v.cps for v in videos], proportion)
+    else:
+        scores, picks, seg_mean, summary, cps_start, sum_start = nat.score_and_summarize_rows(
+            visual, audio, positions, starts, lens, [v.n_frames for v in videos], [v.cps for v in videos], proportion,
+            axis, model.precision)
     picks_h, mean_h, sum_h, scores_h = picks.cpu().numpy(), seg_mean.cpu().numpy(), summary.cpu().numpy(), scores.cpu()
     out = []
     for i in range(len(videos)):

@@ -156,6 +156,53 @@ class NativeModel:
         return picks, seg_mean, summary, cps_start, summary_start
 
 
+    # -- forward + summary in one native call -----------------------------------------------
+    def score_and_summarize_rows(self, visual: torch.Tensor, audio: torch.Tensor, positions: torch.Tensor, row_start,
+                                 lengths, n_frames, cps_list, proportion=0.15, attn_axis: str = "literal_b1",
+                                 precision: str = "tf32", want_summary: bool = True):
+        """avs_forward_summarize: the whole "scored + summarised" step.  All tensors on the model's GPU, or all on
+        the host (pinned recommended): then the features are pipelined across PCIe by video group, the scores
+        never leave the device between the two halves and the call returns after one synchronisation.
+        Returns (scores fp32 [R], picks uint8 [sum S], seg_mean int64 [sum S], summary uint8 | None, cps_start,
+        summary_start)."""
+        vd, ad, _, _ = self.dims
+        if visual.dim() != 2 or audio.dim() != 2 or visual.shape[1] != vd or audio.shape[1] != ad:
+            raise ValueError(f"expected visual [R, {vd}] and audio [R, {ad}], got {tuple(visual.shape)} / {tuple(audio.shape)}")
+        if not (visual.device == audio.device == positions.device):
+            raise ValueError("visual, audio and positions must live on the same device")
+        R = int(visual.shape[0])
+        visual = visual.to(torch.float32).contiguous()
+        audio = audio.to(torch.float32).contiguous()
+        positions = positions.to(torch.int32).contiguous()
+        frac = Fraction(proportion).limit_denominator(10000) if not isinstance(proportion, tuple) else Fraction(*proportion)
+        rs, ln, nf = _i32(row_start), _i32(lengths), _i32(n_frames)
+        n = int(rs.size)
+        cps_start = np.zeros(n + 1, dtype=np.int32)
+        for i, c in enumerate(cps_list):
+            cps_start[i + 1] = cps_start[i] + int(np.asarray(c).reshape(-1, 2).shape[0])
+        cps = _i32(np.concatenate([np.asarray(c, dtype=np.int32).reshape(-1, 2) for c in cps_list], axis=0)
+                   if n else np.zeros((0, 2), np.int32))
+        total_S = int(cps_start[-1])
+        summary_start = np.zeros(n + 1, dtype=np.int64)
+        summary_start[1:] = np.cumsum(nf.astype(np.int64))
+        on_gpu = visual.is_cuda
+        dev, pin = visual.device, not on_gpu
+        scores = torch.empty(R, dtype=torch.float32, device=dev, pin_memory=pin)
+        picks = torch.empty(total_S, dtype=torch.uint8, device=dev, pin_memory=pin)
+        seg_mean = torch.empty(total_S, dtype=torch.int64, device=dev, pin_memory=pin)
+        summary = torch.empty(int(summary_start[-1]), dtype=torch.uint8, device=dev, pin_memory=pin) if want_summary else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.avs_forward_summarize(
+                self._handle, C.c_void_p(visual.data_ptr()), C.c_void_p(audio.data_ptr()), C.c_void_p(positions.data_ptr()),
+                R, n, _cabi.np_ptr(rs), _cabi.np_ptr(ln), _cabi.ATTN_AXES[attn_axis], _cabi.PRECISIONS[precision],
+                _cabi.np_ptr(nf), _cabi.np_ptr(cps), _cabi.np_ptr(cps_start), int(frac.numerator), int(frac.denominator),
+                C.c_void_p(scores.data_ptr()), C.c_void_p(picks.data_ptr()), C.c_void_p(seg_mean.data_ptr()),
+                C.c_void_p(summary.data_ptr()) if want_summary else None,
+                _cabi.np_ptr(summary_start) if want_summary else None,
+                _cabi.AVS_DEVICE if on_gpu else _cabi.AVS_HOST, _stream_ptr(self.device)))
+        return scores, picks, seg_mean, summary, cps_start, summary_start
+
+
 # ---- stateless building blocks (device tensors) ------------------------------------
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,

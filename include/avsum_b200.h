@@ -115,6 +115,16 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
                          uint8_t* picks, int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start,
                          int space, void* cuda_stream);
 
+/* avs_forward followed by avs_summarize in one call (the "scored + summarised" step of BASELINE.json): scores stay
+ * on the device between the two halves; in host space the call returns after ONE synchronisation with scores,
+ * picks, seg_mean (may be NULL) and summary (may be NULL) in the caller's host buffers. */
+avs_status avs_forward_summarize(avs_model* m, const float* visual, const float* audio, const int32_t* positions,
+                                 int64_t total_rows, int32_t n_videos, const int32_t* row_start,
+                                 const int32_t* lengths, int attn_axis, int precision, const int32_t* n_frames,
+                                 const int32_t* cps, const int32_t* cps_start, int32_t prop_num, int32_t prop_den,
+                                 float* scores, uint8_t* picks, int64_t* seg_mean, uint8_t* summary,
+                                 const int64_t* summary_start, int space, void* cuda_stream);
+
 /* ---- building blocks (device pointers only), exported so each kernel can be parity-tested
  * against the reference sub-module it replaces and reused by
  * models/attention.py's drop-in. ---- */

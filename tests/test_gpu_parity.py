@@ -591,3 +591,23 @@ def test_training_rejects_unsupported_attention(cuda_ready):
         m(torch.randn(2, 8, 1024).cuda(), torch.randn(2, 8, 128).cuda())
     out = m(torch.randn(1, 8, 1024).cuda(), torch.randn(1, 8, 128).cuda())      # the reference's B = 1 step
     assert out.shape == (8,) and out.requires_grad
+
+
+def test_fused_score_and_summarize_equals_two_calls(native):
+    """avs_forward_summarize (host space: pipelined by video group, one sync) == avs_forward + avs_summarize."""
+    vids = sorted(synth.config2()[:30], key=lambda v: -v.T)
+    lens = [v.T for v in vids]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    visual, audio = torch.cat([v.visual for v in vids]), torch.cat([v.audio for v in vids])
+    pos = torch.from_numpy(np.concatenate([v.positions for v in vids]).astype(np.int32))
+    nf, cps = [v.n_frames for v in vids], [v.cps for v in vids]
+    for axis in ("literal_b1", "temporal"):
+        want_s = native.forward_rows(visual.cuda(), audio.cuda(), starts, lens, axis)
+        want = native.summarize_rows(want_s, pos.cuda(), starts, lens, nf, cps, 0.15)
+        for dev in ("cpu", "cuda"):
+            v, a, p = (t.pin_memory() if dev == "cpu" else t.cuda() for t in (visual, audio, pos))
+            got = native.score_and_summarize_rows(v, a, p, starts, lens, nf, cps, 0.15, axis)
+            torch.cuda.synchronize()
+            assert torch.equal(got[0].cpu(), want_s.cpu()), (axis, dev)        # same kernels, same data
+            for g, w in zip(got[1:4], want[:3]):
+                assert torch.equal(g.cpu(), w.cpu()), (axis, dev)
