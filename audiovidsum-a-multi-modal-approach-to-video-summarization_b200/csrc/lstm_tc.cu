@@ -44,9 +44,13 @@ constexpr int FUSED_LD = 4 * HC;    // 1024
 // PARTS = 4: all NB slots are real videos, one CTA per SM.  PARTS = 2 (NB = 16 only): 8 real videos per
 // cluster (the other 8 MMA columns are padding), 9 warps and 256 TMEM columns per CTA, so TWO CTAs of
 // different clusters share an SM and one cluster's DSMEM exchange overlaps the other's MMA + cell math.
+// CHAINS = 2 (with PARTS = 2): the two parts are INDEPENDENT recurrences (4 videos each) with their own h
+// buffers, accumulator, barriers and MMA-issuing warp; they share the TMEM-resident W_hh slice.  A step of
+// one chain is exchange -> MMA -> cell math -> send; with two chains per CTA and two CTAs per SM four such
+// chains interleave on every SM, so the DSMEM-bandwidth-bound exchange of one hides behind the others' work.
 constexpr int W_TMEM_COLS = HC / 2;        // W_hh slice as packed fp16 pairs: 128 columns
 
-template <int NB>
+template <int NB, int CHAINS = 1>
 struct Smem {
     // h operand: fp16, UMMA K-major NO-swizzle ("interleaved") layout [k/8][video][k%8]:
     // core matrix = 8 videos x 16 B; LBO (next 8 k) = NB*16 B, SBO (next 8 videos) = 128 B.
@@ -54,12 +58,13 @@ struct Smem {
     static constexpr int H_LBO = NB * 16;
     static constexpr int H_BYTES = (HC / 8) * H_LBO;         // NB * 512
     static constexpr int SLICE_BYTES = (UNITS / 8) * H_LBO;  // NB * 64: this CTA's share of h
-    static constexpr int OFF_H = 0;                           // two buffers
-    static constexpr int OFF_STAGE16 = OFF_H + 2 * H_BYTES;   // double buffered
-    static constexpr int OFF_META = OFF_STAGE16 + 2 * SLICE_BYTES;  // len[NB], row[NB]
-    static constexpr int OFF_BAR = OFF_META + 2 * NB * 4;           // bar_h[2], bar_mma, tmem slot
-    static constexpr int TOTAL = 1024 + OFF_BAR + 4 * 8;
-    static constexpr int TMEM_COLS = (W_TMEM_COLS + NB) <= 256 ? 256 : 512;
+    static constexpr int OFF_H = 0;                           // per chain: two h buffers ...
+    static constexpr int OFF_STAGE16 = OFF_H + 2 * H_BYTES;   // ... and the double-buffered staged slice
+    static constexpr int CHAIN_BYTES = 2 * H_BYTES + 2 * SLICE_BYTES;
+    static constexpr int OFF_META = CHAINS * CHAIN_BYTES;     // len[NB], row[NB]
+    static constexpr int OFF_BAR = OFF_META + 2 * NB * 4;     // per chain bar_h[2], bar_mma; then the tmem slot
+    static constexpr int TOTAL = 1024 + OFF_BAR + (3 * CHAINS + 1) * 8;
+    static constexpr int TMEM_COLS = (W_TMEM_COLS + CHAINS * NB) <= 256 ? 256 : 512;
 };
 
 __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta_rank) {
@@ -174,16 +179,18 @@ __device__ __forceinline__ long long clk64() {
     return t;
 }
 
-template <int NB, int PARTS, bool TRACE>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PARTS * 128 + 32, PARTS == 2 ? 2 : 1)
+template <int NB, int PARTS, int CHAINS, bool TRACE>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PARTS * 128 + CHAINS * 32, PARTS == 2 ? 2 : 1)
 lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
                LstmBatch batch, int op_dtype, void* __restrict__ fused_out, int out_dtype, int round_tf32,
                float4* __restrict__ save_pre, float* __restrict__ save_c) {
-    using S = Smem<NB>;
+    static_assert(CHAINS == 1 || CHAINS == PARTS, "a chain is either the whole CTA or one part");
+    using S = Smem<NB, CHAINS>;
     constexpr int NV = NB / 4;             // video slots per part
     constexpr int SLOTS = NV * PARTS;      // real video slots of this cluster (batch.nb)
+    constexpr int CHAIN_SLOTS = SLOTS / CHAINS;    // real video slots of one chain
     constexpr int EPI_WARPS = 4 * PARTS;
-    constexpr int THREADS = EPI_WARPS * 32 + 32;   // + one MMA-issuing warp
+    constexpr int THREADS = EPI_WARPS * 32 + CHAINS * 32;   // + one MMA-issuing warp per chain
     cg::cluster_group cluster = cg::this_cluster();
     const int r = static_cast<int>(cluster.block_rank());
     const int cid = blockIdx.x / CL;
@@ -196,14 +203,16 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    uint8_t* h_sm = sm + S::OFF_H;
-    uint8_t* stage16 = sm + S::OFF_STAGE16;   // this CTA's h slice in destination layout, double buffered:
-                                              // the bulk copies of step s may still read it during step s+1
+    // which chain this warp works for: epilogue warps by part, MMA warps by index
+    const int chain = CHAINS == 1 ? 0 : (warp < EPI_WARPS ? (warp >> 2) : (warp - EPI_WARPS));
+    uint8_t* h_sm = sm + chain * S::CHAIN_BYTES + S::OFF_H;
+    uint8_t* stage16 = sm + chain * S::CHAIN_BYTES + S::OFF_STAGE16;   // this CTA's h slice in destination layout
     int* s_len = reinterpret_cast<int*>(sm + S::OFF_META);
     int* s_row = s_len + NB;
-    uint64_t* bar_h = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);  // [2]
+    uint64_t* bar_all = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);
+    uint64_t* bar_h = bar_all + 3 * chain;  // [2]
     uint64_t* bar_mma = bar_h + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_all + 3 * CHAINS);
     __shared__ volatile long long tr_ts[2];   // [0] MMA commit issued, [1] bulk copies issued (TRACE only)
     const bool tracing = TRACE && blockIdx.x == 0;
     long long tr_acc[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -213,12 +222,10 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         s_len[tid] = tid < SLOTS ? batch.slot_len[grp * SLOTS + tid] : 0;
         s_row[tid] = tid < SLOTS ? batch.slot_row_start[grp * SLOTS + tid] : 0;
     }
-    for (int i = tid; i < (2 * S::H_BYTES + 2 * S::SLICE_BYTES) / 16; i += THREADS)
-        reinterpret_cast<uint4*>(h_sm)[i] = make_uint4(0, 0, 0, 0);   // h buffers + stage (contiguous)
+    for (int i = tid; i < CHAINS * S::CHAIN_BYTES / 16; i += THREADS)
+        reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);   // h buffers + stages of every chain
     if (tid == 0) {
-        mbar_init(bar_h + 0, 1);
-        mbar_init(bar_h + 1, 1);
-        mbar_init(bar_mma, 1);
+        for (int i = 0; i < 3 * CHAINS; ++i) mbar_init(bar_all + i, 1);
         fence_mbar_init();
     }
     if (warp == EPI_WARPS) {
@@ -231,7 +238,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_w = tmem_base;                 // columns [0, 128): W_hh slice, fp16 pairs
-    const uint32_t tmem_d = tmem_base + W_TMEM_COLS;   // columns [128, 128 + NB): gate accumulator
+    const uint32_t tmem_d = tmem_base + W_TMEM_COLS + chain * NB;   // this chain's gate accumulator (NB columns)
 
     if (warp < EPI_WARPS) {
         // W_hh slice -> tensor memory, resident for the whole kernel.  A-operand layout of
@@ -257,23 +264,25 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     __syncthreads();
     cluster.sync();       // every CTA's barriers and buffers exist before any remote access
     tc_fence_after();
-    const int maxlen = batch.group_maxlen[grp];
+    // slots are sorted by length (longest first), so a chain runs as long as its first slot
+    const int maxlen = CHAINS == 1 ? batch.group_maxlen[grp] : s_len[chain * CHAIN_SLOTS];
 
-    if (warp == EPI_WARPS) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (warp >= EPI_WARPS) {
+        // ------------------------------------------------------------------ MMA issuer (one thread per chain)
         if (elect_one()) {
             const uint32_t idesc = umma_idesc(op_dtype == DT_BF16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, COLS, NB);
             for (int s = 0; s < maxlen; ++s) {
                 const int b = s & 1;
                 // arm the barrier that will collect h_{s+1}: 8 peers x SLICE_BYTES, one local arrival
-                if (s + 1 < maxlen) mbar_expect_tx(bar_h + (b ^ 1), CL * SLOTS * 64);   // 8 peers x 64 B per real video slot
+                if (s + 1 < maxlen) mbar_expect_tx(bar_h + (b ^ 1), CL * CHAIN_SLOTS * 64);   // 8 peers x 64 B per real video slot
                 if (s > 0) {
                     mbar_wait_cluster(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
                     fence_proxy_async();   // peers' st.async (generic proxy) -> visible to the tensor core's reads
                 }
                 tc_fence_after();
                 long long tA = 0;
-                if (tracing) {
+                const bool tr = tracing && chain == 0;
+                if (tr) {
                     tA = clk64();
                     if (s > 0) tr_acc[6] += tA - tr_ts[1];   // copies issued -> all 8 slices of h landed
                 }
@@ -284,13 +293,13 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                     umma_f16_ts(tmem_d, tmem_w + k * 8, bd, idesc, k != 0);
                 }
                 tc_commit(bar_mma);
-                if (tracing) {
+                if (tr) {
                     const long long tB = clk64();
                     tr_ts[0] = tB;
                     tr_acc[0] += tB - tA;                     // h landed -> 16 MMAs + commit issued
                 }
             }
-            if (tracing) {
+            if (tracing && chain == 0) {
                 g_lstm_trace[0] = tr_acc[0];
                 g_lstm_trace[6] = tr_acc[6];
                 g_lstm_trace[7] = maxlen;
@@ -308,11 +317,12 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         const int p = q * 32 + lane;         // gate column inside the slice: 4*jj + gate
         const int g = p & 3;                 // gate held in TMEM == video-in-block owned after the transpose
         const int jj = p >> 2;
-        const int v0 = part * NV;
+        const int v0 = part * NV;                        // first video slot of this part (index into s_len / s_row)
+        const int lv0 = CHAINS == 1 ? v0 : 0;            // the same, relative to this chain's buffers / accumulator
         const float4* xg4 = reinterpret_cast<const float4*>(((ld >> 1) ? xg_a : xg_v) + dir * (4 * HC) + r * COLS + 4 * jj);
         constexpr int XG_LD4 = XG_LD / 4;
         const int out_col = ld * HC + r * UNITS;
-        const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + v0;
+        const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + lv0;
         const bool par1 = (lane & 1) != 0, par2 = (lane & 2) != 0;
         // this thread's slot in the staged slice: [jj/8][video][jj%8] 16-bit values
         uint16_t* stage_mine = reinterpret_cast<uint16_t*>(stage16 + (jj >> 3) * S::H_LBO) + (jj & 7);
@@ -327,8 +337,8 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         // v0 .. v0+NV-1.  After a __syncwarp lane l sends chunk (video v0 + 4k + (l >> 3)) to peer CTA (l & 7)
         // with one st.async: 4 videos x 8 peers = 32 lanes.  No CTA-wide barrier, no bulk-copy engine.
         const uint32_t peer = lane & 7, cvid = lane >> 3;
-        const uint32_t stage_rd = smem_u32(stage16) + q * S::H_LBO + (v0 + cvid) * 16;     // + k*64, + slot
-        const uint32_t remote_h = mapa(smem_u32(h_sm) + (r * 4 + q) * S::H_LBO + (v0 + cvid) * 16, peer);
+        const uint32_t stage_rd = smem_u32(stage16) + q * S::H_LBO + (lv0 + cvid) * 16;     // + k*64, + slot
+        const uint32_t remote_h = mapa(smem_u32(h_sm) + (r * 4 + q) * S::H_LBO + (lv0 + cvid) * 16, peer);
         const uint32_t remote_bar = mapa(smem_u32(bar_h), peer);
 
         float c_state[NP];
@@ -406,7 +416,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                     save_c[o] = cn;
                 }
                 if (on)   // |h| < 1: no saturation needed
-                    stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + vid_r[k] * 8] =
+                    stage_mine[(s & 1) * (S::SLICE_BYTES / 2) + (vid_r[k] - v0 + lv0) * 8] =
                         op_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(h)) : __half_as_ushort(__float2half_rn(h));
             }
             long long tE = 0, tF = 0;
@@ -473,17 +483,17 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
-template <int NB, int PARTS>
+template <int NB, int PARTS, int CHAINS>
 avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, int op_dtype,
                      void* fused, int out_dtype, int round_tf32, float4* save_pre, float* save_c, cudaStream_t stream) {
     static const bool trace = getenv("AVS_LSTM_TRACE") != nullptr;
-    auto kern = trace ? lstm_tc_kernel<NB, PARTS, NB == 16> : lstm_tc_kernel<NB, PARTS, false>;
+    auto kern = trace ? lstm_tc_kernel<NB, PARTS, CHAINS, NB == 16> : lstm_tc_kernel<NB, PARTS, CHAINS, false>;
     static bool configured = false;
     if (!configured) {
-        AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NB>::TOTAL));
+        AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NB, CHAINS>::TOTAL));
         configured = true;
     }
-    kern<<<batch.n_groups * 4 * CL, PARTS * 128 + 32, Smem<NB>::TOTAL, stream>>>(
+    kern<<<batch.n_groups * 4 * CL, PARTS * 128 + CHAINS * 32, Smem<NB, CHAINS>::TOTAL, stream>>>(
         xg_v, xg_a, whh, batch, op_dtype, fused, out_dtype, round_tf32, save_pre, save_c);
     AVS_LAUNCH_CHECK();
     return AVS_OK;
@@ -504,13 +514,13 @@ avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float*
     if (batch.n_groups == 0) return AVS_OK;
     AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
     switch (batch.nb) {   // video slots per cluster
-        case 8: return launch_tc<16, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+        case 8: return launch_tc<16, 2, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
                                                 static_cast<float4*>(save_pre), save_c, stream);
-        case 16: return launch_tc<16, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+        case 16: return launch_tc<16, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
                                                 static_cast<float4*>(save_pre), save_c, stream);
-        case 32: return launch_tc<32, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+        case 32: return launch_tc<32, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
                                                 static_cast<float4*>(save_pre), save_c, stream);
-        case 64: return launch_tc<64, 4>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+        case 64: return launch_tc<64, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
                                                 static_cast<float4*>(save_pre), save_c, stream);
         default: set_error("lstm_tc: unsupported videos-per-cluster %d", batch.nb); return AVS_ERR_INVALID;
     }
