@@ -997,6 +997,8 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
     sb.prop_num = prop_num;
     sb.prop_den = prop_den;
     sb.max_cap = max_cap;
+    sb.max_S = 0;
+    for (int v = 0; v < n; ++v) sb.max_S = std::max(sb.max_S, cps_start[v + 1] - cps_start[v]);
     {
         StageTimer tm(ST_POOL, st);
         AVS_TRY(shot_pool(sc, pos, sb, seg_sum, st));

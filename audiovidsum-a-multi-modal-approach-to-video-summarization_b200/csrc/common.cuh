@@ -149,6 +149,7 @@ struct SummaryBatch {   // device arrays, [n] unless noted
     int n;
     int prop_num, prop_den;
     int max_cap;                 // max capacity over the batch
+    int max_S;                   // max number of shots of one video
 };
 avs_status shot_pool(const float* scores, const int32_t* positions, const SummaryBatch& b, unsigned long long* seg_sum,
                      cudaStream_t stream);

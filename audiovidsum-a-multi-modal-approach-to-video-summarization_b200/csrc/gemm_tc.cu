@@ -32,7 +32,8 @@ template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * 128;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int OUT_WARP_BYTES = 32 * BN * 4;       // one epilogue warp's 32 rows, fp32 worst case
+    // one epilogue warp's 32 rows: fp32 worst case; the 256-wide tile only serves 16-bit outputs
+    static constexpr int OUT_WARP_BYTES = 32 * BN * (BN == 256 ? 2 : 4);
     static constexpr int OUT_BYTES = 4 * OUT_WARP_BYTES;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 8;
     static constexpr int TOTAL = 1024 /*alignment slack*/ + TILE_BYTES + OUT_BYTES + BAR_BYTES;
@@ -366,7 +367,12 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     const int k_blocks = (K + bk_elems - 1) / bk_elems;
     const bool tf32 = in_dtype == DT_F32;
     const uint32_t fmt = tf32 ? UMMA_FMT_TF32 : (in_dtype == DT_F16 ? UMMA_FMT_F16 : UMMA_FMT_BF16);
-    const int BN = (N % 128 == 0) ? 128 : 64;
+    // 128 x 256 tiles move 25 % fewer operand bytes per FLOP through L2 (the bound of these GEMMs); used for
+    // 16-bit outputs (staging fits) when the tile count still balances over the SMs
+    const int64_t m_tiles = (M + BM - 1) / BM;
+    const bool wide_ok = N % 256 == 0 && epi.scores == nullptr && epi.out_dtype != DT_F32 && !(in_dtype == DT_F32) &&
+                         m_tiles * (N / 256) >= 4 * 148;
+    const int BN = wide_ok ? 256 : ((N % 128 == 0) ? 128 : 64);
 
     CUtensorMap tmA, tmB, tmC;
     AVS_TRY(make_tmap(&tmA, A, in_dtype, M, K, lda, BM));
@@ -399,7 +405,9 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
                                                        bk_elems, idesc, tiles_n, num_tiles, epi);            \
     } while (0)
 
-    if (BN == 128) {
+    if (BN == 256) {
+        AVS_GEMM_LAUNCH(256, 3, false);
+    } else if (BN == 128) {
         if (tf32) AVS_GEMM_LAUNCH(128, 4, true);
         else AVS_GEMM_LAUNCH(128, 4, false);
     } else {

@@ -59,10 +59,12 @@ __global__ void __launch_bounds__(256) shot_pool_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------- K8
-// One block per video.  DP rows live in shared memory when 2*(cap+1) int64 fit, else in a
-// global (L2-resident) workspace; the per-item "kept" bits go to global memory, one ballot word
-// per warp, and a single thread walks them backwards.
-constexpr int KNAP_THREADS = 512;
+// One block per video.  Everything the item loop touches lives in shared memory when it fits: the two DP rows
+// (2 * (cap + 1) int64), the items (weight, pooled value -- computed once, in parallel, instead of a global load
+// and a 64-bit division per item on the critical path) and the per-item "kept" bits (one ballot word per warp).
+// Oversized videos fall back to a global (L2-resident) workspace for the DP rows / keep bits.  A single thread
+// walks the keep bits backwards.
+constexpr int KNAP_THREADS = 1024;
 
 __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
                                                                 const unsigned long long* __restrict__ seg_sum,
@@ -70,7 +72,8 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
                                                                 uint8_t* __restrict__ picks,
                                                                 uint8_t* __restrict__ summary,
                                                                 uint32_t* __restrict__ keep_bits,
-                                                                long long* __restrict__ dp_ws, int smem_rows_cap) {
+                                                                long long* __restrict__ dp_ws, int smem_rows_cap,
+                                                                int smem_items_cap, int smem_keep_words) {
     extern __shared__ long long dp_smem[];
     const int v = blockIdx.x;
     const int tid = threadIdx.x;
@@ -80,7 +83,14 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
     const long long cap_ll = (static_cast<long long>(nf) * b.prop_num) / b.prop_den;
     const int cap = static_cast<int>(cap_ll < 0 ? 0 : cap_ll);
     const int words = (cap + 32) >> 5;  // ceil((cap + 1) / 32)
-    uint32_t* keep = keep_bits + b.keep_start[v];
+
+    long long* item_val = dp_smem + 2 * smem_rows_cap;                            // [smem_items_cap]
+    int* item_wt = reinterpret_cast<int*>(item_val + smem_items_cap);             // [smem_items_cap]
+    int* item_beg = item_wt + smem_items_cap;                                     // [smem_items_cap] first frame; < 0: not picked
+    uint32_t* keep_sm = reinterpret_cast<uint32_t*>(item_beg + smem_items_cap);
+    const bool items_in_smem = S <= smem_items_cap;
+    const bool keep_in_smem = static_cast<long long>(S) * words <= smem_keep_words;
+    uint32_t* keep = keep_in_smem ? keep_sm : keep_bits + b.keep_start[v];
 
     long long* cur;
     long long* nxt;
@@ -92,14 +102,33 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
         nxt = cur + (cap + 1);
     }
     for (int w = tid; w <= cap; w += KNAP_THREADS) cur[w] = 0;
-    __syncthreads();
-
-    for (int s = 0; s < S; ++s) {
+    // pooled shot values: mean rounded half up in fixed point (oracle: shot_pool)
+    for (int s = tid; s < S; s += KNAP_THREADS) {
         const int2 seg = cps[s];
         const int wt = seg.y - seg.x + 1;
         const unsigned long long sum = seg_sum[s0 + s];
         const long long val = wt > 0 ? static_cast<long long>((2ull * sum + wt) / (2ull * wt)) : 0ll;
-        if (tid == 0 && seg_mean_out != nullptr) seg_mean_out[s0 + s] = val;
+        if (seg_mean_out != nullptr) seg_mean_out[s0 + s] = val;
+        if (items_in_smem) {
+            item_val[s] = val;
+            item_wt[s] = wt;
+            item_beg[s] = seg.x;
+        }
+    }
+    __syncthreads();
+
+    for (int s = 0; s < S; ++s) {
+        int wt;
+        long long val;
+        if (items_in_smem) {
+            wt = item_wt[s];
+            val = item_val[s];
+        } else {
+            const int2 seg = cps[s];
+            wt = seg.y - seg.x + 1;
+            const unsigned long long sum = seg_sum[s0 + s];
+            val = wt > 0 ? static_cast<long long>((2ull * sum + wt) / (2ull * wt)) : 0ll;
+        }
         for (int wbase = 0; wbase <= cap; wbase += KNAP_THREADS) {  // warp-uniform trip count
             const int w = wbase + tid;
             bool better = false;
@@ -129,17 +158,35 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
             const uint32_t word = keep[static_cast<size_t>(s) * words + (w >> 5)];
             const int take = (word >> (w & 31)) & 1;
             picks[s0 + s] = static_cast<uint8_t>(take);
-            if (take) w -= (cps[s].y - cps[s].x + 1);
+            if (take) w -= items_in_smem ? item_wt[s] : (cps[s].y - cps[s].x + 1);
+            if (items_in_smem && !take) item_wt[s] = -1;      // the bitmap pass below reads the selection from smem
         }
     }
     if (summary != nullptr) {
         __syncthreads();
         uint8_t* out = summary + b.summary_start[v];
-        for (int f = tid; f < nf; f += KNAP_THREADS) out[f] = 0;
+        // zero fill with 16-byte stores where the alignment allows (summary_start is arbitrary), bytes at the edges
+        {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(out);
+            const int head = min(nf, static_cast<int>((16 - (addr & 15)) & 15));
+            const int body = (nf - head) / 16;
+            for (int f = tid; f < head; f += KNAP_THREADS) out[f] = 0;
+            uint4* o4 = reinterpret_cast<uint4*>(out + head);
+            for (int i = tid; i < body; i += KNAP_THREADS) o4[i] = make_uint4(0, 0, 0, 0);
+            for (int f = head + body * 16 + tid; f < nf; f += KNAP_THREADS) out[f] = 0;
+        }
         __syncthreads();
         for (int s = 0; s < S; ++s) {
-            if (!picks[s0 + s]) continue;
-            const int a = max(cps[s].x, 0), z = min(cps[s].y + 1, nf);
+            int a, z;
+            if (items_in_smem) {
+                if (item_wt[s] < 0) continue;
+                a = max(item_beg[s], 0);
+                z = min(item_beg[s] + item_wt[s], nf);
+            } else {
+                if (!picks[s0 + s]) continue;
+                a = max(cps[s].x, 0);
+                z = min(cps[s].y + 1, nf);
+            }
             for (int f = a + tid; f < z; f += KNAP_THREADS) out[f] = 1;
         }
     }
@@ -194,11 +241,21 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
                            uint8_t* picks, uint8_t* summary, uint32_t* keep_bits, long long* dp_ws,
                            cudaStream_t stream) {
     if (b.n == 0) return AVS_OK;
-    // two dp rows in shared memory when they fit (<= 96 KiB keeps 2 blocks per SM)
+    // shared-memory budget (<= 200 KiB): DP rows first, then the items, then the keep bits -- each only if it fits
+    const size_t limit = 200 * 1024;
     int rows_cap = b.max_cap + 1;
     size_t smem = 2ull * rows_cap * sizeof(long long);
-    const size_t limit = 200 * 1024;
     if (smem > limit) { rows_cap = 0; smem = 0; }
+    int items_cap = b.max_S;
+    const size_t items_bytes = static_cast<size_t>(items_cap) * 16 + 8;
+    if (smem + items_bytes > limit) items_cap = 0;
+    else smem += items_bytes;
+    const size_t words_max = static_cast<size_t>(b.max_S) * ((static_cast<size_t>(b.max_cap) + 32) >> 5);
+    int keep_words = 0;
+    if (smem + words_max * 4 <= limit && words_max < (1u << 30)) {
+        keep_words = static_cast<int>(words_max);
+        smem += words_max * 4;
+    }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         AVS_CUDA(cudaFuncSetAttribute(knapsack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -206,7 +263,7 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
         configured = limit;
     }
     knapsack_kernel<<<b.n, KNAP_THREADS, smem, stream>>>(b, seg_sum, seg_mean, picks, summary, keep_bits, dp_ws,
-                                                        rows_cap);
+                                                        rows_cap, items_cap, keep_words);
     AVS_LAUNCH_CHECK();
     return AVS_OK;
 }
