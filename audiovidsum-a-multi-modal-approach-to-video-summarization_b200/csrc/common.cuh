@@ -74,6 +74,7 @@ struct GemmEpilogue {
     int out_dtype = DT_F32;
     int relu = 0;
     int round_tf32 = 0;           // fp32 outputs rounded (RN) to tf32 for a following tf32 GEMM
+    float acc_scale = 1.0f;       // epilogue computes acc * acc_scale + bias (see AVS_PREC_TF32 in api.cu)
     // fused frame-score head (N must be 64): scores[m] = sigmoid(relu(acc + bias) . w2 + b2)
     const float* score_w2 = nullptr;
     const float* score_b2 = nullptr;   // device pointer to 1 float

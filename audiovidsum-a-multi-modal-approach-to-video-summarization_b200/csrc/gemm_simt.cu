@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
         float part = 0.f;
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            float x = acc[i][j];
+            float x = acc[i][j] * epi.acc_scale;
             if (n < N) {
                 if (epi.bias) x += epi.bias[n];
                 if (epi.relu) x = fmaxf(x, 0.f);

@@ -208,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(r[j]) + bv[j];
+                        float x = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]);
                         if (epi.relu) x = fmaxf(x, 0.f);
                         score_acc = fmaf(x, wv[j], score_acc);
                     }
@@ -250,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            float x = __uint_as_float(r[j]) + bv[j];
+                            float x = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]);
                             if (epi.relu) x = fmaxf(x, 0.f);
                             if (epi.round_tf32) x = to_tf32_rn(x);
                             r[j] = __float_as_uint(x);
@@ -270,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             uint32_t pk[16];
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
-                                float x0 = __uint_as_float(r[j]) + bv[j], x1 = __uint_as_float(r[j + 1]) + bv[j + 1];
+                                float x0 = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]), x1 = fmaf(__uint_as_float(r[j + 1]), epi.acc_scale, bv[j + 1]);
                                 if (epi.relu) {
                                     x0 = fmaxf(x0, 0.f);
                                     x1 = fmaxf(x1, 0.f);
