@@ -11,13 +11,16 @@
 //       128 lanes x 128 columns), so a step never re-streams the 64 KB slice through shared memory
 //     - h_prev: fp16, shared memory (no-swizzle K-major), rewritten every step by all 8 CTAs
 //     - accumulator: tensor memory, NB columns
-//   16 epilogue warps: tcgen05.ld -> 4x4 quad shuffle transpose (every thread then owns all four gates of
-//     one (hidden unit, video)) -> + x W_ih^T (precomputed by the GEMM, fp32, one float4) -> cell update on
-//     the SFU with shared denominators (5 ex2 + 2 rcp per cell) in fp32 registers -> h staged as fp16 in
-//     the destination layout; 8 threads then push the CTA's contiguous NB*64-byte slice into every peer's
-//     next-step buffer with cp.async.bulk (DSMEM, async proxy) which complete_tx's the peer's
-//     mbarrier, and 4*NB threads write the slice to the fused output with 16-byte stores.
-//     No cluster-wide barrier, no generic-proxy remote stores, no fences at cluster scope.
+//   epilogue warps (4 per "part" of NB/4 videos): tcgen05.ld -> 4x4 quad shuffle transpose (every thread then
+//     owns all four gates of one (hidden unit, video)) -> + x W_ih^T (precomputed by the GEMM, fp32, one
+//     float4) -> cell update on the SFU with shared denominators (5 ex2 + 2 rcp per cell) in fp32 registers
+//     -> h staged as fp16 in the destination layout, then pushed into every peer CTA's next-step buffer per
+//     warp, right after a __syncwarp: lane l sends the 16-byte chunk of video l/8 to CTA l%8 with st.async,
+//     whose mbarrier complete_tx (release at cluster scope) counts the bytes on the receiver's barrier;
+//     four lanes also write the chunks to the fused output (16-byte stores).
+//     No CTA-wide or cluster-wide barrier, no bulk-copy engine, no fences at cluster scope.
+//   Measured (tools/lstm_scaling.py, B200): 0.71 us per step for an isolated chain, 0.76 us with two chains
+//   per CTA, 0.86 us when two CTAs share every SM (config 2: 50 videos -> 28 clusters on 148 SMs).
 //
 // fp16 operands have the same 11-bit significand as tf32 and |h| < 1, so the recurrent matmul
 // carries tf32-level rounding (measured contribution to the final scores: < 3e-5 relative);
@@ -71,16 +74,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta_rank)
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
     return r;
-}
-// Bulk copy own shared memory -> a peer CTA's shared memory (async proxy on both ends); the
-// destination CTA's mbarrier receives complete_tx(bytes).
-__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
-                                                  uint32_t mbar_cluster_addr) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            dst_cluster_addr),
-        "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
-        : "memory");
 }
 // 16-byte store into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16) (release at
 // cluster scope) when the data has landed.
@@ -149,10 +142,8 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[1
         : "memory");
 }
 
-// Branch-free gate activation on the SFU: act = a * sigmoid(k * x) + b with per-lane constants
-// (i, f, o lanes: k=1, a=1, b=0 -> sigmoid;  g lane: k=2, a=2, b=-1 -> tanh(x) = 2*sigmoid(2x) - 1).
-// ex2.approx / rcp.approx are ~1-2 ulp; saturate correctly at +-inf.  Absolute error ~1e-7, far
-// inside the fp16/tf32 operand rounding of this mode.
+// SFU primitives of the cell update: ex2.approx / rcp.approx are ~1-2 ulp (absolute error ~1e-7 on the gate
+// activations, far inside the fp16 operand rounding of this mode).
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -163,13 +154,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float gate_act(float x, float neg_k_log2e, float a, float b) {
-    return fmaf(a, rcp_approx(1.0f + ex2_approx(x * neg_k_log2e)), b);
-}
-__device__ __forceinline__ float tanh_sfu(float x) {
-    return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(x * -2.885390082f)), -1.0f);
-}
-
 // Optional phase trace (AVS_LSTM_TRACE=1, debugging aid): cluster 0 / CTA 0 accumulates clock64 deltas of the
 // per-step dependency chain; read back with avs_debug_lstm_trace().
 __device__ unsigned long long g_lstm_trace[8];
