@@ -32,7 +32,8 @@ template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * 128;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    // one epilogue warp's 32 rows: fp32 worst case; the 256-wide tile only serves 16-bit outputs
+    // one epilogue warp's staging: its 32 rows of the tile in fp32; the 256-wide tile has room for half of
+    // that (4 boxes of 32 rows x 128 B) and cycles through it twice for fp32 outputs
     static constexpr int OUT_WARP_BYTES = 32 * BN * (BN == 256 ? 2 : 4);
     static constexpr int OUT_BYTES = 4 * OUT_WARP_BYTES;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 8;
@@ -222,6 +223,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool wide = epi.out_dtype != DT_F32;          // 16-bit output: 64 columns per 128-byte box
             const int box_cols = wide ? 64 : 32;
             const int n_boxes = BN / box_cols;
+            constexpr int SLOTS = L::OUT_WARP_BYTES / 4096;     // staging boxes per warp (a 256-wide fp32 tile cycles twice)
+            uint32_t issued = 0;                                // boxes handed to the TMA engine so far
             const uint32_t out_base = smem_u32(tiles + L::TILE_BYTES) + q * L::OUT_WARP_BYTES;
             const uint32_t my_row = out_base + lane * 128;
             const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -236,12 +239,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                 for (int bx = 0; bx < n_boxes; ++bx) {
                     const int nb = n0 + bx * box_cols;
-                    // the TMA store that read this box's staging one tile ago must be done reading
-                    if (lt > 0) {
-                        if (lane == 0) bulk_wait_group_read(n_boxes - 1);
+                    // the TMA store that read this staging slot SLOTS boxes ago must be done reading
+                    const uint32_t slot = issued % SLOTS;
+                    if (issued >= SLOTS) {
+                        if (lane == 0) bulk_wait_group_read(SLOTS - 1);
                         __syncwarp();
                     }
-                    const uint32_t dst = my_row + bx * 4096;
+                    ++issued;
+                    const uint32_t dst = my_row + slot * 4096;
                     if (!wide) {
                         uint32_t r[32];
                         float bv[32];
@@ -286,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA engine
                     __syncwarp();
                     if (lane == 0) {
-                        if (nb < N) tma_store_2d(&tmC, out_base + bx * 4096, nb, m0 + q * 32);
+                        if (nb < N) tma_store_2d(&tmC, out_base + slot * 4096, nb, m0 + q * 32);
                         bulk_commit_group();   // (possibly empty) keeps the group count per tile fixed
                     }
                 }
@@ -368,10 +373,9 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     const bool tf32 = in_dtype == DT_F32;
     const uint32_t fmt = tf32 ? UMMA_FMT_TF32 : (in_dtype == DT_F16 ? UMMA_FMT_F16 : UMMA_FMT_BF16);
     // 128 x 256 tiles move 25 % fewer operand bytes per FLOP through L2 (the bound of these GEMMs); used for
-    // 16-bit outputs (staging fits) when the tile count still balances over the SMs
+    // 16-bit operands when the tile count still balances over the SMs
     const int64_t m_tiles = (M + BM - 1) / BM;
-    const bool wide_ok = N % 256 == 0 && epi.scores == nullptr && epi.out_dtype != DT_F32 && !(in_dtype == DT_F32) &&
-                         m_tiles * (N / 256) >= 4 * 148;
+    const bool wide_ok = N % 256 == 0 && epi.scores == nullptr && !(in_dtype == DT_F32) && m_tiles * (N / 256) >= 4 * 148;
     const int BN = wide_ok ? 256 : ((N % 128 == 0) ? 128 : 64);
 
     CUtensorMap tmA, tmB, tmC;
