@@ -171,12 +171,12 @@ struct avs_model {
     Arena ws;       // activations
     Arena staging;  // raw weights during packing
     Arena host_in;  // device copies of host-space inputs when a call is pipelined by video group
-    Arena ws_grp[3];                 // activations of groups 1..3 (group 0 uses ws): the groups run concurrently
-    cudaStream_t grp_stream[3] = {}; // compute streams of groups 1..3 (group 0 runs on the caller's stream)
-    cudaEvent_t ev_grp[3] = {};
+    Arena ws_grp[5];                 // activations of groups 1..5 (group 0 uses ws): the groups run concurrently
+    cudaStream_t grp_stream[5] = {}; // compute streams of groups 1..5 (group 0 runs on the caller's stream)
+    cudaEvent_t ev_grp[5] = {};
     // host-space calls: H2D copies run on their own stream, chunked, so that the row-parallel
     // front of the pipeline (tf32 rounding, fc and LSTM-input GEMMs) overlaps the PCIe transfer
-    static constexpr int MAX_CHUNKS = 4;
+    static constexpr int MAX_CHUNKS = 6;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
@@ -498,7 +498,7 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming);
         for (int i = 0; i < avs_model::MAX_CHUNKS && ce == cudaSuccess; ++i)
             ce = cudaEventCreateWithFlags(&m->ev_chunk[i], cudaEventDisableTiming);
-        for (int i = 0; i < 3 && ce == cudaSuccess; ++i) {
+        for (int i = 0; i < 5 && ce == cudaSuccess; ++i) {
             ce = cudaStreamCreateWithFlags(&m->grp_stream[i], cudaStreamNonBlocking);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_grp[i], cudaEventDisableTiming);
         }
@@ -532,7 +532,7 @@ void avs_model_destroy(avs_model* m) {
     m->ws.release();
     m->staging.release();
     m->host_in.release();
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 5; ++i) {
         m->ws_grp[i].release();
         if (m->grp_stream[i]) cudaStreamDestroy(m->grp_stream[i]);
         if (m->ev_grp[i]) cudaEventDestroy(m->ev_grp[i]);
@@ -571,7 +571,9 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
                       static_cast<int64_t>(row_start[b]) + lengths[b] <= total_rows &&
                       (b == 0 || row_start[b] >= row_start[b - 1] + lengths[b - 1]);
         }
-        if (ordered) n_groups = (total_rows >= 16384 && n_videos >= 12) ? 4 : ((total_rows >= 8192 && n_videos >= 6) ? 3 : 2);
+        if (ordered)
+            n_groups = (total_rows >= 16384 && n_videos >= 24) ? 6
+                       : (total_rows >= 16384 && n_videos >= 12) ? 4 : ((total_rows >= 8192 && n_videos >= 6) ? 3 : 2);
     }
     if (n_groups == 1) {
         if (scores_dev_out == nullptr)
@@ -611,7 +613,7 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
     // group boundaries at video boundaries.  Shares shrink towards the end: what remains after the last byte has
     // crossed PCIe is the last group's compute, so it should be the smallest (and, for a longest-first batch, the
     // one with the shortest recurrence).
-    static const int kShare[5][4] = {{0, 0, 0, 0}, {100, 0, 0, 0}, {60, 100, 0, 0}, {45, 80, 100, 0}, {40, 70, 90, 100}};
+    static const int kShare[7][6] = {{0}, {100}, {60, 100}, {45, 80, 100}, {40, 70, 90, 100}, {0}, {32, 58, 77, 89, 96, 100}};
     int first[avs_model::MAX_CHUNKS + 1];
     first[0] = 0;
     for (int gi = 1; gi < n_groups; ++gi) {

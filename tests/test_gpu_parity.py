@@ -611,3 +611,36 @@ def test_fused_score_and_summarize_equals_two_calls(native):
             assert torch.equal(got[0].cpu(), want_s.cpu()), (axis, dev)        # same kernels, same data
             for g, w in zip(got[1:4], want[:3]):
                 assert torch.equal(g.cpu(), w.cpu()), (axis, dev)
+
+
+def test_sharded_result_equals_single_gpu_result(native):
+    """SURVEY section 4 'multi-GPU': the N-shard result equals the 1-GPU result EXACTLY (same kernels, sharding
+    only).  The shards of sharding.shard_videos are run one after the other on this GPU and re-assembled."""
+    from avsum_b200 import sharding
+    vids = synth.config2()[:18]
+    lens_all = [v.T for v in vids]
+
+    def run(idx):
+        sub = [vids[i] for i in idx]
+        lens = [v.T for v in sub]
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+        pos = torch.from_numpy(np.concatenate([v.positions for v in sub]).astype(np.int32)).cuda()
+        sc, picks, segm, summ, cps_start, sum_start = native.score_and_summarize_rows(
+            torch.cat([v.visual for v in sub]).cuda(), torch.cat([v.audio for v in sub]).cuda(), pos, starts, lens,
+            [v.n_frames for v in sub], [v.cps for v in sub], 0.15, "temporal")
+        torch.cuda.synchronize()
+        out = {}
+        for k, i in enumerate(idx):
+            out[i] = (sc[starts[k]:starts[k] + lens[k]].cpu(), picks[cps_start[k]:cps_start[k + 1]].cpu(),
+                      summ[sum_start[k]:sum_start[k + 1]].cpu())
+        return out
+
+    whole = run(list(range(len(vids))))
+    for world in (2, 4):
+        merged = {}
+        for shard in sharding.shard_videos(lens_all, world):
+            merged.update(run(shard))
+        assert sorted(merged) == list(range(len(vids)))
+        for i in range(len(vids)):
+            for a, b in zip(merged[i], whole[i]):
+                assert torch.equal(a, b), (world, i)
