@@ -26,6 +26,7 @@
 // carries tf32-level rounding (measured contribution to the final scores: < 3e-5 relative);
 // cell state, gate math and accumulation stay fp32.  Latency bound: ~T dependent steps.
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -167,7 +168,7 @@ template <int NB, int PARTS, int CHAINS, bool TRACE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PARTS * 128 + CHAINS * 32, PARTS == 2 ? 2 : 1)
 lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
                LstmBatch batch, int op_dtype, void* __restrict__ fused_out, int out_dtype, int round_tf32,
-               float4* __restrict__ save_pre, float* __restrict__ save_c) {
+               float4* __restrict__ save_pre, float* __restrict__ save_c, int grp_off) {
     static_assert(CHAINS == 1 || CHAINS == PARTS, "a chain is either the whole CTA or one part");
     using S = Smem<NB, CHAINS>;
     constexpr int NV = NB / 4;             // video slots per part
@@ -178,7 +179,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     cg::cluster_group cluster = cg::this_cluster();
     const int r = static_cast<int>(cluster.block_rank());
     const int cid = blockIdx.x / CL;
-    const int grp = cid >> 2;
+    const int grp = (cid >> 2) + grp_off;   // grp_off: this launch covers groups [grp_off, grp_off + gridDim.x / 32)
     const int ld = cid & 3;
     const int dir = ld & 1;
     const int tid = threadIdx.x;
@@ -467,19 +468,70 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
+// Streams / events for the split launch below (one set per process; the library serialises calls per handle).
+struct SplitCtx {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+SplitCtx& split_ctx() {
+    static SplitCtx c;
+    if (!c.ok && c.aux == nullptr) {
+        if (cudaStreamCreateWithFlags(&c.aux, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess)
+            c.ok = true;
+    }
+    return c;
+}
+
 template <int NB, int PARTS, int CHAINS>
 avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, int op_dtype,
                      void* fused, int out_dtype, int round_tf32, float4* save_pre, float* save_c, cudaStream_t stream) {
     static const bool trace = getenv("AVS_LSTM_TRACE") != nullptr;
+    static const bool no_split = getenv("AVS_LSTM_NO_SPLIT") != nullptr;
     auto kern = trace ? lstm_tc_kernel<NB, PARTS, CHAINS, NB == 16> : lstm_tc_kernel<NB, PARTS, CHAINS, false>;
+    constexpr int SMEM = Smem<NB, CHAINS>::TOTAL;
+    constexpr int SMEM_EXCLUSIVE = 200 * 1024;   // more than half an SM: no second CTA of either launch fits beside it
     static bool configured = false;
     if (!configured) {
-        AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NB, CHAINS>::TOTAL));
+        AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PARTS == 2 ? SMEM_EXCLUSIVE : SMEM));
         configured = true;
     }
-    kern<<<batch.n_groups * 4 * CL, PARTS * 128 + CHAINS * 32, Smem<NB, CHAINS>::TOTAL, stream>>>(
-        xg_v, xg_a, whh, batch, op_dtype, fused, out_dtype, round_tf32, save_pre, save_c);
+    const int threads = PARTS * 128 + CHAINS * 32;
+    // The kernel lasts as long as the LONGEST group's chain of dependent steps, and a step is ~13 % slower on
+    // an SM that two CTAs share (tools/lstm_scaling.py: 0.76 vs 0.86 us).  When the batch needs shared SMs
+    // anyway, the longest groups (groups are sorted by length) are launched on their own, with a shared-memory
+    // request that keeps their CTAs alone on their SMs; the other groups, which have fewer steps to run, share
+    // the remaining SMs two CTAs each.  Small batches (<= 16 clusters) run entirely on exclusive SMs.
+    // A = number of leading (longest) groups that get exclusive SMs.  Clusters are placed inside one GPC (16-20
+    // SMs on B200): a GPC holds 2 exclusive clusters or 4 shared ones, so with 8 GPCs 2A + (n - A) <= 8 must hold
+    // for n groups; measured on B200, 16 exclusive clusters do NOT fit at once (one waits for a second wave), 12
+    // do, and n = 7 with A = 1 does -- hence the table (one GPC of slack whenever A >= 2).
+    SplitCtx& sc = split_ctx();
+    int n_excl = 0;
+    if (PARTS == 2 && !no_split) {
+        static const int kExclusive[8] = {0, 1, 2, 3, 3, 2, 1, 1};
+        n_excl = batch.n_groups <= 7 ? kExclusive[batch.n_groups] : 0;
+        if (n_excl < batch.n_groups && !sc.ok) n_excl = 0;
+    }
+    if (n_excl == 0 || n_excl == batch.n_groups) {
+        kern<<<batch.n_groups * 4 * CL, threads, n_excl ? SMEM_EXCLUSIVE : SMEM, stream>>>(
+            xg_v, xg_a, whh, batch, op_dtype, fused, out_dtype, round_tf32, save_pre, save_c, 0);
+        AVS_LAUNCH_CHECK();
+        return AVS_OK;
+    }
+    AVS_CUDA(cudaEventRecord(sc.fork, stream));
+    kern<<<n_excl * 4 * CL, threads, SMEM_EXCLUSIVE, stream>>>(xg_v, xg_a, whh, batch, op_dtype, fused, out_dtype,
+                                                               round_tf32, save_pre, save_c, 0);
     AVS_LAUNCH_CHECK();
+    AVS_CUDA(cudaStreamWaitEvent(sc.aux, sc.fork, 0));
+    kern<<<(batch.n_groups - n_excl) * 4 * CL, threads, SMEM, sc.aux>>>(xg_v, xg_a, whh, batch, op_dtype, fused,
+                                                                        out_dtype, round_tf32, save_pre, save_c, n_excl);
+    AVS_LAUNCH_CHECK();
+    AVS_CUDA(cudaEventRecord(sc.join, sc.aux));
+    AVS_CUDA(cudaStreamWaitEvent(stream, sc.join, 0));
     return AVS_OK;
 }
 

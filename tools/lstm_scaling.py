@@ -13,7 +13,7 @@ model = AVBiLSTMModel(1024, 128, 512, attn_axis="literal_b1").eval()
 model.load_state_dict(synth.seeded_state_dict())
 model = model.cuda()
 nat = model.native()
-for n in (1, 4, 8, 12, 16, 24, 32, 40, 50):
+for n in (1, 4, 8, 16, 24, 28, 32, 36, 40, 44, 48, 50):
     sub = vids[:n]
     lens = [v.T for v in sub]
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
