@@ -991,7 +991,6 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
     }
     AVS_CUDA(cudaMemcpyAsync(off_dev, off64.data(), off64.size() * 8, cudaMemcpyHostToDevice, st));
     AVS_CUDA(cudaMemcpyAsync(desc_dev, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st));
-    AVS_CUDA(cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(std::max(total_S, 1)) * 8, st));
 
     SummaryBatch sb;
     sb.row_start = desc_dev;
@@ -1008,7 +1007,10 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
     sb.max_cap = max_cap;
     sb.max_S = 0;
     for (int v = 0; v < n; ++v) sb.max_S = std::max(sb.max_S, cps_start[v + 1] - cps_start[v]);
-    {
+    // K7 + K8 in one launch when every video's shots fit in shared memory (always, for TVSum/SumMe-sized inputs)
+    const bool fuse_pool = knapsack_can_fuse_pool(sb);
+    if (!fuse_pool) {
+        AVS_CUDA(cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(std::max(total_S, 1)) * 8, st));
         StageTimer tm(ST_POOL, st);
         AVS_TRY(shot_pool(sc, pos, sb, seg_sum, st));
     }
@@ -1016,7 +1018,8 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
                                                     : reinterpret_cast<long long*>(seg_mean);
     {
         StageTimer tm(ST_KNAPSACK, st);
-        AVS_TRY(knapsack_select(sb, seg_sum, seg_mean_target, picks_dev, summary_dev, keep, dp_ws, st));
+        AVS_TRY(knapsack_select(sb, seg_sum, seg_mean_target, picks_dev, summary_dev, keep, dp_ws, st,
+                                fuse_pool ? sc : nullptr, pos));
     }
     if (space == AVS_HOST) {
         AVS_CUDA(cudaMemcpyAsync(picks, picks_dev, total_S, cudaMemcpyDeviceToHost, st));

@@ -154,9 +154,12 @@ struct SummaryBatch {   // device arrays, [n] unless noted
 };
 avs_status shot_pool(const float* scores, const int32_t* positions, const SummaryBatch& b, unsigned long long* seg_sum,
                      cudaStream_t stream);
+// scores / positions non-null (and knapsack_can_fuse_pool(b)): the kernel pools the frame scores itself (fused K7)
+// and seg_sum is not read.
+bool knapsack_can_fuse_pool(const SummaryBatch& b);
 avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_sum, long long* seg_mean,
                            uint8_t* picks, uint8_t* summary, uint32_t* keep_bits, long long* dp_ws,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const float* scores = nullptr, const int32_t* positions = nullptr);
 avs_status temporal_f1_device(const int32_t* pred, const int32_t* pred_start, const int32_t* gt,
                               const int32_t* gt_start, int n, double* f1_dev, cudaStream_t stream);
 

@@ -29,15 +29,10 @@ __device__ __forceinline__ long long quantize_score(float s) {
 // ---------------------------------------------------------------------------- K7
 // One block per video; thread i owns sampled frame i (stride loop).  HBM-bound:
 // 8 B read per sampled frame + 8 B per shot, 8 B written per shot.
-__global__ void __launch_bounds__(256) shot_pool_kernel(const float* __restrict__ scores,
-                                                        const int32_t* __restrict__ positions, SummaryBatch b,
-                                                        unsigned long long* __restrict__ seg_sum) {
-    const int v = blockIdx.x;
-    const int row0 = b.row_start[v];
-    const int T = b.lengths[v];
-    const int nf = b.n_frames[v];
-    const int s0 = b.cps_start[v], S = b.cps_start[v + 1] - s0;
-    const int2* cps = reinterpret_cast<const int2*>(b.cps) + s0;
+// acc: per-shot accumulators of this video (shared or global memory), indexed by the shot number in the video
+__device__ __forceinline__ void pool_video(const float* __restrict__ scores, const int32_t* __restrict__ positions,
+                                           int row0, int T, int nf, const int2* __restrict__ cps, int S,
+                                           unsigned long long* acc) {
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
         const long long q = quantize_score(scores[row0 + i]);
         const int lo = positions[row0 + i];
@@ -53,9 +48,18 @@ __global__ void __launch_bounds__(256) shot_pool_kernel(const float* __restrict_
             const int2 seg = cps[s];
             if (seg.x >= hi) break;
             const int ov = min(hi, seg.y + 1) - max(lo, seg.x);
-            if (ov > 0) atomicAdd(seg_sum + s0 + s, static_cast<unsigned long long>(q * ov));
+            if (ov > 0) atomicAdd(acc + s, static_cast<unsigned long long>(q * ov));
         }
     }
+}
+
+__global__ void __launch_bounds__(256) shot_pool_kernel(const float* __restrict__ scores,
+                                                        const int32_t* __restrict__ positions, SummaryBatch b,
+                                                        unsigned long long* __restrict__ seg_sum) {
+    const int v = blockIdx.x;
+    const int s0 = b.cps_start[v], S = b.cps_start[v + 1] - s0;
+    pool_video(scores, positions, b.row_start[v], b.lengths[v], b.n_frames[v],
+               reinterpret_cast<const int2*>(b.cps) + s0, S, seg_sum + s0);
 }
 
 // ---------------------------------------------------------------------------- K8
@@ -73,7 +77,9 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
                                                                 uint8_t* __restrict__ summary,
                                                                 uint32_t* __restrict__ keep_bits,
                                                                 long long* __restrict__ dp_ws, int smem_rows_cap,
-                                                                int smem_items_cap, int smem_keep_words) {
+                                                                int smem_items_cap, int smem_keep_words,
+                                                                const float* __restrict__ scores,
+                                                                const int32_t* __restrict__ positions) {
     extern __shared__ long long dp_smem[];
     const int v = blockIdx.x;
     const int tid = threadIdx.x;
@@ -102,11 +108,21 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
         nxt = cur + (cap + 1);
     }
     for (int w = tid; w <= cap; w += KNAP_THREADS) cur[w] = 0;
+    // fused K7 (scores != nullptr; the host only asks for it when the items fit in shared memory): pool this
+    // video's frame scores into per-shot sums held in item_val, no global accumulators / memset / extra launch
+    const bool fused_pool = scores != nullptr;
+    if (fused_pool) {
+        for (int s = tid; s < S; s += KNAP_THREADS) item_val[s] = 0;
+        __syncthreads();
+        pool_video(scores, positions, b.row_start[v], b.lengths[v], nf, cps, S,
+                   reinterpret_cast<unsigned long long*>(item_val));
+        __syncthreads();
+    }
     // pooled shot values: mean rounded half up in fixed point (oracle: shot_pool)
     for (int s = tid; s < S; s += KNAP_THREADS) {
         const int2 seg = cps[s];
         const int wt = seg.y - seg.x + 1;
-        const unsigned long long sum = seg_sum[s0 + s];
+        const unsigned long long sum = fused_pool ? static_cast<unsigned long long>(item_val[s]) : seg_sum[s0 + s];
         const long long val = wt > 0 ? static_cast<long long>((2ull * sum + wt) / (2ull * wt)) : 0ll;
         if (seg_mean_out != nullptr) seg_mean_out[s0 + s] = val;
         if (items_in_smem) {
@@ -237,9 +253,17 @@ avs_status shot_pool(const float* scores, const int32_t* positions, const Summar
     return AVS_OK;
 }
 
+bool knapsack_can_fuse_pool(const SummaryBatch& b) {
+    // the fused pooling needs every video's items in shared memory (see the budget below)
+    const size_t limit = 200 * 1024;
+    size_t smem = 2ull * (static_cast<size_t>(b.max_cap) + 1) * sizeof(long long);
+    if (smem > limit) smem = 0;
+    return smem + static_cast<size_t>(b.max_S) * 16 + 8 <= limit;
+}
+
 avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_sum, long long* seg_mean,
                            uint8_t* picks, uint8_t* summary, uint32_t* keep_bits, long long* dp_ws,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const float* scores, const int32_t* positions) {
     if (b.n == 0) return AVS_OK;
     // shared-memory budget (<= 200 KiB): DP rows first, then the items, then the keep bits -- each only if it fits
     const size_t limit = 200 * 1024;
@@ -263,7 +287,8 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
         configured = limit;
     }
     knapsack_kernel<<<b.n, KNAP_THREADS, smem, stream>>>(b, seg_sum, seg_mean, picks, summary, keep_bits, dp_ws,
-                                                        rows_cap, items_cap, keep_words);
+                                                        rows_cap, items_cap, keep_words,
+                                                        items_cap > 0 ? scores : nullptr, positions);
     AVS_LAUNCH_CHECK();
     return AVS_OK;
 }
