@@ -10,6 +10,8 @@
 //   seg_mean_s = floor((2 seg_sum_s + nf_s) / (2 nf_s)),  nf_s = b_s - a_s + 1
 //   dp_s[w]    = max(dp_{s-1}[w], dp_{s-1}[w - nf_s] + seg_mean_s), item kept only on strict gain
 //   back-trace from (S-1, capacity), capacity = floor(n_frames * num / den).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace avs {
@@ -208,6 +210,169 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
     }
 }
 
+// ---------------------------------------------------------------------------- K7 + K8, fast path
+// The common case (TVSum / SumMe-sized videos: capacity < 4096 frames, everything fits in shared memory):
+//   * the shots are loaded into shared memory once; pooling binary-searches them there,
+//   * every thread keeps its DP cells in REGISTERS (cell w = tid + c * 1024); per item it publishes them to one of
+//     two shared buffers and reads dp[w - wt] from the other -- one load + one store per cell and item instead of
+//     two loads + one store, in int32 when the total value fits (S <= 127 shots of <= 2^24 each),
+//   * the keyshot bitmap is produced 16 bytes per thread with one binary search per block.
+// Bit-exact against the same oracle as the general kernel above (which remains for oversized videos).
+constexpr int KNAP_CPT = 4;   // DP cells per thread
+
+template <typename V>
+__global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatch b, const float* __restrict__ scores,
+                                                                     const int32_t* __restrict__ positions,
+                                                                     long long* __restrict__ seg_mean_out,
+                                                                     uint8_t* __restrict__ picks,
+                                                                     uint8_t* __restrict__ summary, int rows_cap,
+                                                                     int items_cap) {
+    extern __shared__ long long fsm[];
+    const int v = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nf = b.n_frames[v];
+    const int s0 = b.cps_start[v], S = b.cps_start[v + 1] - s0;
+    const int2* cps = reinterpret_cast<const int2*>(b.cps) + s0;
+    const long long cap_ll = (static_cast<long long>(nf) * b.prop_num) / b.prop_den;
+    const int cap = static_cast<int>(cap_ll < 0 ? 0 : cap_ll);
+    const int words = (cap + 32) >> 5;
+
+    long long* item_val = fsm;                                           // [items_cap]  sums, then pooled values
+    V* buf_a = reinterpret_cast<V*>(item_val + items_cap);               // [rows_cap]
+    V* buf_b = buf_a + rows_cap + (rows_cap & 1);                        // [rows_cap]  (kept 8-byte aligned)
+    int* item_beg = reinterpret_cast<int*>(buf_b + rows_cap + (rows_cap & 1));   // [items_cap] first frame of the shot
+    int* item_len = item_beg + items_cap;                                // [items_cap] frames; negated once not picked
+    uint32_t* keep = reinterpret_cast<uint32_t*>(item_len + items_cap);  // [S][words]
+
+    for (int s = tid; s < S; s += KNAP_THREADS) {
+        const int2 seg = cps[s];
+        item_beg[s] = seg.x;
+        item_len[s] = seg.y - seg.x + 1;
+        item_val[s] = 0;
+    }
+    __syncthreads();
+    // ---- K7: pool the frame scores of this video into per-shot sums (int64 shared-memory atomics)
+    {
+        const int row0 = b.row_start[v], T = b.lengths[v];
+        unsigned long long* acc = reinterpret_cast<unsigned long long*>(item_val);
+        for (int i = tid; i < T; i += KNAP_THREADS) {
+            const long long q = quantize_score(scores[row0 + i]);
+            const int lo = positions[row0 + i];
+            const int hi = (i + 1 < T) ? positions[row0 + i + 1] : nf;
+            if (hi <= lo || q == 0) continue;
+            int a = 0, z = S;   // first shot whose inclusive end >= lo
+            while (a < z) {
+                const int mid = (a + z) >> 1;
+                if (item_beg[mid] + item_len[mid] - 1 < lo) a = mid + 1; else z = mid;
+            }
+            for (int s = a; s < S; ++s) {
+                const int sb = item_beg[s];
+                if (sb >= hi) break;
+                const int ov = min(hi, sb + item_len[s]) - max(lo, sb);
+                if (ov > 0) atomicAdd(acc + s, static_cast<unsigned long long>(q * ov));
+            }
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < S; s += KNAP_THREADS) {
+        const int wt = item_len[s];
+        const unsigned long long sum = static_cast<unsigned long long>(item_val[s]);
+        const long long val = wt > 0 ? static_cast<long long>((2ull * sum + wt) / (2ull * wt)) : 0ll;
+        if (seg_mean_out != nullptr) seg_mean_out[s0 + s] = val;
+        item_val[s] = val;
+    }
+    // ---- K8: DP with register-resident cells
+    V mine[KNAP_CPT];
+#pragma unroll
+    for (int c = 0; c < KNAP_CPT; ++c) {
+        mine[c] = 0;
+        const int w = tid + c * KNAP_THREADS;
+        if (w <= cap) buf_a[w] = 0;
+    }
+    __syncthreads();
+    for (int s = 0; s < S; ++s) {
+        const int wt = item_len[s];
+        const V val = static_cast<V>(item_val[s]);
+        const V* rd = (s & 1) ? buf_b : buf_a;
+        V* wr = (s & 1) ? buf_a : buf_b;
+#pragma unroll
+        for (int c = 0; c < KNAP_CPT; ++c) {
+            const int w = tid + c * KNAP_THREADS;
+            if (c * KNAP_THREADS <= cap) {   // warp-uniform
+                bool better = false;
+                if (w <= cap) {
+                    const V old = mine[c];
+                    V cand = old;
+                    if (wt > 0 && w >= wt) {
+                        cand = rd[w - wt] + val;
+                        better = cand > old;
+                    } else if (wt == 0 && val > 0) {
+                        cand = old + val;
+                        better = true;
+                    }
+                    mine[c] = better ? cand : old;
+                    wr[w] = mine[c];
+                }
+                const uint32_t bits = __ballot_sync(0xffffffffu, better);
+                if ((tid & 31) == 0 && (w >> 5) < words) keep[s * words + (w >> 5)] = bits;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int w = cap;
+        for (int s = S - 1; s >= 0; --s) {
+            const int take = (keep[s * words + (w >> 5)] >> (w & 31)) & 1;
+            picks[s0 + s] = static_cast<uint8_t>(take);
+            if (take) w -= item_len[s];
+            else item_len[s] = -item_len[s];          // the bitmap pass reads the selection from the sign
+        }
+    }
+    if (summary == nullptr) return;
+    __syncthreads();
+    // ---- keyshot bitmap: frame f is set iff it lies inside a picked shot
+    uint8_t* out = summary + b.summary_start[v];
+    auto shot_of = [&](int f) {   // last shot with beg <= f, or -1
+        int a = 0, z = S;
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (item_beg[mid] <= f) a = mid + 1; else z = mid;
+        }
+        return a - 1;
+    };
+    auto bit_at = [&](int f, int& s) -> uint32_t {   // s: cursor, advanced monotonically
+        while (s + 1 < S && item_beg[s + 1] <= f) ++s;
+        if (s < 0) return 0u;
+        const int len = item_len[s];
+        return (len > 0 && f < item_beg[s] + len) ? 1u : 0u;
+    };
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(out);
+    const int head = min(nf, static_cast<int>((16 - (addr & 15)) & 15));
+    const int body = (nf - head) / 16;
+    for (int f = tid; f < head; f += KNAP_THREADS) {
+        int s = shot_of(f);
+        out[f] = static_cast<uint8_t>(bit_at(f, s));
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(out + head);
+    for (int i = tid; i < body; i += KNAP_THREADS) {
+        const int f0 = head + 16 * i;
+        int s = shot_of(f0);
+        uint32_t wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x |= bit_at(f0 + 4 * k + j, s) << (8 * j);
+            wv[k] = x;
+        }
+        o4[i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    for (int f = head + body * 16 + tid; f < nf; f += KNAP_THREADS) {
+        int s = shot_of(f);
+        out[f] = static_cast<uint8_t>(bit_at(f, s));
+    }
+}
+
 // ------------------------------------------------------------------- overlap F1
 __global__ void __launch_bounds__(256) temporal_f1_kernel(const int2* __restrict__ pred,
                                                           const int32_t* __restrict__ pred_start,
@@ -265,8 +430,40 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
                            uint8_t* picks, uint8_t* summary, uint32_t* keep_bits, long long* dp_ws,
                            cudaStream_t stream, const float* scores, const int32_t* positions) {
     if (b.n == 0) return AVS_OK;
-    // shared-memory budget (<= 200 KiB): DP rows first, then the items, then the keep bits -- each only if it fits
     const size_t limit = 200 * 1024;
+    // ---- fast path: fused pooling, register-resident DP cells, everything in shared memory
+    if (scores != nullptr && b.max_cap + 1 <= KNAP_CPT * KNAP_THREADS) {
+        const bool narrow = b.max_S <= 127;                       // total value < 2^31: int32 DP
+        const int rows = b.max_cap + 1, items = std::max(b.max_S, 1);
+        const size_t vsz = narrow ? 4 : 8;
+        const size_t words_all = static_cast<size_t>(b.max_S) * ((static_cast<size_t>(b.max_cap) + 32) >> 5);
+        const size_t need = static_cast<size_t>(items) * 8 + 2 * (static_cast<size_t>(rows) + 1) * vsz +
+                            static_cast<size_t>(items) * 8 + words_all * 4 + 64;
+        if (need <= limit) {
+            static bool cfg32 = false, cfg64 = false;
+            if (narrow) {
+                if (!cfg32 && need > 48 * 1024) {
+                    AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  static_cast<int>(limit)));
+                    cfg32 = true;
+                }
+                knapsack_fast_kernel<int><<<b.n, KNAP_THREADS, need, stream>>>(b, scores, positions, seg_mean, picks,
+                                                                               summary, rows, items);
+            } else {
+                if (!cfg64 && need > 48 * 1024) {
+                    AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<long long>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(limit)));
+                    cfg64 = true;
+                }
+                knapsack_fast_kernel<long long><<<b.n, KNAP_THREADS, need, stream>>>(b, scores, positions, seg_mean,
+                                                                                     picks, summary, rows, items);
+            }
+            AVS_LAUNCH_CHECK();
+            return AVS_OK;
+        }
+    }
+    // ---- general path.  Shared-memory budget (<= 200 KiB): DP rows first, then the items, then the keep bits --
+    // each only if it fits
     int rows_cap = b.max_cap + 1;
     size_t smem = 2ull * rows_cap * sizeof(long long);
     if (smem > limit) { rows_cap = 0; smem = 0; }
