@@ -768,9 +768,19 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         const int64_t Rc = r1 - r0;
         const float* src_v = (space == AVS_HOST ? in_v : visual) + r0 * Dv;
         const float* src_a = (space == AVS_HOST ? in_a : audio) + r0 * Da;
+        if (space == AVS_HOST) AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[c], 0));
+        // the GEMMs read the features through TMA, which needs 16-byte aligned rows: a caller-owned device buffer
+        // that is not (never the case for a torch tensor) is staged in the workspace first
+        if (space == AVS_DEVICE && !simt && (reinterpret_cast<uintptr_t>(src_v) & 15)) {
+            AVS_CUDA(cudaMemcpyAsync(in_v + r0 * Dv, src_v, static_cast<size_t>(Rc) * Dv * 4, cudaMemcpyDeviceToDevice, st));
+            src_v = in_v + r0 * Dv;
+        }
+        if (space == AVS_DEVICE && !simt && (reinterpret_cast<uintptr_t>(src_a) & 15)) {
+            AVS_CUDA(cudaMemcpyAsync(in_a + r0 * Da, src_a, static_cast<size_t>(Rc) * Da * 4, cudaMemcpyDeviceToDevice, st));
+            src_a = in_a + r0 * Da;
+        }
         const void* xv = src_v;
         const void* xa = src_a;
-        if (space == AVS_HOST) AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[c], 0));
         if (bf16) {
             StageTimer tm(ST_CONVERT, st);
             void* dv = in_v16 + r0 * Dv;

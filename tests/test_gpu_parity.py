@@ -644,3 +644,21 @@ def test_sharded_result_equals_single_gpu_result(native):
         for i in range(len(vids)):
             for a, b in zip(merged[i], whole[i]):
                 assert torch.equal(a, b), (world, i)
+
+
+def test_unaligned_device_features_are_staged(native):
+    """A raw C-ABI caller may hand over device buffers that are only 4-byte aligned; the TMA-fed GEMMs need 16."""
+    v = synth.config1()
+    big_v = torch.zeros(320 * 1024 + 1, device="cuda")
+    big_a = torch.zeros(320 * 128 + 1, device="cuda")
+    big_v[1:] = v.visual.cuda().reshape(-1)
+    big_a[1:] = v.audio.cuda().reshape(-1)
+    want = native.forward_rows(v.visual.cuda(), v.audio.cuda(), [0], [320], "temporal")
+    out = torch.empty(320, device="cuda")
+    rs, ln = np.zeros(1, np.int32), np.full(1, 320, np.int32)
+    _cabi.check(native.lib.avs_forward(native._handle, C.c_void_p(big_v.data_ptr() + 4), C.c_void_p(big_a.data_ptr() + 4),
+                                       320, 1, _cabi.np_ptr(rs), _cabi.np_ptr(ln), _cabi.AVS_ATTN_TEMPORAL, _cabi.AVS_PREC_TF32,
+                                       C.c_void_p(out.data_ptr()), _cabi.AVS_DEVICE,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
