@@ -45,10 +45,14 @@ def test_mhsa_surface():
     assert a.num_heads == 4 and a.dim_head == 256
 
 
-def test_training_mode_is_refused():
+def test_training_mode_has_no_cpu_fallback_and_rejects_unsupported_attention():
     m = AVBiLSTMModel(1024, 128, 512).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):       # the training step needs the CUDA kernels too
         m(torch.zeros(1, 2, 1024), torch.zeros(1, 2, 128))
+    with pytest.raises(NotImplementedError):                         # cross-video attention has no backward
+        m(torch.zeros(2, 2, 1024), torch.zeros(2, 2, 128))
+    with pytest.raises(NotImplementedError):
+        AVBiLSTMModel(1024, 128, 512, attn_axis="temporal").train()(torch.zeros(1, 2, 1024), torch.zeros(1, 2, 128))
 
 
 def test_synthetic_workloads_are_deterministic():
