@@ -1,6 +1,6 @@
 """Seeded synthetic TVSum/SumMe-shaped workloads.
 
-Shared by the tests, ``bench.py`` and ``tools/make_golden.py`` so that the
+Shared by the tests, ``bench.py`` and ``tests/golden/make_golden.py`` so that the
 oracle, the golden fixtures and the CUDA path all see identical bytes.  Uses
 only torch/numpy CPU generators, which are platform independent.
 """

@@ -13,7 +13,7 @@ Two halves:
    ``nn.MultiheadAttention``, ``nn.Sigmoid``; unpinned version, torch 2.11.0 in
    this image) is restated from its published definitions.  PARITY PINNED: the
    restatement is checked against ``tests/golden/*.npz``, which were produced by
-   importing the reference itself (``tools/make_golden.py``).
+   importing the reference itself (``tests/golden/make_golden.py``).
 
 2. **Summary generation** (shot pooling over change points, 0/1 knapsack at a
    length budget, keyshot bitmap).  The reference contains NO such code

@@ -6,7 +6,7 @@ so its CPU cost *is* the cost of ATen's ``nn.Linear`` / ``nn.LSTM`` /
 GPU box, therefore the bench's ``cpu_baseline`` / ``--impl reference`` legs time
 this restatement ("kind": "port"): same modules, same call order, same B=1
 per-video loop as ``scripts/evaluate.py:12-18`` (minus ``.cuda()``), followed by
-the numpy summary oracle.  ``tools/make_golden.py`` checks, in the container
+the numpy summary oracle.  ``tests/golden/make_golden.py`` checks, in the container
 that has the reference, that this module reproduces the imported reference
 bit for bit (``torch.equal``) from the same state_dict.
 

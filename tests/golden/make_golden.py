@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by IMPORTING THE REFERENCE from /root/reference.
 
 Run in the build container only (the GPU box has no /root/reference):
-    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 Every fixture stores the seeded-input recipe, the reference's outputs and a
 checksum of the weights, so the tests can rebuild identical inputs without the
 reference.  Also cross-checks oracle/av_oracle_torch.py (bit-exact) and
@@ -13,7 +13,7 @@ import types
 
 os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
 sys.dont_write_bytecode = True
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(1, "/root/reference")
 

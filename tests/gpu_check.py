@@ -1,8 +1,8 @@
 """First-contact GPU checks, one subprocess per stage so a trap/hang in one kernel does not
 hide the results of the others.  Run on the GPU box:
 
-    python tools/gpu_check.py            # all stages, each under its own timeout
-    python tools/gpu_check.py --stage gemm_tc
+    python tests/gpu_check.py            # all stages, each under its own timeout
+    python tests/gpu_check.py --stage gemm_tc
 
 Prints one line per check; exits non-zero if any stage failed.
 """

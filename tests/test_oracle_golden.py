@@ -1,5 +1,5 @@
 """CPU tests: the oracle against the golden vectors produced by the imported reference
-(tools/make_golden.py), plus property tests of the repo-specified summary oracle."""
+(tests/golden/make_golden.py), plus property tests of the repo-specified summary oracle."""
 import itertools
 import os
 

@@ -25,7 +25,6 @@ def main():
     qkv = (torch.randn(T, 3072, generator=g) * 0.5).cuda()
     ctx = runtime.attention(qkv, 1024, 4, [0], [1], [T])
     torch.cuda.synchronize()
-    from oracle import av_oracle
     q = qkv[:, :256].cpu().numpy(); k = qkv[:, 1024:1280].cpu().numpy(); v = qkv[:, 2048:2304].cpu().numpy()
     rows = np.arange(0, T, max(1, T // 64))
     s = (q[rows] @ k.T) / 16.0

@@ -81,9 +81,26 @@ def main():
                 "n_gpus": world, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "frames_per_s": B * T * world / (ms * 1e-3),
                 "approx_tflops": flops / (ms * 1e-3) / 1e12, "final_loss": float(loss)}
         if args.cpu_baseline and world == 1:
-            from oracle import av_oracle_torch
+            import torch.nn as nn
+
+            class RefModel(nn.Module):   # the reference's module tree and forward (models/av_model.py:7-46), CPU timing only
+                def __init__(self, vd, ad, hd):
+                    super().__init__()
+                    self.visual_fc = nn.Sequential(nn.Linear(vd, hd), nn.ReLU(), nn.Dropout(0.3))
+                    self.audio_fc = nn.Sequential(nn.Linear(ad, hd), nn.ReLU(), nn.Dropout(0.3))
+                    self.visual_bilstm = nn.LSTM(hd, hd // 2, bidirectional=True, batch_first=True)
+                    self.audio_bilstm = nn.LSTM(hd, hd // 2, bidirectional=True, batch_first=True)
+                    self.attention = nn.MultiheadAttention(embed_dim=hd * 2, num_heads=4)
+                    self.scorer = nn.Sequential(nn.Linear(hd * 2, 64), nn.ReLU(), nn.Linear(64, 1), nn.Sigmoid())
+
+                def forward(self, visual, audio):
+                    v, _ = self.visual_bilstm(self.visual_fc(visual))
+                    a, _ = self.audio_bilstm(self.audio_fc(audio))
+                    fused = torch.cat([v, a], dim=-1)
+                    return self.scorer(self.attention(fused, fused, fused)[0]).squeeze()
+
             torch.set_num_threads(os.cpu_count() or 1)
-            port = av_oracle_torch.RefPortModel(1024, 128, 512).train()
+            port = RefModel(1024, 128, 512).train()
             port.load_state_dict(synth.seeded_state_dict())
             popt = torch.optim.AdamW(port.parameters(), lr=1e-4)
             vh, ah, th = visual.cpu(), audio.cpu(), target.cpu()
