@@ -662,3 +662,47 @@ def test_unaligned_device_features_are_staged(native):
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("prop", [(15, 100), (1, 2), (0, 1), (1, 1), (3, 7)])
+def test_summarize_randomised_batches_bit_exact(native, prop):
+    """Randomised change points (gaps, one-frame shots, shots longer than the capacity), irregular positions,
+    degenerate scores and budgets: picks / shot means / bitmap bit-exact against the oracle, on the fast path
+    (everything in shared memory) and, with one oversized video in the batch, on the general path."""
+    rng = np.random.default_rng(100 + prop[0] * 7 + prop[1])
+    for oversized in (False, True):
+        vids, scores = [], []
+        n_vid = 40
+        for i in range(n_vid):
+            nf = int(rng.integers(1, 3000)) if not (oversized and i == 0) else 40000
+            # sorted, disjoint, inclusive shots with random gaps
+            cuts = np.sort(rng.choice(nf + 1, size=min(nf + 1, 2 * int(rng.integers(1, 40))), replace=False))
+            shots = []
+            for a, b in zip(cuts[0::2], cuts[1::2]):
+                if b > a:
+                    shots.append((int(a), int(b) - 1))
+            if not shots:
+                shots = [(0, nf - 1)]
+            T = int(rng.integers(1, min(nf, 400) + 1))
+            pos = np.sort(rng.choice(nf, size=T, replace=False)).astype(np.int32)
+            sc = rng.random(T).astype(np.float32)
+            sc[rng.random(T) < 0.05] = 0.0
+            sc[rng.random(T) < 0.05] = 1.0
+            if T > 3:
+                sc[1] = np.nan
+            vids.append(synth.Video(torch.zeros(T, 1), torch.zeros(T, 1), nf, pos, np.asarray(shots, np.int32)))
+            scores.append(sc)
+        lens = [v.T for v in vids]
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+        allsc = np.concatenate(scores)
+        allpos = np.concatenate([v.positions for v in vids]).astype(np.int32)
+        picks, seg_mean, summary, cps_start, sum_start = native.summarize_rows(
+            torch.from_numpy(allsc).cuda(), torch.from_numpy(allpos).cuda(), starts, lens, [v.n_frames for v in vids],
+            [v.cps for v in vids], prop)
+        torch.cuda.synchronize()
+        picks, seg_mean, summary = picks.cpu().numpy(), seg_mean.cpu().numpy(), summary.cpu().numpy()
+        for i, v in enumerate(vids):
+            wp, ws, wm = av_oracle.generate_summary(scores[i], v.cps, v.n_frames, v.positions, prop[0], prop[1])
+            assert np.array_equal(wm, seg_mean[cps_start[i]:cps_start[i + 1]]), (oversized, i)
+            assert np.array_equal(wp, picks[cps_start[i]:cps_start[i + 1]]), (oversized, i)
+            assert np.array_equal(ws, summary[sum_start[i]:sum_start[i + 1]]), (oversized, i)
