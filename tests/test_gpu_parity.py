@@ -706,3 +706,24 @@ def test_summarize_randomised_batches_bit_exact(native, prop):
             assert np.array_equal(wm, seg_mean[cps_start[i]:cps_start[i + 1]]), (oversized, i)
             assert np.array_equal(wp, picks[cps_start[i]:cps_start[i + 1]]), (oversized, i)
             assert np.array_equal(ws, summary[sum_start[i]:sum_start[i + 1]]), (oversized, i)
+
+
+@pytest.mark.parametrize("n_videos", [20, 70, 150, 300])
+def test_forward_many_short_videos_all_lstm_variants(cuda_ready, n_videos):
+    """Batches of 20 / 70 / 150 / 300 videos select the 16- / 32- / 64-slot recurrence kernels (and, beyond one
+    wave of clusters, several waves); every video must equal its own B = 1 run bit for bit, and the reference."""
+    rng = np.random.default_rng(n_videos)
+    lens = [int(x) for x in rng.integers(1, 12, n_videos)]
+    g = torch.Generator().manual_seed(n_videos)
+    vis = [torch.randn(t, 1024, generator=g) for t in lens]
+    aud = [torch.randn(t, 128, generator=g) for t in lens]
+    m = make_model(spread=True, attn_axis="temporal")
+    got = m.score_videos([(v.cuda(), a.cuda()) for v, a in zip(vis, aud)])
+    sd = synth.seeded_state_dict(spread=True)
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
+    port.load_state_dict(sd)
+    for i in list(range(0, n_videos, max(1, n_videos // 12))) + [n_videos - 1]:
+        alone = m.score_videos([(vis[i].cuda(), aud[i].cuda())])[0]
+        assert torch.equal(got[i], alone), i
+        want = av_oracle_torch.run_videos(port, [(vis[i], aud[i])], "temporal")[0]
+        assert rel(got[i].cpu().numpy(), want.numpy()) < 1e-3, i
