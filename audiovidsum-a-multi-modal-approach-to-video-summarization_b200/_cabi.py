@@ -29,6 +29,7 @@ EXPORTS = [
     "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace",
     "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
     "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
+    "avs_debug_e2e_trace",
 ]
 
 
@@ -123,6 +124,8 @@ def lib() -> C.CDLL:
     L.avs_linear_bwd.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     L.avs_debug_lstm_trace.restype = C.c_int
     L.avs_debug_lstm_trace.argtypes = [vp]
+    L.avs_debug_e2e_trace.restype = C.c_int
+    L.avs_debug_e2e_trace.argtypes = [vp]
     L.avs_profile.restype = None
     L.avs_profile.argtypes = [C.c_int]
     L.avs_profile_stages.restype = C.c_int

@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <numeric>
 #include <vector>
 
@@ -80,6 +82,35 @@ struct StageTimer {
         }
     }
 };
+
+// ---- optional timeline of a pipelined host-space call (AVS_E2E_TRACE=1; read with avs_debug_e2e_trace) ----------
+// CUDA events with timing next to the (timing-disabled) dependency events of forward_entry / avs_forward_summarize,
+// plus host clock samples; a debugging aid that explains where an end-to-end step goes.
+struct E2ETrace {
+    int on = -1;
+    cudaEvent_t t0 = nullptr, chunk[6] = {}, grp[6] = {}, knap = nullptr, end = nullptr;
+    int n_groups = 0;
+    double host[6] = {};   // seconds: [0] entry, [1] copies queued, [2] groups queued, [3] tail queued, [4] synchronised
+    bool enabled() {
+        if (on < 0) {
+            const char* e = getenv("AVS_E2E_TRACE");
+            on = (e && e[0] == '1') ? 1 : 0;
+            if (on) {
+                cudaEventCreate(&t0);
+                cudaEventCreate(&knap);
+                cudaEventCreate(&end);
+                for (int i = 0; i < 6; ++i) { cudaEventCreate(&chunk[i]); cudaEventCreate(&grp[i]); }
+            }
+        }
+        return on == 1;
+    }
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + ts.tv_nsec * 1e-9;
+    }
+};
+static E2ETrace g_e2e;
 
 namespace {
 
@@ -431,6 +462,27 @@ avs_status avs_debug_lstm_trace(uint64_t* out8) {
     return lstm_trace_read(reinterpret_cast<unsigned long long*>(out8));
 }
 
+/* Debugging aid: timeline of the last pipelined host-space avs_forward_summarize call (AVS_E2E_TRACE=1).
+ * out[0] = number of video groups G; out[1..5] = host clock at entry / copies queued / groups queued / tail queued /
+ * synchronised (ms after entry); then, in ms after the first device timestamp: out[6..6+G) = group g's features
+ * landed, out[12..12+G) = group g's forward finished, out[18] = knapsack finished, out[19] = last D2H finished. */
+avs_status avs_debug_e2e_trace(double* out20) {
+    AVS_CHECK(out20 != nullptr, AVS_ERR_INVALID, "null pointer");
+    AVS_CHECK(g_e2e.on == 1 && g_e2e.n_groups > 0, AVS_ERR_INVALID, "no trace recorded (AVS_E2E_TRACE=1, pipelined call)");
+    for (int i = 0; i < 20; ++i) out20[i] = 0.0;
+    out20[0] = g_e2e.n_groups;
+    for (int i = 0; i < 5; ++i) out20[1 + i] = (g_e2e.host[i] - g_e2e.host[0]) * 1e3;
+    float t = 0.f;
+    for (int g = 0; g < g_e2e.n_groups; ++g) {
+        if (cudaEventElapsedTime(&t, g_e2e.t0, g_e2e.chunk[g]) == cudaSuccess) out20[6 + g] = t;
+        if (cudaEventElapsedTime(&t, g_e2e.t0, g_e2e.grp[g]) == cudaSuccess) out20[12 + g] = t;
+    }
+    if (cudaEventElapsedTime(&t, g_e2e.t0, g_e2e.knap) == cudaSuccess) out20[18] = t;
+    if (cudaEventElapsedTime(&t, g_e2e.t0, g_e2e.end) == cudaSuccess) out20[19] = t;
+    cudaGetLastError();
+    return AVS_OK;
+}
+
 int avs_device_ok(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -623,6 +675,11 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
         first[gi] = b;
     }
     first[n_groups] = n_videos;
+    const bool trace = g_e2e.enabled();
+    if (trace) {
+        g_e2e.n_groups = n_groups;
+        cudaEventRecord(g_e2e.t0, st);
+    }
     AVS_CUDA(cudaEventRecord(m->ev_start, st));                 // staging is free once prior work on st is done
     AVS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
     if (positions_host)   // summary input, a few KB: goes first so it never waits behind the features
@@ -639,7 +696,9 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
                                      m->copy_stream));
         }
         AVS_CUDA(cudaEventRecord(m->ev_chunk[gi], m->copy_stream));
+        if (trace) cudaEventRecord(g_e2e.chunk[gi], m->copy_stream);
     }
+    if (trace) g_e2e.host[1] = E2ETrace::now();
     // every group on its own stream and workspace: the recurrence of group g (a chain of max(T_g) dependent steps
     // that leaves most of the chip idle) keeps running while group g+1 starts
     std::vector<int32_t> rs;
@@ -653,11 +712,13 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
         AVS_TRY(forward_impl(m, in_v + lo[gi] * Dv, in_a + lo[gi] * Da, hi[gi] - lo[gi], nv, rs.data(),
                              lengths + first[gi], attn_axis, precision, sc_dev + lo[gi], AVS_DEVICE, gs,
                              gi == 0 ? nullptr : &m->ws_grp[gi - 1]));
+        if (trace) cudaEventRecord(g_e2e.grp[gi], gs);
         if (gi > 0) {
             AVS_CUDA(cudaEventRecord(m->ev_grp[gi - 1], gs));
             AVS_CUDA(cudaStreamWaitEvent(st, m->ev_grp[gi - 1], 0));
         }
     }
+    if (trace) g_e2e.host[2] = E2ETrace::now();
     if (scores_dev_out != nullptr) {   // the caller continues on the stream with the scores still on the device
         *scores_dev_out = sc_dev;
         if (positions_dev_out) *positions_dev_out = pos_dev;
@@ -1031,12 +1092,19 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
         AVS_TRY(knapsack_select(sb, seg_sum, seg_mean_target, picks_dev, summary_dev, keep, dp_ws, st,
                                 fuse_pool ? sc : nullptr, pos));
     }
+    const bool trace = g_e2e.enabled() && space == AVS_HOST;
+    if (trace) cudaEventRecord(g_e2e.knap, st);
     if (space == AVS_HOST) {
         AVS_CUDA(cudaMemcpyAsync(picks, picks_dev, total_S, cudaMemcpyDeviceToHost, st));
         if (seg_mean) AVS_CUDA(cudaMemcpyAsync(seg_mean, seg_mean_dev, static_cast<size_t>(total_S) * 8,
                                                cudaMemcpyDeviceToHost, st));
         if (summary) AVS_CUDA(cudaMemcpyAsync(summary, summary_dev, sum_bytes, cudaMemcpyDeviceToHost, st));
+        if (trace) {
+            cudaEventRecord(g_e2e.end, st);
+            g_e2e.host[3] = E2ETrace::now();
+        }
         AVS_CUDA(cudaStreamSynchronize(st));
+        if (trace) g_e2e.host[4] = E2ETrace::now();
     }
     return AVS_OK;
 }
@@ -1067,6 +1135,7 @@ avs_status avs_forward_summarize(avs_model* m, const float* visual, const float*
     }
     // host space: features in, scores stay on the device for pooling + knapsack, everything comes back with ONE
     // synchronisation at the end (no D2H -> H2D round trip of the scores between the two halves)
+    if (g_e2e.enabled()) g_e2e.host[0] = E2ETrace::now();
     int max_len = 0;
     AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
     if (total_rows == 0 || n_videos == 0 || max_len == 0)

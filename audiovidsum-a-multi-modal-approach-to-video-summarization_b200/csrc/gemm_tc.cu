@@ -84,8 +84,140 @@ __device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int 
         }
     }
 }
+// arrive on an mbarrier given by its shared::cluster address (own CTA or the pair's leader)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// The epilogue warps (4 warps, one per TMEM lane quarter) of both GEMM kernels.  Tiles t = tile0, tile0 + tile_step,
+// ...; this CTA owns rows [m0, m0 + 128) of the tile with m0 = (t / tiles_n) * tile_rows + m_off.  tmem_empty_addr:
+// shared::cluster address of the two "accumulator drained" barriers (in the leader CTA for the 2-CTA kernel).
+template <int BN, class L>
+__device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint32_t tmem_empty_addr, const CUtensorMap& tmC, int M, int N, int tiles_n,
+                                              int num_tiles, int tile0, int tile_step, int tile_rows, int m_off,
+                                              const GemmEpilogue& epi, int warp, int lane) {
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const uint32_t lane_taddr = static_cast<uint32_t>(q * 32) << 16;
+        if (epi.scores != nullptr) {
+            // fused frame-score head: one float per row, straight from registers
+            const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
+            const bool w2_vec = (reinterpret_cast<uintptr_t>(epi.score_w2) & 15) == 0;
+            uint32_t lt = 0;
+            for (int t = tile0; t < num_tiles; t += tile_step, ++lt) {
+                const int m0 = (t / tiles_n) * tile_rows + m_off, n0 = (t % tiles_n) * BN;
+                const uint32_t acc = lt & 1;
+                mbar_wait(tmem_full + acc, (lt >> 1) & 1);
+                tc_fence_after();
+                const int row = m0 + q * 32 + lane;
+                float score_acc = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    float bv[32], wv[32];
+                    const int nb = n0 + c;
+                    tmem_ld_32x32(tmem_base + acc * BN + lane_taddr + c, r);
+                    load_bias32(epi.bias, nb, N, bias_vec, bv);
+                    load_bias32(epi.score_w2, nb, N, w2_vec, wv);   // zero beyond N: those columns drop out
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]);
+                        if (epi.relu) x = fmaxf(x, 0.f);
+                        score_acc = fmaf(x, wv[j], score_acc);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(tmem_empty_addr + acc * 8);
+                if (row < M) epi.scores[row] = sigmoidf_acc(score_acc + __ldg(epi.score_b2));
+            }
+        } else {
+            // stage 32 rows x 128 B boxes (32 fp32 or 64 half columns) in swizzled shared memory, TMA-store each
+            const bool wide = epi.out_dtype != DT_F32;          // 16-bit output: 64 columns per 128-byte box
+            const int box_cols = wide ? 64 : 32;
+            const int n_boxes = BN / box_cols;
+            constexpr int SLOTS = L::OUT_WARP_BYTES / 4096;     // staging boxes per warp (a 256-wide fp32 tile cycles twice)
+            uint32_t issued = 0;                                // boxes handed to the TMA engine so far
+            const uint32_t out_base = smem_u32(tiles + L::TILE_BYTES) + q * L::OUT_WARP_BYTES;
+            const uint32_t my_row = out_base + lane * 128;
+            const uint32_t sw = static_cast<uint32_t>(lane & 7);
+            const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
+            uint32_t lt = 0;
+            for (int t = tile0; t < num_tiles; t += tile_step, ++lt) {
+                const int m0 = (t / tiles_n) * tile_rows + m_off, n0 = (t % tiles_n) * BN;
+                const uint32_t acc = lt & 1;
+                mbar_wait(tmem_full + acc, (lt >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * BN + lane_taddr;
+#pragma unroll 1
+                for (int bx = 0; bx < n_boxes; ++bx) {
+                    const int nb = n0 + bx * box_cols;
+                    // the TMA store that read this staging slot SLOTS boxes ago must be done reading
+                    const uint32_t slot = issued % SLOTS;
+                    if (issued >= SLOTS) {
+                        if (lane == 0) bulk_wait_group_read(SLOTS - 1);
+                        __syncwarp();
+                    }
+                    ++issued;
+                    const uint32_t dst = my_row + slot * 4096;
+                    if (!wide) {
+                        uint32_t r[32];
+                        float bv[32];
+                        tmem_ld_32x32(taddr + bx * 32, r);
+                        load_bias32(epi.bias, nb, N, bias_vec, bv);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]);
+                            if (epi.relu) x = fmaxf(x, 0.f);
+                            if (epi.round_tf32) x = to_tf32_rn(x);
+                            r[j] = __float_as_uint(x);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), r[4 * j], r[4 * j + 1],
+                                         r[4 * j + 2], r[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t r[32];
+                            float bv[32];
+                            tmem_ld_32x32(taddr + bx * 64 + hf * 32, r);
+                            load_bias32(epi.bias, nb + hf * 32, N, bias_vec, bv);
+                            tmem_ld_wait();
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float x0 = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]), x1 = fmaf(__uint_as_float(r[j + 1]), epi.acc_scale, bv[j + 1]);
+                                if (epi.relu) {
+                                    x0 = fmaxf(x0, 0.f);
+                                    x1 = fmaxf(x1, 0.f);
+                                }
+                                pk[j >> 1] = pack_lowp2(x0, x1, epi.out_dtype);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                st_shared_v4(dst + ((static_cast<uint32_t>(hf * 4 + j) ^ sw) << 4), pk[4 * j],
+                                             pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                    fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (nb < N) tma_store_2d(&tmC, out_base + slot * 4096, nb, m0 + q * 32);
+                        bulk_commit_group();   // (possibly empty) keeps the group count per tile fixed
+                    }
+                }
+                // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
+                tc_fence_before();
+                mbar_arrive_cluster(tmem_empty_addr + acc * 8);
+            }
+            if (lane == 0) bulk_wait_group_read(0);   // shared memory must outlive the last stores' reads
+            __syncwarp();
+        }
 }
 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, + gridDim.x, ...
@@ -183,125 +315,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const uint32_t lane_taddr = static_cast<uint32_t>(q * 32) << 16;
-        if (epi.scores != nullptr) {
-            // fused frame-score head: one float per row, straight from registers
-            const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
-            const bool w2_vec = (reinterpret_cast<uintptr_t>(epi.score_w2) & 15) == 0;
-            uint32_t lt = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
-                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
-                const uint32_t acc = lt & 1;
-                mbar_wait(tmem_full + acc, (lt >> 1) & 1);
-                tc_fence_after();
-                const int row = m0 + q * 32 + lane;
-                float score_acc = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    uint32_t r[32];
-                    float bv[32], wv[32];
-                    const int nb = n0 + c;
-                    tmem_ld_32x32(tmem_base + acc * BN + lane_taddr + c, r);
-                    load_bias32(epi.bias, nb, N, bias_vec, bv);
-                    load_bias32(epi.score_w2, nb, N, w2_vec, wv);   // zero beyond N: those columns drop out
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]);
-                        if (epi.relu) x = fmaxf(x, 0.f);
-                        score_acc = fmaf(x, wv[j], score_acc);
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(tmem_empty + acc);
-                if (row < M) epi.scores[row] = sigmoidf_acc(score_acc + __ldg(epi.score_b2));
-            }
-        } else {
-            // stage 32 rows x 128 B boxes (32 fp32 or 64 half columns) in swizzled shared memory, TMA-store each
-            const bool wide = epi.out_dtype != DT_F32;          // 16-bit output: 64 columns per 128-byte box
-            const int box_cols = wide ? 64 : 32;
-            const int n_boxes = BN / box_cols;
-            constexpr int SLOTS = L::OUT_WARP_BYTES / 4096;     // staging boxes per warp (a 256-wide fp32 tile cycles twice)
-            uint32_t issued = 0;                                // boxes handed to the TMA engine so far
-            const uint32_t out_base = smem_u32(tiles + L::TILE_BYTES) + q * L::OUT_WARP_BYTES;
-            const uint32_t my_row = out_base + lane * 128;
-            const uint32_t sw = static_cast<uint32_t>(lane & 7);
-            const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
-            uint32_t lt = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
-                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
-                const uint32_t acc = lt & 1;
-                mbar_wait(tmem_full + acc, (lt >> 1) & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + acc * BN + lane_taddr;
-#pragma unroll 1
-                for (int bx = 0; bx < n_boxes; ++bx) {
-                    const int nb = n0 + bx * box_cols;
-                    // the TMA store that read this staging slot SLOTS boxes ago must be done reading
-                    const uint32_t slot = issued % SLOTS;
-                    if (issued >= SLOTS) {
-                        if (lane == 0) bulk_wait_group_read(SLOTS - 1);
-                        __syncwarp();
-                    }
-                    ++issued;
-                    const uint32_t dst = my_row + slot * 4096;
-                    if (!wide) {
-                        uint32_t r[32];
-                        float bv[32];
-                        tmem_ld_32x32(taddr + bx * 32, r);
-                        load_bias32(epi.bias, nb, N, bias_vec, bv);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float x = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]);
-                            if (epi.relu) x = fmaxf(x, 0.f);
-                            if (epi.round_tf32) x = to_tf32_rn(x);
-                            r[j] = __float_as_uint(x);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            st_shared_v4(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), r[4 * j], r[4 * j + 1],
-                                         r[4 * j + 2], r[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            uint32_t r[32];
-                            float bv[32];
-                            tmem_ld_32x32(taddr + bx * 64 + hf * 32, r);
-                            load_bias32(epi.bias, nb + hf * 32, N, bias_vec, bv);
-                            tmem_ld_wait();
-                            uint32_t pk[16];
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                float x0 = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]), x1 = fmaf(__uint_as_float(r[j + 1]), epi.acc_scale, bv[j + 1]);
-                                if (epi.relu) {
-                                    x0 = fmaxf(x0, 0.f);
-                                    x1 = fmaxf(x1, 0.f);
-                                }
-                                pk[j >> 1] = pack_lowp2(x0, x1, epi.out_dtype);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                st_shared_v4(dst + ((static_cast<uint32_t>(hf * 4 + j) ^ sw) << 4), pk[4 * j],
-                                             pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        }
-                    }
-                    fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA engine
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (nb < N) tma_store_2d(&tmC, out_base + slot * 4096, nb, m0 + q * 32);
-                        bulk_commit_group();   // (possibly empty) keeps the group count per tile fixed
-                    }
-                }
-                // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
-                tc_fence_before();
-                mbar_arrive(tmem_empty + acc);
-            }
-            if (lane == 0) bulk_wait_group_read(0);   // shared memory must outlive the last stores' reads
-            __syncwarp();
-        }
+        gemm_epilogue<BN, L>(tiles, tmem_base, tmem_full, smem_u32(tmem_empty), tmC, M, N, tiles_n, num_tiles,
+                             static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), BM, 0, epi, warp, lane);
     }
     tc_fence_before();
     __syncthreads();

@@ -225,6 +225,13 @@ void avs_profile_read(double* ms, int64_t* calls);
  * next h landed), out8[7] = number of steps. */
 avs_status avs_debug_lstm_trace(uint64_t* out8);
 
+/* Debugging aid: timeline of the last pipelined host-space avs_forward_summarize call, recorded when the
+ * environment variable AVS_E2E_TRACE is 1.  out20[0] = number of video groups G; out20[1..5] = host clock (ms after
+ * entry) at entry / copies queued / groups queued / tail queued / synchronised; in ms after the first device
+ * timestamp: out20[6..6+G) = features of group g landed, out20[12..12+G) = forward of group g finished,
+ * out20[18] = pooling + knapsack finished, out20[19] = last D2H copy finished. */
+avs_status avs_debug_e2e_trace(double* out20);
+
 #ifdef __cplusplus
 }
 #endif
