@@ -29,7 +29,7 @@ EXPORTS = [
     "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace",
     "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
     "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
-    "avs_debug_e2e_trace",
+    "avs_debug_e2e_trace", "avs_forward_summarize_async", "avs_slot_wait",
 ]
 
 
@@ -100,6 +100,11 @@ def lib() -> C.CDLL:
     L.avs_forward_summarize.restype = C.c_int
     L.avs_forward_summarize.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, C.c_int, C.c_int, vp, vp, vp, i32, i32,
                                         vp, vp, vp, vp, vp, C.c_int, vp]
+    L.avs_forward_summarize_async.restype = C.c_int
+    L.avs_forward_summarize_async.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, C.c_int, C.c_int, vp, vp, vp, i32, i32,
+                                              vp, vp, vp, vp, vp, C.c_int, vp]
+    L.avs_slot_wait.restype = C.c_int
+    L.avs_slot_wait.argtypes = [vp, C.c_int]
     L.avs_linear.restype = C.c_int
     L.avs_linear.argtypes = [vp, vp, vp, i64, i32, i32, C.c_int, C.c_int, vp, vp]
     L.avs_bilstm_pair.restype = C.c_int

@@ -201,7 +201,13 @@ struct avs_model {
     uint16_t *fc_v_w_l[2], *fc_a_w_l[2], *ih_v_l[2], *ih_a_l[2], *in_w_l[2], *out_w_l[2], *sc0_w_l[2];
     Arena ws;       // activations
     Arena staging;  // raw weights during packing
-    Arena host_in;  // device copies of host-space inputs when a call is pipelined by video group
+    // device copies of host-space inputs when a call is pipelined by video group, and the pooling / knapsack
+    // workspace; two slots so that avs_forward_summarize_async can stream batch i+1 while batch i finishes
+    static constexpr int SLOTS = 2;
+    Arena host_in[SLOTS];
+    Arena sum_ws[SLOTS];
+    cudaEvent_t ev_slot[SLOTS] = {};   // recorded at the end of an asynchronous step
+    bool slot_busy[SLOTS] = {};
     Arena ws_grp[5];                 // activations of groups 1..5 (group 0 uses ws): the groups run concurrently
     cudaStream_t grp_stream[5] = {}; // compute streams of groups 1..5 (group 0 runs on the caller's stream)
     cudaEvent_t ev_grp[5] = {};
@@ -554,6 +560,8 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
             ce = cudaStreamCreateWithFlags(&m->grp_stream[i], cudaStreamNonBlocking);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_grp[i], cudaEventDisableTiming);
         }
+        for (int i = 0; i < avs_model::SLOTS && ce == cudaSuccess; ++i)
+            ce = cudaEventCreateWithFlags(&m->ev_slot[i], cudaEventDisableTiming);
         if (ce != cudaSuccess) {
             set_error("creating the copy stream / events failed: %s", cudaGetErrorString(ce));
             s = AVS_ERR_CUDA;
@@ -583,7 +591,11 @@ void avs_model_destroy(avs_model* m) {
     cudaDeviceSynchronize();
     m->ws.release();
     m->staging.release();
-    m->host_in.release();
+    for (int i = 0; i < avs_model::SLOTS; ++i) {
+        m->host_in[i].release();
+        m->sum_ws[i].release();
+        if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
+    }
     for (int i = 0; i < 5; ++i) {
         m->ws_grp[i].release();
         if (m->grp_stream[i]) cudaStreamDestroy(m->grp_stream[i]);
@@ -599,33 +611,42 @@ void avs_model_destroy(avs_model* m) {
 
 static avs_status forward_impl(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
                                int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int attn_axis,
-                               int precision, float* scores, int space, void* cuda_stream, Arena* arena = nullptr);
+                               int precision, float* scores, int space, void* cuda_stream, Arena* arena = nullptr,
+                               int lstm_excl = 0);
 
 // scores_dev_out != nullptr (host space only): leave the scores on the device (pointer returned), skip the D2H copy
 // and the final synchronisation -- the caller continues on the stream (avs_forward_summarize).
 static avs_status forward_entry(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
                                 int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int attn_axis,
                                 int precision, float* scores, int space, void* cuda_stream, float** scores_dev_out,
-                                const int32_t* positions_host, int32_t** positions_dev_out) {
+                                const int32_t* positions_host, int32_t** positions_dev_out, int slot = 0,
+                                bool async = false) {
     // Host-space calls on large packed batches are pipelined by VIDEO GROUP: all H2D copies are queued on the
     // copy stream up front, and the complete forward of group g (GEMMs, recurrences, attention, score head) runs
     // on the caller's stream as soon as its rows have landed -- i.e. while group g+1 is still crossing PCIe.
     // The recurrence of a group lasts as long as its longest video, so callers that order the batch longest
     // video first (data/dataset.py packed_batches does) hide most of the compute behind the transfer.
     const bool per_video = attn_axis == AVS_ATTN_TEMPORAL || attn_axis == AVS_ATTN_LITERAL_B1;
+    const bool host = space == AVS_HOST;
     int n_groups = 1;
-    if (m != nullptr && space == AVS_HOST && per_video && visual && audio && (scores || scores_dev_out) && row_start &&
-        lengths &&
-        n_videos >= 2 && total_rows >= 4096 && total_rows < (1ll << 31)) {
+    if (m != nullptr && (host || space == AVS_DEVICE) && per_video && visual && audio && (scores || scores_dev_out) &&
+        row_start && lengths && n_videos >= 2 && total_rows >= 4096 && total_rows < (1ll << 31)) {
         bool ordered = true;   // groups must be contiguous, disjoint row ranges
         for (int b = 0; b < n_videos && ordered; ++b) {
             ordered = lengths[b] >= 0 && row_start[b] >= 0 &&
                       static_cast<int64_t>(row_start[b]) + lengths[b] <= total_rows &&
                       (b == 0 || row_start[b] >= row_start[b - 1] + lengths[b - 1]);
         }
-        if (ordered)
+        if (ordered && host)
             n_groups = (total_rows >= 16384 && n_videos >= 24) ? 6
                        : (total_rows >= 16384 && n_videos >= 12) ? 4 : ((total_rows >= 8192 && n_videos >= 6) ? 3 : 2);
+        if (ordered && !host) {
+            // device-resident inputs: nothing to hide a transfer behind, but the recurrence of the longest videos
+            // is a chain of dependent steps that leaves the tensor pipe idle -- the other groups' GEMMs run beside it
+            const char* e = getenv("AVS_DEV_GROUPS");
+            const int want = e ? atoi(e) : 1;
+            if (want >= 2 && want <= avs_model::MAX_CHUNKS && want != 5 && n_videos >= 8 * want) n_groups = want;
+        }
     }
     if (n_groups == 1) {
         if (scores_dev_out == nullptr)
@@ -636,12 +657,13 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
         Guard g1(m->device);
         cudaStream_t s1 = static_cast<cudaStream_t>(cuda_stream);
         const size_t r1 = static_cast<size_t>(total_rows);
-        AVS_TRY(m->host_in.reserve(r1 * (m->Dv + m->Da + 2) * 4 + 5 * 256));
-        m->host_in.reset();
-        float* v1 = m->host_in.take<float>(r1 * m->Dv);
-        float* a1 = m->host_in.take<float>(r1 * m->Da);
-        float* sc1 = m->host_in.take<float>(r1);
-        int32_t* p1 = m->host_in.take<int32_t>(r1);
+        Arena& HI = m->host_in[slot];
+        AVS_TRY(HI.reserve(r1 * (m->Dv + m->Da + 2) * 4 + 5 * 256));
+        HI.reset();
+        float* v1 = HI.take<float>(r1 * m->Dv);
+        float* a1 = HI.take<float>(r1 * m->Da);
+        float* sc1 = HI.take<float>(r1);
+        int32_t* p1 = HI.take<int32_t>(r1);
         AVS_CUDA(cudaMemcpyAsync(v1, visual, r1 * m->Dv * 4, cudaMemcpyHostToDevice, s1));
         AVS_CUDA(cudaMemcpyAsync(a1, audio, r1 * m->Da * 4, cudaMemcpyHostToDevice, s1));
         if (positions_host) AVS_CUDA(cudaMemcpyAsync(p1, positions_host, r1 * 4, cudaMemcpyHostToDevice, s1));
@@ -656,62 +678,99 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int Dv = m->Dv, Da = m->Da;
     const size_t uR = static_cast<size_t>(total_rows);
-    AVS_TRY(m->host_in.reserve(uR * (Dv + Da + 2) * 4 + 5 * 256));
-    m->host_in.reset();
-    float* in_v = m->host_in.take<float>(uR * Dv);
-    float* in_a = m->host_in.take<float>(uR * Da);
-    float* sc_dev = m->host_in.take<float>(uR);
-    int32_t* pos_dev = m->host_in.take<int32_t>(uR);
-    // group boundaries at video boundaries.  Shares shrink towards the end: what remains after the last byte has
-    // crossed PCIe is the last group's compute, so it should be the smallest (and, for a longest-first batch, the
-    // one with the shortest recurrence).
-    static const int kShare[7][6] = {{0}, {100}, {60, 100}, {45, 80, 100}, {40, 70, 90, 100}, {0}, {32, 58, 77, 89, 96, 100}};
+    const float* in_v = visual;
+    const float* in_a = audio;
+    float* sc_dev = scores;
+    int32_t* pos_dev = nullptr;
+    if (host) {
+        Arena& HI = m->host_in[slot];
+        AVS_TRY(HI.reserve(uR * (Dv + Da + 2) * 4 + 5 * 256));
+        HI.reset();
+        in_v = HI.take<float>(uR * Dv);
+        in_a = HI.take<float>(uR * Da);
+        sc_dev = HI.take<float>(uR);
+        pos_dev = HI.take<int32_t>(uR);
+    }
+    // group boundaries at video boundaries.  Host space: shares shrink towards the end -- what remains after the
+    // last byte has crossed PCIe is the last group's compute, so it should be the smallest (and, for a
+    // longest-first batch, the one with the shortest recurrence).  Device space: the first group holds the longest
+    // videos (the critical chain) and is kept small so that its recurrence starts early.
+    static const int kShareHost[7][6] = {{0}, {100}, {60, 100}, {45, 80, 100}, {40, 70, 90, 100}, {0}, {32, 58, 77, 89, 96, 100}};
+    static const int kShareDev[7][6] = {{0}, {100}, {30, 100}, {25, 60, 100}, {24, 48, 74, 100}, {0}, {24, 45, 62, 76, 88, 100}};
+    int share[6];
+    for (int i = 0; i < 6; ++i) share[i] = host ? kShareHost[n_groups][i] : kShareDev[n_groups][i];
+    if (const char* e = getenv(host ? "AVS_HOST_SHARES" : "AVS_DEV_SHARES")) {   // tuning aid: "24,48,74,100"
+        int v[6], k = 0;
+        for (const char* p = e; *p && k < 6;) {
+            v[k++] = atoi(p);
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+        if (k == n_groups && v[k - 1] == 100)
+            for (int i = 0; i < k; ++i) share[i] = v[i];
+    }
     int first[avs_model::MAX_CHUNKS + 1];
     first[0] = 0;
     for (int gi = 1; gi < n_groups; ++gi) {
-        const int64_t want = total_rows * kShare[n_groups][gi - 1] / 100;
+        const int64_t want = total_rows * share[gi - 1] / 100;
         int b = first[gi - 1] + 1;
-        while (b < n_videos - (n_groups - gi) && row_start[b] < want) ++b;
+        const int b_max = n_videos - (n_groups - gi);
+        while (b < b_max && row_start[b] < want) ++b;
+        // a cluster of the recurrence kernel carries up to 8 videos: groups of 8k videos waste no cluster slots
+        const int cnt = b - first[gi - 1];
+        if (cnt >= 6) {
+            const int snapped = first[gi - 1] + (cnt + 3) / 8 * 8;
+            if (snapped > first[gi - 1] && snapped <= b_max) b = snapped;
+        }
         first[gi] = b;
     }
     first[n_groups] = n_videos;
-    const bool trace = g_e2e.enabled();
+    const bool trace = host && g_e2e.enabled();
     if (trace) {
         g_e2e.n_groups = n_groups;
         cudaEventRecord(g_e2e.t0, st);
     }
-    AVS_CUDA(cudaEventRecord(m->ev_start, st));                 // staging is free once prior work on st is done
-    AVS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
-    if (positions_host)   // summary input, a few KB: goes first so it never waits behind the features
-        AVS_CUDA(cudaMemcpyAsync(pos_dev, positions_host, uR * 4, cudaMemcpyHostToDevice, m->copy_stream));
+    // Synchronous calls: the staging area is free once prior work on st is done.  Asynchronous calls own a staging
+    // slot whose previous user has completed (avs_slot_wait), so the copies start at once -- while the previous
+    // batch (other slot) is still being computed.
+    if (!async) AVS_CUDA(cudaEventRecord(m->ev_start, st));
     int64_t lo[avs_model::MAX_CHUNKS], hi[avs_model::MAX_CHUNKS];
     for (int gi = 0; gi < n_groups; ++gi) {
         lo[gi] = row_start[first[gi]];
         hi[gi] = static_cast<int64_t>(row_start[first[gi + 1] - 1]) + lengths[first[gi + 1] - 1];
-        const size_t rows = static_cast<size_t>(hi[gi] - lo[gi]);
-        if (rows) {
-            AVS_CUDA(cudaMemcpyAsync(in_v + lo[gi] * Dv, visual + lo[gi] * Dv, rows * Dv * 4, cudaMemcpyHostToDevice,
-                                     m->copy_stream));
-            AVS_CUDA(cudaMemcpyAsync(in_a + lo[gi] * Da, audio + lo[gi] * Da, rows * Da * 4, cudaMemcpyHostToDevice,
-                                     m->copy_stream));
+    }
+    if (host) {
+        if (!async) AVS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
+        if (positions_host)   // summary input, a few KB: goes first so it never waits behind the features
+            AVS_CUDA(cudaMemcpyAsync(pos_dev, positions_host, uR * 4, cudaMemcpyHostToDevice, m->copy_stream));
+        for (int gi = 0; gi < n_groups; ++gi) {
+            const size_t rows = static_cast<size_t>(hi[gi] - lo[gi]);
+            if (rows) {
+                AVS_CUDA(cudaMemcpyAsync(const_cast<float*>(in_v) + lo[gi] * Dv, visual + lo[gi] * Dv, rows * Dv * 4,
+                                         cudaMemcpyHostToDevice, m->copy_stream));
+                AVS_CUDA(cudaMemcpyAsync(const_cast<float*>(in_a) + lo[gi] * Da, audio + lo[gi] * Da, rows * Da * 4,
+                                         cudaMemcpyHostToDevice, m->copy_stream));
+            }
+            AVS_CUDA(cudaEventRecord(m->ev_chunk[gi], m->copy_stream));
+            if (trace) cudaEventRecord(g_e2e.chunk[gi], m->copy_stream);
         }
-        AVS_CUDA(cudaEventRecord(m->ev_chunk[gi], m->copy_stream));
-        if (trace) cudaEventRecord(g_e2e.chunk[gi], m->copy_stream);
     }
     if (trace) g_e2e.host[1] = E2ETrace::now();
     // every group on its own stream and workspace: the recurrence of group g (a chain of max(T_g) dependent steps
-    // that leaves most of the chip idle) keeps running while group g+1 starts
+    // that leaves the tensor pipe idle) keeps running while the other groups' GEMMs execute.  The groups share
+    // the GPU, so their recurrences do not ask for exclusive SMs -- except the first group of a device-space call,
+    // whose chain (the longest videos) is the critical path.
     std::vector<int32_t> rs;
     for (int gi = 0; gi < n_groups; ++gi) {
         const int nv = first[gi + 1] - first[gi];
         rs.assign(nv, 0);
         for (int b = 0; b < nv; ++b) rs[b] = row_start[first[gi] + b] - static_cast<int32_t>(lo[gi]);
         cudaStream_t gs = gi == 0 ? st : m->grp_stream[gi - 1];
-        if (gi > 0) AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_start, 0));   // not before earlier work on st is done
-        AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_chunk[gi], 0));
+        if (gi > 0 && !async) AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_start, 0));   // not before earlier work on st is done
+        if (host) AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_chunk[gi], 0));
         AVS_TRY(forward_impl(m, in_v + lo[gi] * Dv, in_a + lo[gi] * Da, hi[gi] - lo[gi], nv, rs.data(),
                              lengths + first[gi], attn_axis, precision, sc_dev + lo[gi], AVS_DEVICE, gs,
-                             gi == 0 ? nullptr : &m->ws_grp[gi - 1]));
+                             gi == 0 ? nullptr : &m->ws_grp[gi - 1], (!host && gi == 0) ? 0 : -1));
         if (trace) cudaEventRecord(g_e2e.grp[gi], gs);
         if (gi > 0) {
             AVS_CUDA(cudaEventRecord(m->ev_grp[gi - 1], gs));
@@ -719,6 +778,7 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
         }
     }
     if (trace) g_e2e.host[2] = E2ETrace::now();
+    if (!host) return AVS_OK;   // device space: the caller's stream now depends on every group
     if (scores_dev_out != nullptr) {   // the caller continues on the stream with the scores still on the device
         *scores_dev_out = sc_dev;
         if (positions_dev_out) *positions_dev_out = pos_dev;
@@ -738,7 +798,7 @@ avs_status avs_forward(avs_model* m, const float* visual, const float* audio, in
 
 static avs_status forward_impl(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
                                int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int attn_axis,
-                               int precision, float* scores, int space, void* cuda_stream, Arena* arena) {
+                               int precision, float* scores, int space, void* cuda_stream, Arena* arena, int lstm_excl) {
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
     Arena& WS = arena ? *arena : m->ws;
     AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
@@ -887,7 +947,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     // ---- K2b: recurrences; writes [v_fwd | v_bwd | a_fwd | a_bwd] = torch.cat of av_model.py:43
     {
         const int slots = plan.n_groups * plan.nb;
-        LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
+        LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb, lstm_excl};
         int64_t covered = 0;
         for (int b = 0; b < n_videos; ++b) covered += lengths[b];
         if (covered < R)  // padded layout: rows no video owns must stay finite (0 * NaN would poison P*V)
@@ -971,20 +1031,38 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     return AVS_OK;
 }
 
-static avs_status summarize_impl(avs_model* m, const float* scores, const int32_t* positions, int32_t n_videos,
-                                 const int32_t* row_start, const int32_t* lengths, const int32_t* n_frames,
-                                 const int32_t* cps, const int32_t* cps_start, int32_t prop_num, int32_t prop_den,
-                                 uint8_t* picks, int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start,
-                                 int in_space, int space, void* cuda_stream) {
+// Pooling + knapsack in two halves.  summarize_prepare validates the change points, lays the workspace out in the
+// slot's arena and uploads the descriptors (as kernel parameters: a pageable-memory copy would queue on the H2D
+// copy engine behind the feature transfers of a pipelined call); it does not depend on the scores, so callers
+// enqueue it BEFORE the forward and keep it off the critical tail.  summarize_run launches the kernels and, in
+// host space, the D2H copies.
+struct SummaryPlan {
+    SummaryBatch sb;
+    unsigned long long* seg_sum = nullptr;
+    long long* seg_mean_dev = nullptr;
+    uint32_t* keep = nullptr;
+    long long* dp_ws = nullptr;
+    float* sc_stage = nullptr;       // device copies of host-space scores / positions (avs_summarize in host space)
+    int32_t* pos_stage = nullptr;
+    uint8_t* picks_dev = nullptr;    // device staging of host-space outputs
+    uint8_t* summary_dev = nullptr;
+    int total_S = 0;
+    int64_t rows = 0, sum_bytes = 0;
+    bool fuse_pool = false;
+};
+
+static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, const int32_t* row_start,
+                                    const int32_t* lengths, const int32_t* n_frames, const int32_t* cps,
+                                    const int32_t* cps_start, int32_t prop_num, int32_t prop_den, bool want_summary,
+                                    const int64_t* summary_start, int in_space, int space, cudaStream_t st,
+                                    SummaryPlan* P) {
     // in_space: where scores / positions live; space: where picks / seg_mean / summary go
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
     AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
-    AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
-    if (n_videos == 0) return AVS_OK;
-    AVS_CHECK(scores && positions && row_start && lengths && n_frames && cps_start && picks, AVS_ERR_INVALID,
-              "a required pointer is null");
+    AVS_CHECK(n_videos > 0, AVS_ERR_INVALID, "n_videos must be positive");
+    AVS_CHECK(row_start && lengths && n_frames && cps_start, AVS_ERR_INVALID, "a required pointer is null");
     AVS_CHECK(prop_den > 0 && prop_num >= 0, AVS_ERR_INVALID, "bad proportion %d/%d", prop_num, prop_den);
-    AVS_CHECK(summary == nullptr || summary_start != nullptr, AVS_ERR_INVALID, "summary_start is null");
+    AVS_CHECK(!want_summary || summary_start != nullptr, AVS_ERR_INVALID, "summary_start is null");
     const int n = n_videos;
     AVS_CHECK(cps_start[0] == 0, AVS_ERR_INVALID, "cps_start[0] must be 0");
     const int total_S = cps_start[n];
@@ -1010,16 +1088,14 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
         const int S = cps_start[v + 1] - cps_start[v];
         off[v + 1] = off[v] + static_cast<int64_t>(S) * ((cap + 32) >> 5);
         off[n + 1 + v + 1] = off[n + 1 + v] + 2 * (cap + 1);
-        if (summary) AVS_CHECK(summary_start[v + 1] - summary_start[v] >= n_frames[v], AVS_ERR_INVALID,
-                               "summary_start leaves fewer than n_frames bytes for video %d", v);
+        if (want_summary) AVS_CHECK(summary_start[v + 1] - summary_start[v] >= n_frames[v], AVS_ERR_INVALID,
+                                    "summary_start leaves fewer than n_frames bytes for video %d", v);
     }
     const int64_t keep_words = off[n];
     const bool dp_global = 2ull * (static_cast<size_t>(max_cap) + 1) * 8 > 200 * 1024;
     const int64_t dp_elems = dp_global ? off[2 * n + 1] : 0;
-    const int64_t sum_bytes = summary ? summary_start[n] : 0;
+    const int64_t sum_bytes = want_summary ? summary_start[n] : 0;
 
-    Guard g(m->device);
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     // int32 descriptor block: row_start | lengths | n_frames | cps_start | cps
     std::vector<int32_t> desc;
     desc.insert(desc.end(), row_start, row_start + n);
@@ -1030,40 +1106,32 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
     const size_t cps_off = desc.size();
     desc.insert(desc.end(), cps, cps + 2 * static_cast<size_t>(total_S));
     std::vector<int64_t> off64(off);
-    if (summary) off64.insert(off64.end(), summary_start, summary_start + n + 1);
+    if (want_summary) off64.insert(off64.end(), summary_start, summary_start + n + 1);
 
     size_t need = desc.size() * 4 + off64.size() * 8 + static_cast<size_t>(total_S) * (8 + 8 + 1) +
                   static_cast<size_t>(keep_words) * 4 + static_cast<size_t>(dp_elems) * 8 + 64 * 256;
     if (in_space == AVS_HOST) need += static_cast<size_t>(rows) * 8 + 512;
     if (space == AVS_HOST) need += static_cast<size_t>(sum_bytes) + static_cast<size_t>(total_S) + 512;
-    AVS_TRY(m->ws.reserve(need));
-    m->ws.reset();
-    int64_t* off_dev = m->ws.take<int64_t>(off64.size());
-    int32_t* desc_dev = m->ws.take<int32_t>(desc.size());
-    unsigned long long* seg_sum = m->ws.take<unsigned long long>(std::max(total_S, 1));
-    long long* seg_mean_dev = m->ws.take<long long>(std::max(total_S, 1));
-    uint32_t* keep = m->ws.take<uint32_t>(std::max<int64_t>(keep_words, 1));
-    long long* dp_ws = m->ws.take<long long>(std::max<int64_t>(dp_elems, 1));
-    const float* sc = scores;
-    const int32_t* pos = positions;
-    uint8_t* picks_dev = picks;
-    uint8_t* summary_dev = summary;
+    AVS_TRY(A.reserve(need));
+    A.reset();
+    int64_t* off_dev = A.take<int64_t>(off64.size());
+    int32_t* desc_dev = A.take<int32_t>(desc.size());
+    P->seg_sum = A.take<unsigned long long>(std::max(total_S, 1));
+    P->seg_mean_dev = A.take<long long>(std::max(total_S, 1));
+    P->keep = A.take<uint32_t>(std::max<int64_t>(keep_words, 1));
+    P->dp_ws = A.take<long long>(std::max<int64_t>(dp_elems, 1));
     if (in_space == AVS_HOST) {
-        float* s2 = m->ws.take<float>(rows);
-        int32_t* p2 = m->ws.take<int32_t>(rows);
-        AVS_CUDA(cudaMemcpyAsync(s2, scores, rows * 4, cudaMemcpyHostToDevice, st));
-        AVS_CUDA(cudaMemcpyAsync(p2, positions, rows * 4, cudaMemcpyHostToDevice, st));
-        sc = s2;
-        pos = p2;
+        P->sc_stage = A.take<float>(rows);
+        P->pos_stage = A.take<int32_t>(rows);
     }
     if (space == AVS_HOST) {
-        picks_dev = m->ws.take<uint8_t>(std::max(total_S, 1));
-        if (summary) summary_dev = m->ws.take<uint8_t>(sum_bytes);
+        P->picks_dev = A.take<uint8_t>(std::max(total_S, 1));
+        if (want_summary) P->summary_dev = A.take<uint8_t>(sum_bytes);
     }
-    AVS_CUDA(cudaMemcpyAsync(off_dev, off64.data(), off64.size() * 8, cudaMemcpyHostToDevice, st));
-    AVS_CUDA(cudaMemcpyAsync(desc_dev, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st));
+    AVS_TRY(upload_small(off_dev, off64.data(), off64.size() * 8, st));
+    AVS_TRY(upload_small(desc_dev, desc.data(), desc.size() * 4, st));
 
-    SummaryBatch sb;
+    SummaryBatch& sb = P->sb;
     sb.row_start = desc_dev;
     sb.lengths = desc_dev + n;
     sb.n_frames = desc_dev + 2 * n;
@@ -1071,7 +1139,7 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
     sb.cps = desc_dev + cps_off;
     sb.keep_start = off_dev;
     sb.dp_start = off_dev + (n + 1);
-    sb.summary_start = summary ? off_dev + 2 * (n + 1) : nullptr;
+    sb.summary_start = want_summary ? off_dev + 2 * (n + 1) : nullptr;
     sb.n = n;
     sb.prop_num = prop_num;
     sb.prop_den = prop_den;
@@ -1079,32 +1147,55 @@ static avs_status summarize_impl(avs_model* m, const float* scores, const int32_
     sb.max_S = 0;
     for (int v = 0; v < n; ++v) sb.max_S = std::max(sb.max_S, cps_start[v + 1] - cps_start[v]);
     // K7 + K8 in one launch when every video's shots fit in shared memory (always, for TVSum/SumMe-sized inputs)
-    const bool fuse_pool = knapsack_can_fuse_pool(sb);
-    if (!fuse_pool) {
-        AVS_CUDA(cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(std::max(total_S, 1)) * 8, st));
-        StageTimer tm(ST_POOL, st);
-        AVS_TRY(shot_pool(sc, pos, sb, seg_sum, st));
+    P->fuse_pool = knapsack_can_fuse_pool(sb);
+    P->total_S = total_S;
+    P->rows = rows;
+    P->sum_bytes = sum_bytes;
+    return AVS_OK;
+}
+
+// sync: end with a stream synchronisation (host space); otherwise the caller records its own completion event
+static avs_status summarize_run(const SummaryPlan& P, const float* scores, const int32_t* positions, uint8_t* picks,
+                                int64_t* seg_mean, uint8_t* summary, int in_space, int space, cudaStream_t st,
+                                bool sync) {
+    AVS_CHECK(scores && positions && picks, AVS_ERR_INVALID, "a required pointer is null");
+    const float* sc = scores;
+    const int32_t* pos = positions;
+    if (in_space == AVS_HOST) {
+        AVS_CUDA(cudaMemcpyAsync(P.sc_stage, scores, P.rows * 4, cudaMemcpyHostToDevice, st));
+        AVS_CUDA(cudaMemcpyAsync(P.pos_stage, positions, P.rows * 4, cudaMemcpyHostToDevice, st));
+        sc = P.sc_stage;
+        pos = P.pos_stage;
     }
-    long long* seg_mean_target = space == AVS_HOST ? (seg_mean ? seg_mean_dev : nullptr)
+    uint8_t* picks_dev = space == AVS_HOST ? P.picks_dev : picks;
+    uint8_t* summary_dev = space == AVS_HOST ? (summary ? P.summary_dev : nullptr) : summary;
+    if (!P.fuse_pool) {
+        AVS_CUDA(cudaMemsetAsync(P.seg_sum, 0, static_cast<size_t>(std::max(P.total_S, 1)) * 8, st));
+        StageTimer tm(ST_POOL, st);
+        AVS_TRY(shot_pool(sc, pos, P.sb, P.seg_sum, st));
+    }
+    long long* seg_mean_target = space == AVS_HOST ? (seg_mean ? P.seg_mean_dev : nullptr)
                                                     : reinterpret_cast<long long*>(seg_mean);
     {
         StageTimer tm(ST_KNAPSACK, st);
-        AVS_TRY(knapsack_select(sb, seg_sum, seg_mean_target, picks_dev, summary_dev, keep, dp_ws, st,
-                                fuse_pool ? sc : nullptr, pos));
+        AVS_TRY(knapsack_select(P.sb, P.seg_sum, seg_mean_target, picks_dev, summary_dev, P.keep, P.dp_ws, st,
+                                P.fuse_pool ? sc : nullptr, pos));
     }
     const bool trace = g_e2e.enabled() && space == AVS_HOST;
     if (trace) cudaEventRecord(g_e2e.knap, st);
     if (space == AVS_HOST) {
-        AVS_CUDA(cudaMemcpyAsync(picks, picks_dev, total_S, cudaMemcpyDeviceToHost, st));
-        if (seg_mean) AVS_CUDA(cudaMemcpyAsync(seg_mean, seg_mean_dev, static_cast<size_t>(total_S) * 8,
+        AVS_CUDA(cudaMemcpyAsync(picks, picks_dev, P.total_S, cudaMemcpyDeviceToHost, st));
+        if (seg_mean) AVS_CUDA(cudaMemcpyAsync(seg_mean, P.seg_mean_dev, static_cast<size_t>(P.total_S) * 8,
                                                cudaMemcpyDeviceToHost, st));
-        if (summary) AVS_CUDA(cudaMemcpyAsync(summary, summary_dev, sum_bytes, cudaMemcpyDeviceToHost, st));
+        if (summary) AVS_CUDA(cudaMemcpyAsync(summary, summary_dev, P.sum_bytes, cudaMemcpyDeviceToHost, st));
         if (trace) {
             cudaEventRecord(g_e2e.end, st);
             g_e2e.host[3] = E2ETrace::now();
         }
-        AVS_CUDA(cudaStreamSynchronize(st));
-        if (trace) g_e2e.host[4] = E2ETrace::now();
+        if (sync) {
+            AVS_CUDA(cudaStreamSynchronize(st));
+            if (trace) g_e2e.host[4] = E2ETrace::now();
+        }
     }
     return AVS_OK;
 }
@@ -1114,8 +1205,71 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
                          const int32_t* cps_start, int32_t prop_num, int32_t prop_den, uint8_t* picks,
                          int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start, int space,
                          void* cuda_stream) {
-    return summarize_impl(m, scores, positions, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
-                          prop_den, picks, seg_mean, summary, summary_start, space, space, cuda_stream);
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
+    if (n_videos == 0) return AVS_OK;
+    AVS_CHECK(!m->slot_busy[0], AVS_ERR_INVALID, "slot 0 is in flight: call avs_slot_wait first");
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    SummaryPlan P;
+    AVS_TRY(summarize_prepare(m, m->sum_ws[0], n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
+                              prop_den, summary != nullptr, summary_start, space, space, st, &P));
+    return summarize_run(P, scores, positions, picks, seg_mean, summary, space, space, st, true);
+}
+
+static avs_status forward_summarize_impl(avs_model* m, const float* visual, const float* audio,
+                                         const int32_t* positions, int64_t total_rows, int32_t n_videos,
+                                         const int32_t* row_start, const int32_t* lengths, int attn_axis,
+                                         int precision, const int32_t* n_frames, const int32_t* cps,
+                                         const int32_t* cps_start, int32_t prop_num, int32_t prop_den, float* scores,
+                                         uint8_t* picks, int64_t* seg_mean, uint8_t* summary,
+                                         const int64_t* summary_start, int space, void* cuda_stream, int slot,
+                                         bool async) {
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
+    AVS_CHECK(positions != nullptr && scores != nullptr, AVS_ERR_INVALID, "positions / scores pointer is null");
+    AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
+    AVS_CHECK(slot >= 0 && slot < avs_model::SLOTS, AVS_ERR_INVALID, "bad slot %d", slot);
+    AVS_CHECK(!m->slot_busy[slot], AVS_ERR_INVALID, "slot %d is in flight: call avs_slot_wait first", slot);
+    AVS_CHECK(!async || space == AVS_HOST, AVS_ERR_INVALID, "the asynchronous call is for host-space (pinned) buffers");
+    Guard g(m->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (g_e2e.enabled() && space == AVS_HOST) g_e2e.host[0] = E2ETrace::now();
+    int max_len = 0;
+    AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
+    SummaryPlan P;
+    if (n_videos > 0)   // descriptors first: they do not depend on the scores and stay off the critical tail
+        AVS_TRY(summarize_prepare(m, m->sum_ws[slot], n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
+                                  prop_den, summary != nullptr, summary_start, AVS_DEVICE, space, st, &P));
+    if (space == AVS_DEVICE) {
+        AVS_TRY(forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, scores,
+                              AVS_DEVICE, cuda_stream, nullptr, nullptr, nullptr));
+        if (n_videos == 0) return AVS_OK;
+        return summarize_run(P, scores, positions, picks, seg_mean, summary, AVS_DEVICE, AVS_DEVICE, st, true);
+    }
+    // host space: features in, scores stay on the device for pooling + knapsack, everything comes back with ONE
+    // synchronisation at the end (no D2H -> H2D round trip of the scores between the two halves)
+    if (n_videos == 0) return AVS_OK;
+    float* sc_dev = nullptr;
+    int32_t* pos_dev = nullptr;
+    if (total_rows == 0 || max_len == 0) {   // nothing to score: every shot pools to zero
+        Arena& HI = m->host_in[slot];
+        AVS_TRY(HI.reserve(1024));
+        HI.reset();
+        sc_dev = HI.take<float>(1);
+        pos_dev = HI.take<int32_t>(1);
+    } else {
+        AVS_TRY(forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, nullptr,
+                              AVS_HOST, cuda_stream, &sc_dev, positions, &pos_dev, slot, async));
+        AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[0], 0));   // positions travelled on the copy stream (grouped path)
+        AVS_CUDA(cudaMemcpyAsync(scores, sc_dev, static_cast<size_t>(total_rows) * 4, cudaMemcpyDeviceToHost, st));
+    }
+    AVS_TRY(summarize_run(P, sc_dev, pos_dev, picks, seg_mean, summary, AVS_DEVICE, AVS_HOST, st, !async));
+    if (async) {
+        AVS_CUDA(cudaEventRecord(m->ev_slot[slot], st));
+        m->slot_busy[slot] = true;
+    }
+    return AVS_OK;
 }
 
 avs_status avs_forward_summarize(avs_model* m, const float* visual, const float* audio, const int32_t* positions,
@@ -1124,33 +1278,31 @@ avs_status avs_forward_summarize(avs_model* m, const float* visual, const float*
                                  const int32_t* cps, const int32_t* cps_start, int32_t prop_num, int32_t prop_den,
                                  float* scores, uint8_t* picks, int64_t* seg_mean, uint8_t* summary,
                                  const int64_t* summary_start, int space, void* cuda_stream) {
+    return forward_summarize_impl(m, visual, audio, positions, total_rows, n_videos, row_start, lengths, attn_axis,
+                                  precision, n_frames, cps, cps_start, prop_num, prop_den, scores, picks, seg_mean,
+                                  summary, summary_start, space, cuda_stream, 0, false);
+}
+
+avs_status avs_forward_summarize_async(avs_model* m, const float* visual, const float* audio,
+                                       const int32_t* positions, int64_t total_rows, int32_t n_videos,
+                                       const int32_t* row_start, const int32_t* lengths, int attn_axis, int precision,
+                                       const int32_t* n_frames, const int32_t* cps, const int32_t* cps_start,
+                                       int32_t prop_num, int32_t prop_den, float* scores, uint8_t* picks,
+                                       int64_t* seg_mean, uint8_t* summary, const int64_t* summary_start, int slot,
+                                       void* cuda_stream) {
+    return forward_summarize_impl(m, visual, audio, positions, total_rows, n_videos, row_start, lengths, attn_axis,
+                                  precision, n_frames, cps, cps_start, prop_num, prop_den, scores, picks, seg_mean,
+                                  summary, summary_start, AVS_HOST, cuda_stream, slot, true);
+}
+
+avs_status avs_slot_wait(avs_model* m, int slot) {
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
-    AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
-    AVS_CHECK(positions != nullptr && scores != nullptr, AVS_ERR_INVALID, "positions / scores pointer is null");
-    if (space == AVS_DEVICE) {
-        AVS_TRY(forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, scores,
-                              AVS_DEVICE, cuda_stream, nullptr, nullptr, nullptr));
-        return summarize_impl(m, scores, positions, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
-                              prop_den, picks, seg_mean, summary, summary_start, AVS_DEVICE, AVS_DEVICE, cuda_stream);
-    }
-    // host space: features in, scores stay on the device for pooling + knapsack, everything comes back with ONE
-    // synchronisation at the end (no D2H -> H2D round trip of the scores between the two halves)
-    if (g_e2e.enabled()) g_e2e.host[0] = E2ETrace::now();
-    int max_len = 0;
-    AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
-    if (total_rows == 0 || n_videos == 0 || max_len == 0)
-        return summarize_impl(m, scores, positions, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
-                              prop_den, picks, seg_mean, summary, summary_start, AVS_HOST, AVS_HOST, cuda_stream);
-    float* sc_dev = nullptr;
-    int32_t* pos_dev = nullptr;
-    AVS_TRY(forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, nullptr,
-                          AVS_HOST, cuda_stream, &sc_dev, positions, &pos_dev));
+    AVS_CHECK(slot >= 0 && slot < avs_model::SLOTS, AVS_ERR_INVALID, "bad slot %d", slot);
+    if (!m->slot_busy[slot]) return AVS_OK;
     Guard g(m->device);
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[0], 0));   // positions travelled on the copy stream (grouped path)
-    AVS_CUDA(cudaMemcpyAsync(scores, sc_dev, static_cast<size_t>(total_rows) * 4, cudaMemcpyDeviceToHost, st));
-    return summarize_impl(m, sc_dev, pos_dev, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num, prop_den,
-                          picks, seg_mean, summary, summary_start, AVS_DEVICE, AVS_HOST, cuda_stream);
+    AVS_CUDA(cudaEventSynchronize(m->ev_slot[slot]));
+    m->slot_busy[slot] = false;
+    return AVS_OK;
 }
 
 avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t M, int32_t N, int32_t K, int relu,

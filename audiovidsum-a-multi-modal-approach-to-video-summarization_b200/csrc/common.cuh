@@ -99,6 +99,8 @@ struct LstmBatch {            // device arrays, one entry per slot (n_groups * N
     const int32_t* group_maxlen;  // [n_groups]
     int n_groups;
     int nb;                       // videos per cluster (1, 2, 4, 8, 16)
+    int excl = 0;                 // tensor-core kernel, 8-slot variant: 0 = launch policy decides which groups get
+                                  // exclusive SMs, -1 = none (the call shares the GPU with other video groups)
 };
 // xg_v, xg_a: [rows, 2048] gate pre-activations (biases included) in the packed column order
 //   col = dir * 1024 + cta * 128 + jj * 4 + gate   (hidden unit j = cta * 32 + jj)

@@ -511,7 +511,7 @@ avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, con
     // do, and n = 7 with A = 1 does -- hence the table (one GPC of slack whenever A >= 2).
     SplitCtx& sc = split_ctx();
     int n_excl = 0;
-    if (PARTS == 2 && !no_split) {
+    if (PARTS == 2 && !no_split && batch.excl >= 0) {
         static const int kExclusive[8] = {0, 1, 2, 3, 3, 2, 1, 1};
         n_excl = batch.n_groups <= 7 ? kExclusive[batch.n_groups] : 0;
         if (n_excl < batch.n_groups && !sc.ok) n_excl = 0;

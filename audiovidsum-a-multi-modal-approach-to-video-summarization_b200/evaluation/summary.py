@@ -69,3 +69,32 @@ def summarize_videos(model, videos, proportion=0.15, attn_axis: Optional[str] = 
         out.append(VideoSummary(scores_h[starts[i]:starts[i] + lens[i]], picks_h[cps_start[i]:cps_start[i + 1]],
                                 mean_h[cps_start[i]:cps_start[i + 1]], sum_h[sum_start[i]:sum_start[i + 1]]))
     return out
+
+
+@torch.no_grad()
+def summarize_stream(model, batches, proportion=0.15, attn_axis: Optional[str] = None, depth: int = 2):
+    """Score + pool + select a STREAM of packed host batches, two in flight (the ``scripts/evaluate.py:12-18`` loop
+    over a whole dataset): while batch i is being computed the features of batch i+1 already cross PCIe
+    (``avs_forward_summarize_async``, one device staging slot per batch in flight), so the steady-state cost of a
+    batch is its H2D transfer.
+
+    ``batches`` yields tuples ``(visual, audio, positions, row_start, lengths, shots)`` of pinned host tensors /
+    descriptor arrays, ``shots`` being a ``runtime.ShotDesc``.  Yields, in order, what
+    ``NativeModel.score_and_summarize_rows`` returns for each batch.
+    """
+    if depth not in (1, 2):
+        raise ValueError("depth must be 1 or 2 (the library has two staging slots)")
+    nat = model.native()
+    axis = attn_axis or ("literal_b1" if model.attn_axis == "literal" else model.attn_axis)
+    if axis == "literal":
+        raise ValueError("literal attention mixes the videos of a batch and cannot be pipelined; use literal_b1 / temporal")
+    pending = []
+    slot = 0
+    for visual, audio, positions, row_start, lengths, shots in batches:
+        if len(pending) == depth:
+            yield pending.pop(0).wait()
+        pending.append(nat.score_and_summarize_rows(visual, audio, positions, row_start, lengths, None, shots,
+                                                    proportion, axis, model.precision, slot=slot))
+        slot = (slot + 1) % 2 if depth == 2 else 0
+    while pending:
+        yield pending.pop(0).wait()

@@ -30,6 +30,57 @@ def _i32(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 
 
+class ShotDesc:
+    """Host descriptors of the shots of a batch, packed once (by the loader) instead of on every call:
+    ``n_frames`` int32 [n], ``cps`` int32 [sum S, 2] (inclusive change points), ``cps_start`` int32 [n + 1],
+    ``summary_start`` int64 [n + 1]."""
+
+    __slots__ = ("n_frames", "cps", "cps_start", "summary_start")
+
+    def __init__(self, n_frames, cps_list):
+        self.n_frames = _i32(n_frames)
+        n = int(self.n_frames.size)
+        if len(cps_list) != n:
+            raise ValueError("one change-point array per video expected")
+        arrs = [np.asarray(c, dtype=np.int32).reshape(-1, 2) for c in cps_list]
+        self.cps_start = np.zeros(n + 1, dtype=np.int32)
+        if n:
+            np.cumsum([a.shape[0] for a in arrs], out=self.cps_start[1:])
+        self.cps = _i32(np.concatenate(arrs, axis=0) if n else np.zeros((0, 2), np.int32))
+        self.summary_start = np.zeros(n + 1, dtype=np.int64)
+        self.summary_start[1:] = np.cumsum(self.n_frames.astype(np.int64))
+
+
+def _shots(n_frames, cps_list) -> ShotDesc:
+    return cps_list if isinstance(cps_list, ShotDesc) else ShotDesc(n_frames, cps_list)
+
+
+_FRACTIONS = {}
+
+
+def _fraction(proportion) -> Fraction:
+    f = _FRACTIONS.get(proportion)
+    if f is None:
+        f = Fraction(*proportion) if isinstance(proportion, tuple) else Fraction(proportion).limit_denominator(10000)
+        _FRACTIONS[proportion] = f
+    return f
+
+
+class PendingSummary:
+    """An asynchronous score_and_summarize_rows step in flight on one of the model's two staging slots."""
+
+    def __init__(self, model, slot, outputs, keep):
+        self._model, self.slot, self._outputs, self._keep = model, slot, outputs, keep
+
+    def wait(self):
+        """Block until the step has completed; returns what score_and_summarize_rows returns."""
+        if self._model is not None:
+            with torch.cuda.device(self._model.device):
+                _cabi.check(self._model.lib.avs_slot_wait(self._model._handle, self.slot))
+            self._model, self._keep = None, None
+        return self._outputs
+
+
 class NativeModel:
     """Owns one ``avs_model`` handle built from a reference-format state_dict."""
 
@@ -126,17 +177,14 @@ class NativeModel:
         """Batched shot pooling + knapsack.  Returns (picks uint8[sum S], seg_mean int64[sum S],
         summary uint8[sum n_frames] | None, cps_start, summary_start) as torch tensors in the
         memory space of ``scores``."""
-        frac = Fraction(proportion).limit_denominator(10000) if not isinstance(proportion, tuple) else Fraction(*proportion)
-        rs, ln, nf = _i32(row_start), _i32(lengths), _i32(n_frames)
+        frac = _fraction(proportion)
+        rs, ln = _i32(row_start), _i32(lengths)
         n = int(rs.size)
-        cps_start = np.zeros(n + 1, dtype=np.int32)
-        for i, c in enumerate(cps_list):
-            cps_start[i + 1] = cps_start[i] + int(np.asarray(c).reshape(-1, 2).shape[0])
-        cps = _i32(np.concatenate([np.asarray(c, dtype=np.int32).reshape(-1, 2) for c in cps_list], axis=0)
-                   if n else np.zeros((0, 2), np.int32))
+        sd = _shots(n_frames, cps_list)
+        nf, cps, cps_start, summary_start = sd.n_frames, sd.cps, sd.cps_start, sd.summary_start
+        if int(nf.size) != n:
+            raise ValueError("n_frames / change points do not match the number of videos")
         total_S = int(cps_start[-1])
-        summary_start = np.zeros(n + 1, dtype=np.int64)
-        summary_start[1:] = np.cumsum(nf.astype(np.int64))
         on_gpu = scores.is_cuda
         dev = scores.device
         scores = scores.to(torch.float32).contiguous()
@@ -159,12 +207,17 @@ class NativeModel:
     # -- forward + summary in one native call -----------------------------------------------
     def score_and_summarize_rows(self, visual: torch.Tensor, audio: torch.Tensor, positions: torch.Tensor, row_start,
                                  lengths, n_frames, cps_list, proportion=0.15, attn_axis: str = "literal_b1",
-                                 precision: str = "tf32", want_summary: bool = True):
+                                 precision: str = "tf32", want_summary: bool = True, slot: Optional[int] = None):
         """avs_forward_summarize: the whole "scored + summarised" step.  All tensors on the model's GPU, or all on
         the host (pinned recommended): then the features are pipelined across PCIe by video group, the scores
         never leave the device between the two halves and the call returns after one synchronisation.
+        ``cps_list`` may be a ShotDesc packed once by the loader (``n_frames`` is then ignored).
         Returns (scores fp32 [R], picks uint8 [sum S], seg_mean int64 [sum S], summary uint8 | None, cps_start,
-        summary_start)."""
+        summary_start).
+
+        ``slot`` (0 or 1, pinned host tensors only) makes the call asynchronous (avs_forward_summarize_async): it
+        returns a PendingSummary at once and the next batch can be submitted on the other slot, so that its
+        features cross PCIe while this batch is still being computed; ``.wait()`` returns the tuple above."""
         vd, ad, _, _ = self.dims
         if visual.dim() != 2 or audio.dim() != 2 or visual.shape[1] != vd or audio.shape[1] != ad:
             raise ValueError(f"expected visual [R, {vd}] and audio [R, {ad}], got {tuple(visual.shape)} / {tuple(audio.shape)}")
@@ -174,23 +227,34 @@ class NativeModel:
         visual = visual.to(torch.float32).contiguous()
         audio = audio.to(torch.float32).contiguous()
         positions = positions.to(torch.int32).contiguous()
-        frac = Fraction(proportion).limit_denominator(10000) if not isinstance(proportion, tuple) else Fraction(*proportion)
-        rs, ln, nf = _i32(row_start), _i32(lengths), _i32(n_frames)
+        frac = _fraction(proportion)
+        rs, ln = _i32(row_start), _i32(lengths)
         n = int(rs.size)
-        cps_start = np.zeros(n + 1, dtype=np.int32)
-        for i, c in enumerate(cps_list):
-            cps_start[i + 1] = cps_start[i] + int(np.asarray(c).reshape(-1, 2).shape[0])
-        cps = _i32(np.concatenate([np.asarray(c, dtype=np.int32).reshape(-1, 2) for c in cps_list], axis=0)
-                   if n else np.zeros((0, 2), np.int32))
+        sd = _shots(n_frames, cps_list)
+        nf, cps, cps_start, summary_start = sd.n_frames, sd.cps, sd.cps_start, sd.summary_start
+        if int(nf.size) != n:
+            raise ValueError("n_frames / change points do not match the number of videos")
         total_S = int(cps_start[-1])
-        summary_start = np.zeros(n + 1, dtype=np.int64)
-        summary_start[1:] = np.cumsum(nf.astype(np.int64))
         on_gpu = visual.is_cuda
         dev, pin = visual.device, not on_gpu
         scores = torch.empty(R, dtype=torch.float32, device=dev, pin_memory=pin)
         picks = torch.empty(total_S, dtype=torch.uint8, device=dev, pin_memory=pin)
         seg_mean = torch.empty(total_S, dtype=torch.int64, device=dev, pin_memory=pin)
         summary = torch.empty(int(summary_start[-1]), dtype=torch.uint8, device=dev, pin_memory=pin) if want_summary else None
+        outputs = (scores, picks, seg_mean, summary, cps_start, summary_start)
+        if slot is not None:
+            if on_gpu or not (visual.is_pinned() and audio.is_pinned() and positions.is_pinned()):
+                raise ValueError("asynchronous steps need pinned host tensors")
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.avs_forward_summarize_async(
+                    self._handle, C.c_void_p(visual.data_ptr()), C.c_void_p(audio.data_ptr()),
+                    C.c_void_p(positions.data_ptr()), R, n, _cabi.np_ptr(rs), _cabi.np_ptr(ln),
+                    _cabi.ATTN_AXES[attn_axis], _cabi.PRECISIONS[precision], _cabi.np_ptr(nf), _cabi.np_ptr(cps),
+                    _cabi.np_ptr(cps_start), int(frac.numerator), int(frac.denominator),
+                    C.c_void_p(scores.data_ptr()), C.c_void_p(picks.data_ptr()), C.c_void_p(seg_mean.data_ptr()),
+                    C.c_void_p(summary.data_ptr()) if want_summary else None,
+                    _cabi.np_ptr(summary_start) if want_summary else None, int(slot), _stream_ptr(self.device)))
+            return PendingSummary(self, int(slot), outputs, (visual, audio, positions))
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.avs_forward_summarize(
                 self._handle, C.c_void_p(visual.data_ptr()), C.c_void_p(audio.data_ptr()), C.c_void_p(positions.data_ptr()),
@@ -200,7 +264,7 @@ class NativeModel:
                 C.c_void_p(summary.data_ptr()) if want_summary else None,
                 _cabi.np_ptr(summary_start) if want_summary else None,
                 _cabi.AVS_DEVICE if on_gpu else _cabi.AVS_HOST, _stream_ptr(self.device)))
-        return scores, picks, seg_mean, summary, cps_start, summary_start
+        return outputs
 
 
 # ---- stateless building blocks (device tensors) ------------------------------------

@@ -125,6 +125,21 @@ avs_status avs_forward_summarize(avs_model* m, const float* visual, const float*
                                  float* scores, uint8_t* picks, int64_t* seg_mean, uint8_t* summary,
                                  const int64_t* summary_start, int space, void* cuda_stream);
 
+/* Streaming form of avs_forward_summarize for HOST-space (pinned) buffers -- the scripts/evaluate.py:12-18 loop over
+ * many batches: the call enqueues the whole step on `cuda_stream` and returns WITHOUT synchronising, so the
+ * features of batch i+1 cross PCIe while batch i is still being computed.  `slot` (0 or 1) selects one of two
+ * device staging areas; a slot may be reused only after avs_slot_wait(m, slot) has returned, which is also when
+ * the slot's output buffers are valid.  The input buffers must stay untouched until then. */
+avs_status avs_forward_summarize_async(avs_model* m, const float* visual, const float* audio,
+                                       const int32_t* positions, int64_t total_rows, int32_t n_videos,
+                                       const int32_t* row_start, const int32_t* lengths, int attn_axis,
+                                       int precision, const int32_t* n_frames, const int32_t* cps,
+                                       const int32_t* cps_start, int32_t prop_num, int32_t prop_den, float* scores,
+                                       uint8_t* picks, int64_t* seg_mean, uint8_t* summary,
+                                       const int64_t* summary_start, int slot, void* cuda_stream);
+/* Block until the asynchronous step that used `slot` has completed (no-op for an idle slot). */
+avs_status avs_slot_wait(avs_model* m, int slot);
+
 /* ---- building blocks (device pointers only), exported so each kernel can be parity-tested
  * against the reference sub-module it replaces and reused by
  * models/attention.py's drop-in. ---- */

@@ -727,3 +727,36 @@ def test_forward_many_short_videos_all_lstm_variants(cuda_ready, n_videos):
         assert torch.equal(got[i], alone), i
         want = av_oracle_torch.run_videos(port, [(vis[i], aud[i])], "temporal")[0]
         assert rel(got[i].cpu().numpy(), want.numpy()) < 1e-3, i
+
+
+def test_streamed_batches_equal_synchronous_calls(cuda_ready):
+    """avs_forward_summarize_async (two batches in flight on the two staging slots, evaluation.summary.
+    summarize_stream) returns, batch by batch, exactly what the synchronous call returns -- including when the
+    batches differ in size (arena growth while the other slot is in flight) and when a slot is reused."""
+    from avsum_b200.evaluation.summary import summarize_stream
+    from avsum_b200.runtime import ShotDesc
+    model = make_model(spread=True, attn_axis="literal_b1")
+    nat = model.native()
+    vids = sorted(synth.config2(), key=lambda v: -v.T)
+    subsets = [vids[10:22], vids[0:50], vids[30:50], vids[0:50], vids[5:9], vids[20:45]]
+    batches = []
+    for sub in subsets:
+        lens = [v.T for v in sub]
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+        batches.append((torch.cat([v.visual for v in sub]).pin_memory(), torch.cat([v.audio for v in sub]).pin_memory(),
+                        torch.from_numpy(np.concatenate([v.positions for v in sub]).astype(np.int32)).pin_memory(),
+                        starts, lens, ShotDesc([v.n_frames for v in sub], [v.cps for v in sub])))
+    want = [nat.score_and_summarize_rows(b[0], b[1], b[2], b[3], b[4], None, b[5], 0.15, "literal_b1") for b in batches]
+    for depth in (2, 1):
+        got = list(summarize_stream(model, iter(batches), 0.15, depth=depth))
+        assert len(got) == len(want)
+        for k, (g, w) in enumerate(zip(got, want)):
+            for a, b in zip(g[:4], w[:4]):
+                assert torch.equal(a, b), (depth, k)
+    # protocol: a busy slot is refused until it has been waited for
+    b = batches[0]
+    p = nat.score_and_summarize_rows(b[0], b[1], b[2], b[3], b[4], None, b[5], 0.15, "literal_b1", slot=0)
+    with pytest.raises(ValueError):
+        nat.score_and_summarize_rows(b[0], b[1], b[2], b[3], b[4], None, b[5], 0.15, "literal_b1", slot=0)
+    out = p.wait()
+    assert torch.equal(out[1], want[0][1])
