@@ -205,7 +205,18 @@ struct avs_model {
     // workspace; two slots so that avs_forward_summarize_async can stream batch i+1 while batch i finishes
     static constexpr int SLOTS = 2;
     Arena host_in[SLOTS];
-    Arena sum_ws[SLOTS];
+    // pooling / knapsack workspaces: [0], [1] belong to the asynchronous slots, [2], [3] alternate between the
+    // other calls.  `done` marks the end of an arena's last user, so the descriptor uploads of the next user can
+    // run on the side stream while the caller's stream is still busy with the forward.
+    struct SumArena {
+        Arena a;
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    };
+    SumArena sum_ws[SLOTS + 2];
+    int sum_flip = 0;
+    cudaStream_t sum_stream = nullptr;  // side stream of the summary descriptor uploads
+    cudaEvent_t ev_sum_out = nullptr;
     cudaEvent_t ev_slot[SLOTS] = {};   // recorded at the end of an asynchronous step
     bool slot_busy[SLOTS] = {};
     Arena ws_grp[5];                 // activations of groups 1..5 (group 0 uses ws): the groups run concurrently
@@ -392,7 +403,11 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
             if (((B + nb - 1) / nb) * 4 <= 16) { p.nb = nb; break; }
         }
     }
-    p.n_groups = (B + p.nb - 1) / p.nb;
+    // The 8-slot kernel runs two independent chains of 4 videos per CTA; an isolated chain is faster (0.67 vs 0.76
+    // us per step, tools/lstm_scaling.py).  A small batch therefore takes 4 videos per cluster -- the second chain of
+    // every CTA stays empty -- as long as all clusters still get SMs of their own (16 videos -> 16 clusters).
+    const int per_cluster = (tensor_core && p.nb == 8 && B <= 16) ? 4 : p.nb;
+    p.n_groups = (B + per_cluster - 1) / per_cluster;
     const int slots = p.n_groups * p.nb;
     p.host.assign(2 * slots + p.n_groups, 0);
     const int base = B / p.n_groups, rem = B % p.n_groups;
@@ -562,6 +577,10 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
         }
         for (int i = 0; i < avs_model::SLOTS && ce == cudaSuccess; ++i)
             ce = cudaEventCreateWithFlags(&m->ev_slot[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&m->sum_stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_sum_out, cudaEventDisableTiming);
+        for (int i = 0; i < avs_model::SLOTS + 2 && ce == cudaSuccess; ++i)
+            ce = cudaEventCreateWithFlags(&m->sum_ws[i].done, cudaEventDisableTiming);
         if (ce != cudaSuccess) {
             set_error("creating the copy stream / events failed: %s", cudaGetErrorString(ce));
             s = AVS_ERR_CUDA;
@@ -593,7 +612,6 @@ void avs_model_destroy(avs_model* m) {
     m->staging.release();
     for (int i = 0; i < avs_model::SLOTS; ++i) {
         m->host_in[i].release();
-        m->sum_ws[i].release();
         if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
     }
     for (int i = 0; i < 5; ++i) {
@@ -602,6 +620,12 @@ void avs_model_destroy(avs_model* m) {
         if (m->ev_grp[i]) cudaEventDestroy(m->ev_grp[i]);
     }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->sum_stream) cudaStreamDestroy(m->sum_stream);
+    if (m->ev_sum_out) cudaEventDestroy(m->ev_sum_out);
+    for (int i = 0; i < avs_model::SLOTS + 2; ++i) {
+        m->sum_ws[i].a.release();
+        if (m->sum_ws[i].done) cudaEventDestroy(m->sum_ws[i].done);
+    }
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     for (cudaEvent_t e : m->ev_chunk)
         if (e) cudaEventDestroy(e);
@@ -1031,11 +1055,11 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     return AVS_OK;
 }
 
-// Pooling + knapsack in two halves.  summarize_prepare validates the change points, lays the workspace out in the
-// slot's arena and uploads the descriptors (as kernel parameters: a pageable-memory copy would queue on the H2D
-// copy engine behind the feature transfers of a pipelined call); it does not depend on the scores, so callers
-// enqueue it BEFORE the forward and keep it off the critical tail.  summarize_run launches the kernels and, in
-// host space, the D2H copies.
+// Pooling + knapsack in three steps.  summarize_prepare (host only) validates the change points and lays the
+// workspace out in the slot's arena; summarize_upload sends the descriptors as kernel parameters (a pageable-memory
+// copy would queue on the H2D copy engine behind the feature transfers of a pipelined call) -- it does not depend
+// on the scores, so the fused call runs it on a side stream, off the critical path; summarize_run launches the
+// kernels and, in host space, the D2H copies.
 struct SummaryPlan {
     SummaryBatch sb;
     unsigned long long* seg_sum = nullptr;
@@ -1049,13 +1073,17 @@ struct SummaryPlan {
     int total_S = 0;
     int64_t rows = 0, sum_bytes = 0;
     bool fuse_pool = false;
+    // host copies of the descriptors until summarize_upload has sent them
+    std::vector<int32_t> desc;
+    std::vector<int64_t> off64;
+    int32_t* desc_dev = nullptr;
+    int64_t* off_dev = nullptr;
 };
 
 static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, const int32_t* row_start,
                                     const int32_t* lengths, const int32_t* n_frames, const int32_t* cps,
                                     const int32_t* cps_start, int32_t prop_num, int32_t prop_den, bool want_summary,
-                                    const int64_t* summary_start, int in_space, int space, cudaStream_t st,
-                                    SummaryPlan* P) {
+                                    const int64_t* summary_start, int in_space, int space, SummaryPlan* P) {
     // in_space: where scores / positions live; space: where picks / seg_mean / summary go
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
     AVS_CHECK(space == AVS_HOST || space == AVS_DEVICE, AVS_ERR_INVALID, "bad memory space %d", space);
@@ -1097,7 +1125,8 @@ static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, co
     const int64_t sum_bytes = want_summary ? summary_start[n] : 0;
 
     // int32 descriptor block: row_start | lengths | n_frames | cps_start | cps
-    std::vector<int32_t> desc;
+    std::vector<int32_t>& desc = P->desc;
+    desc.clear();
     desc.insert(desc.end(), row_start, row_start + n);
     desc.insert(desc.end(), lengths, lengths + n);
     desc.insert(desc.end(), n_frames, n_frames + n);
@@ -1105,7 +1134,8 @@ static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, co
     if (desc.size() % 2) desc.push_back(0);  // keep cps 8-byte aligned for int2 loads
     const size_t cps_off = desc.size();
     desc.insert(desc.end(), cps, cps + 2 * static_cast<size_t>(total_S));
-    std::vector<int64_t> off64(off);
+    std::vector<int64_t>& off64 = P->off64;
+    off64 = off;
     if (want_summary) off64.insert(off64.end(), summary_start, summary_start + n + 1);
 
     size_t need = desc.size() * 4 + off64.size() * 8 + static_cast<size_t>(total_S) * (8 + 8 + 1) +
@@ -1128,8 +1158,8 @@ static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, co
         P->picks_dev = A.take<uint8_t>(std::max(total_S, 1));
         if (want_summary) P->summary_dev = A.take<uint8_t>(sum_bytes);
     }
-    AVS_TRY(upload_small(off_dev, off64.data(), off64.size() * 8, st));
-    AVS_TRY(upload_small(desc_dev, desc.data(), desc.size() * 4, st));
+    P->off_dev = off_dev;
+    P->desc_dev = desc_dev;
 
     SummaryBatch& sb = P->sb;
     sb.row_start = desc_dev;
@@ -1151,6 +1181,25 @@ static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, co
     P->total_S = total_S;
     P->rows = rows;
     P->sum_bytes = sum_bytes;
+    return AVS_OK;
+}
+
+static avs_status summarize_upload(const SummaryPlan& P, cudaStream_t st) {
+    AVS_TRY(upload_small(P.off_dev, P.off64.data(), P.off64.size() * 8, st));
+    return upload_small(P.desc_dev, P.desc.data(), P.desc.size() * 4, st);
+}
+
+// the uploads run on the side stream as soon as the arena's previous user has finished; st then waits for them
+static avs_status summarize_upload_side(avs_model* m, avs_model::SumArena& sa, const SummaryPlan& P, cudaStream_t st) {
+    if (sa.used) AVS_CUDA(cudaStreamWaitEvent(m->sum_stream, sa.done, 0));
+    AVS_TRY(summarize_upload(P, m->sum_stream));
+    AVS_CUDA(cudaEventRecord(m->ev_sum_out, m->sum_stream));
+    AVS_CUDA(cudaStreamWaitEvent(st, m->ev_sum_out, 0));
+    return AVS_OK;
+}
+static avs_status summarize_mark_done(avs_model::SumArena& sa, cudaStream_t st) {
+    AVS_CUDA(cudaEventRecord(sa.done, st));
+    sa.used = true;
     return AVS_OK;
 }
 
@@ -1208,13 +1257,15 @@ avs_status avs_summarize(avs_model* m, const float* scores, const int32_t* posit
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
     AVS_CHECK(n_videos >= 0, AVS_ERR_INVALID, "n_videos negative");
     if (n_videos == 0) return AVS_OK;
-    AVS_CHECK(!m->slot_busy[0], AVS_ERR_INVALID, "slot 0 is in flight: call avs_slot_wait first");
     Guard g(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    avs_model::SumArena& sa = m->sum_ws[avs_model::SLOTS + (m->sum_flip++ & 1)];
     SummaryPlan P;
-    AVS_TRY(summarize_prepare(m, m->sum_ws[0], n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
-                              prop_den, summary != nullptr, summary_start, space, space, st, &P));
-    return summarize_run(P, scores, positions, picks, seg_mean, summary, space, space, st, true);
+    AVS_TRY(summarize_prepare(m, sa.a, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num, prop_den,
+                              summary != nullptr, summary_start, space, space, &P));
+    AVS_TRY(summarize_upload_side(m, sa, P, st));
+    AVS_TRY(summarize_run(P, scores, positions, picks, seg_mean, summary, space, space, st, true));
+    return summarize_mark_done(sa, st);
 }
 
 static avs_status forward_summarize_impl(avs_model* m, const float* visual, const float* audio,
@@ -1237,15 +1288,18 @@ static avs_status forward_summarize_impl(avs_model* m, const float* visual, cons
     if (g_e2e.enabled() && space == AVS_HOST) g_e2e.host[0] = E2ETrace::now();
     int max_len = 0;
     AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
+    avs_model::SumArena& sa = m->sum_ws[async ? slot : avs_model::SLOTS + (m->sum_flip++ & 1)];
     SummaryPlan P;
-    if (n_videos > 0)   // descriptors first: they do not depend on the scores and stay off the critical tail
-        AVS_TRY(summarize_prepare(m, m->sum_ws[slot], n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num,
-                                  prop_den, summary != nullptr, summary_start, AVS_DEVICE, space, st, &P));
+    if (n_videos > 0)   // validate everything before any work is queued
+        AVS_TRY(summarize_prepare(m, sa.a, n_videos, row_start, lengths, n_frames, cps, cps_start, prop_num, prop_den,
+                                  summary != nullptr, summary_start, AVS_DEVICE, space, &P));
     if (space == AVS_DEVICE) {
         AVS_TRY(forward_entry(m, visual, audio, total_rows, n_videos, row_start, lengths, attn_axis, precision, scores,
                               AVS_DEVICE, cuda_stream, nullptr, nullptr, nullptr));
         if (n_videos == 0) return AVS_OK;
-        return summarize_run(P, scores, positions, picks, seg_mean, summary, AVS_DEVICE, AVS_DEVICE, st, true);
+        AVS_TRY(summarize_upload_side(m, sa, P, st));
+        AVS_TRY(summarize_run(P, scores, positions, picks, seg_mean, summary, AVS_DEVICE, AVS_DEVICE, st, true));
+        return summarize_mark_done(sa, st);
     }
     // host space: features in, scores stay on the device for pooling + knapsack, everything comes back with ONE
     // synchronisation at the end (no D2H -> H2D round trip of the scores between the two halves)
@@ -1264,7 +1318,11 @@ static avs_status forward_summarize_impl(avs_model* m, const float* visual, cons
         AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[0], 0));   // positions travelled on the copy stream (grouped path)
         AVS_CUDA(cudaMemcpyAsync(scores, sc_dev, static_cast<size_t>(total_rows) * 4, cudaMemcpyDeviceToHost, st));
     }
+    // the descriptor uploads go to the side stream, queued (on the host) after the feature copies and the groups'
+    // kernels: they need nothing but the workspace
+    AVS_TRY(summarize_upload_side(m, sa, P, st));
     AVS_TRY(summarize_run(P, sc_dev, pos_dev, picks, seg_mean, summary, AVS_DEVICE, AVS_HOST, st, !async));
+    AVS_TRY(summarize_mark_done(sa, st));
     if (async) {
         AVS_CUDA(cudaEventRecord(m->ev_slot[slot], st));
         m->slot_busy[slot] = true;

@@ -101,6 +101,7 @@ struct LstmBatch {            // device arrays, one entry per slot (n_groups * N
     int nb;                       // videos per cluster (1, 2, 4, 8, 16)
     int excl = 0;                 // tensor-core kernel, 8-slot variant: 0 = launch policy decides which groups get
                                   // exclusive SMs, -1 = none (the call shares the GPU with other video groups)
+    int lane_map = 0;             // h exchange: 0 = lane -> (peer = lane % 8, video = lane / 8), 1 = (lane / 4, lane % 4)
 };
 // xg_v, xg_a: [rows, 2048] gate pre-activations (biases included) in the packed column order
 //   col = dir * 1024 + cta * 128 + jj * 4 + gate   (hidden unit j = cta * 32 + jj)

@@ -321,7 +321,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         // h exchange, warp-local: this warp produces the 16-byte chunks (8 hidden units of chunk q) of videos
         // v0 .. v0+NV-1.  After a __syncwarp lane l sends chunk (video v0 + 4k + (l >> 3)) to peer CTA (l & 7)
         // with one st.async: 4 videos x 8 peers = 32 lanes.  No CTA-wide barrier, no bulk-copy engine.
-        const uint32_t peer = lane & 7, cvid = lane >> 3;
+        const uint32_t peer = batch.lane_map ? (lane >> 2) : (lane & 7), cvid = batch.lane_map ? (lane & 3) : (lane >> 3);
         const uint32_t stage_rd = smem_u32(stage16) + q * S::H_LBO + (lv0 + cvid) * 16;     // + k*64, + slot
         const uint32_t remote_h = mapa(smem_u32(h_sm) + (r * 4 + q) * S::H_LBO + (lv0 + cvid) * 16, peer);
         const uint32_t remote_bar = mapa(smem_u32(bar_h), peer);
@@ -486,10 +486,14 @@ SplitCtx& split_ctx() {
 }
 
 template <int NB, int PARTS, int CHAINS>
-avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch, int op_dtype,
+avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch_in, int op_dtype,
                      void* fused, int out_dtype, int round_tf32, float4* save_pre, float* save_c, cudaStream_t stream) {
     static const bool trace = getenv("AVS_LSTM_TRACE") != nullptr;
     static const bool no_split = getenv("AVS_LSTM_NO_SPLIT") != nullptr;
+    LstmBatch batch = batch_in;
+    batch.lane_map = 1;   // adjacent lanes address adjacent 16-byte chunks of ONE peer (measured: an isolated chain
+                          // takes 0.67 instead of 0.71 us per step; no difference once chains share an SM)
+    if (const char* e = getenv("AVS_LSTM_LANEMAP")) batch.lane_map = atoi(e);
     auto kern = trace ? lstm_tc_kernel<NB, PARTS, CHAINS, NB == 16> : lstm_tc_kernel<NB, PARTS, CHAINS, false>;
     constexpr int SMEM = Smem<NB, CHAINS>::TOTAL;
     constexpr int SMEM_EXCLUSIVE = 200 * 1024;   // more than half an SM: no second CTA of either launch fits beside it
@@ -550,8 +554,12 @@ avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float*
     if (batch.n_groups == 0) return AVS_OK;
     AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
     switch (batch.nb) {   // video slots per cluster
-        case 8: return launch_tc<16, 2, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
-                                                static_cast<float4*>(save_pre), save_c, stream);
+        case 8:
+            if (getenv("AVS_LSTM_ONE_CHAIN") != nullptr)   // experiment: 8 videos in ONE chain per CTA
+                return launch_tc<16, 2, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+                                           static_cast<float4*>(save_pre), save_c, stream);
+            return launch_tc<16, 2, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
+                                       static_cast<float4*>(save_pre), save_c, stream);
         case 16: return launch_tc<16, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
                                                 static_cast<float4*>(save_pre), save_c, stream);
         case 32: return launch_tc<32, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,

@@ -34,13 +34,14 @@ def main():
     vh = torch.cat([v.visual for v in vids]).pin_memory()
     ah = torch.cat([v.audio for v in vids]).pin_memory()
     ph = torch.from_numpy(np.concatenate([v.positions for v in vids]).astype(np.int32)).pin_memory()
-    nf = [v.n_frames for v in vids]
-    cps = [v.cps for v in vids]
+    from avsum_b200.runtime import ShotDesc
+    shots = ShotDesc([v.n_frames for v in vids], [v.cps for v in vids])
+    noflush = len(sys.argv) > 2 and sys.argv[2] == "noflush"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     vd, ad = torch.empty_like(vh, device="cuda"), torch.empty_like(ah, device="cuda")
 
     def step():
-        return nat.score_and_summarize_rows(vh, ah, ph, starts, lens, nf, cps, 0.15, "literal_b1", "tf32")
+        return nat.score_and_summarize_rows(vh, ah, ph, starts, lens, None, shots, 0.15, "literal_b1", "tf32")
 
     for _ in range(3):
         step()
@@ -49,7 +50,8 @@ def main():
     wall = 0.0
     out = np.zeros(20)
     for _ in range(n):
-        flush.fill_(1)
+        if not noflush:
+            flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         step()
