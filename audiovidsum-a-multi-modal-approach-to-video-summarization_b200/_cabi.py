@@ -30,6 +30,7 @@ EXPORTS = [
     "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
     "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
     "avs_debug_e2e_trace", "avs_forward_summarize_async", "avs_slot_wait",
+    "avs_debug_gemm_trace",
 ]
 
 
@@ -129,6 +130,8 @@ def lib() -> C.CDLL:
     L.avs_linear_bwd.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     L.avs_debug_lstm_trace.restype = C.c_int
     L.avs_debug_lstm_trace.argtypes = [vp]
+    L.avs_debug_gemm_trace.restype = C.c_int
+    L.avs_debug_gemm_trace.argtypes = [vp]
     L.avs_debug_e2e_trace.restype = C.c_int
     L.avs_debug_e2e_trace.argtypes = [vp]
     L.avs_profile.restype = None

@@ -483,6 +483,14 @@ avs_status avs_debug_lstm_trace(uint64_t* out8) {
     return lstm_trace_read(reinterpret_cast<unsigned long long*>(out8));
 }
 
+/* Debugging aid: clock64 totals of the tensor-core GEMM pipeline on block 0 since the last read (AVS_GEMM_TRACE=1):
+ * [0] MMA thread span, [1] MMA waiting for operands, [2] MMA waiting for a drained accumulator, [3] producer waiting
+ * for a free stage, [4] epilogue warp waiting for an accumulator, [5] epilogue span, [6] tiles. */
+avs_status avs_debug_gemm_trace(uint64_t* out8) {
+    AVS_CHECK(out8 != nullptr, AVS_ERR_INVALID, "null pointer");
+    return gemm_trace_read(reinterpret_cast<unsigned long long*>(out8));
+}
+
 /* Debugging aid: timeline of the last pipelined host-space avs_forward_summarize call (AVS_E2E_TRACE=1).
  * out[0] = number of video groups G; out[1..5] = host clock at entry / copies queued / groups queued / tail queued /
  * synchronised (ms after entry); then, in ms after the first device timestamp: out[6..6+G) = group g's features

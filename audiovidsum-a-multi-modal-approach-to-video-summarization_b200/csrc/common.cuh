@@ -84,6 +84,7 @@ struct GemmEpilogue {
 // tcgen05 / TMA path.  in_dtype: DT_F32 (kind::tf32), DT_F16 or DT_BF16 (kind::f16).
 avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, int64_t M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t stream);
+avs_status gemm_trace_read(unsigned long long* out8);   // debugging aid (AVS_GEMM_TRACE=1)
 // CUDA-core fp32 path (debug / exact-order aid).
 avs_status gemm_simt(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int N, int K,
                      const GemmEpilogue& epi, cudaStream_t stream);

@@ -7,7 +7,8 @@
 // Persistent kernel, one CTA per SM, static round-robin over 128 x BN output tiles:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, 6-8 stage mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32 or kind::f16)
-//   warps 2..5  : epilogue -- tcgen05.ld the fp32 accumulator (double buffered in TMEM, so it
+//   warps 2..9  : epilogue (two warps per TMEM lane quarter, half of the tile's columns each; measured: with four
+//                 warps the fp32-output GEMMs were epilogue bound, tools/gemm_trace.py) -- tcgen05.ld the fp32 accumulator (double buffered in TMEM, so it
 //                 overlaps the next tile's main loop), fuse bias / ReLU / tf32 rounding /
 //                 fp16-bf16 cast, stage the warp's 32 rows in 128B-swizzled shared memory and write
 //                 them with TMA stores (cp.async.bulk.tensor ... bulk_group: full-line coalesced
@@ -16,6 +17,8 @@
 //
 // Tile 128 x BN x 128 B of K per stage (32 tf32 or 64 half elements), 4 MMAs (K = 32 B) per stage.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -26,7 +29,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int A_STAGE_BYTES = BM * 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                      // two per TMEM lane quarter: each takes half of the tile's columns
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -41,6 +45,17 @@ struct SmemLayout {
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Optional pipeline trace (AVS_GEMM_TRACE=1, debugging aid): block 0 accumulates clock64 totals --
+// [0] MMA thread busy span, [1] MMA waiting for operands (full), [2] MMA waiting for a drained accumulator,
+// [3] producer waiting for a free stage, [4] epilogue warp waiting for an accumulator, [5] epilogue span, [6] tiles.
+__device__ int g_gemm_trace_on = 0;
+__device__ unsigned long long g_gemm_trace[8];
+__device__ __forceinline__ long long gclk() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
 
 // TMA store shared::cta -> global (bulk async group completion).
 __device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src, int32_t c0, int32_t c1) {
@@ -101,9 +116,10 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
                                               int num_tiles, int tile0, int tile_step, int tile_rows, int m_off,
                                               const GemmEpilogue& epi, int warp, int lane) {
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int cg = (warp - 2) >> 2;   // column group: which half of the tile's columns this warp handles
         const uint32_t lane_taddr = static_cast<uint32_t>(q * 32) << 16;
         if (epi.scores != nullptr) {
-            // fused frame-score head: one float per row, straight from registers
+            // fused frame-score head: one float per row, straight from registers (64 columns: column group 0 only)
             const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
             const bool w2_vec = (reinterpret_cast<uintptr_t>(epi.score_w2) & 15) == 0;
             uint32_t lt = 0;
@@ -112,6 +128,10 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
                 const uint32_t acc = lt & 1;
                 mbar_wait(tmem_full + acc, (lt >> 1) & 1);
                 tc_fence_after();
+                if (cg != 0) {
+                    mbar_arrive_cluster(tmem_empty_addr + acc * 8);
+                    continue;
+                }
                 const int row = m0 + q * 32 + lane;
                 float score_acc = 0.f;
 #pragma unroll 1
@@ -139,21 +159,28 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
             const bool wide = epi.out_dtype != DT_F32;          // 16-bit output: 64 columns per 128-byte box
             const int box_cols = wide ? 64 : 32;
             const int n_boxes = BN / box_cols;
-            constexpr int SLOTS = L::OUT_WARP_BYTES / 4096;     // staging boxes per warp (a 256-wide fp32 tile cycles twice)
+            const int bx_mid = (n_boxes + 1) / 2;               // column group 0: boxes [0, mid), group 1: [mid, n_boxes)
+            const int bx_lo = cg ? bx_mid : 0, bx_hi = cg ? n_boxes : bx_mid;
+            constexpr int SLOTS = L::OUT_WARP_BYTES / 2 / 4096;   // staging boxes per warp (cycled when a tile has more)
+            static_assert(SLOTS >= 1, "staging area too small");
             uint32_t issued = 0;                                // boxes handed to the TMA engine so far
-            const uint32_t out_base = smem_u32(tiles + L::TILE_BYTES) + q * L::OUT_WARP_BYTES;
+            const uint32_t out_base = smem_u32(tiles + L::TILE_BYTES) + (q * 2 + cg) * (L::OUT_WARP_BYTES / 2);
             const uint32_t my_row = out_base + lane * 128;
             const uint32_t sw = static_cast<uint32_t>(lane & 7);
             const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
+            const bool tr = g_gemm_trace_on && blockIdx.x == 0 && warp == 2 && lane == 0;   // (warp 2: q = 2, cg = 0)
+            long long tr_wait = 0, tr_t0 = tr ? gclk() : 0;
             uint32_t lt = 0;
             for (int t = tile0; t < num_tiles; t += tile_step, ++lt) {
                 const int m0 = (t / tiles_n) * tile_rows + m_off, n0 = (t % tiles_n) * BN;
                 const uint32_t acc = lt & 1;
+                const long long w0 = tr ? gclk() : 0;
                 mbar_wait(tmem_full + acc, (lt >> 1) & 1);
+                if (tr) tr_wait += gclk() - w0;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * BN + lane_taddr;
 #pragma unroll 1
-                for (int bx = 0; bx < n_boxes; ++bx) {
+                for (int bx = bx_lo; bx < bx_hi; ++bx) {
                     const int nb = n0 + bx * box_cols;
                     // the TMA store that read this staging slot SLOTS boxes ago must be done reading
                     const uint32_t slot = issued % SLOTS;
@@ -217,6 +244,11 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
             }
             if (lane == 0) bulk_wait_group_read(0);   // shared memory must outlive the last stores' reads
             __syncwarp();
+            if (tr) {
+                g_gemm_trace[4] += tr_wait;
+                g_gemm_trace[5] += gclk() - tr_t0;
+                g_gemm_trace[6] += lt;
+            }
         }
 }
 
@@ -253,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full + a, 1);
-            mbar_init(tmem_empty + a, 128);
+            mbar_init(tmem_empty + a, EPI_WARPS * 32);
         }
         fence_mbar_init();
     }
@@ -269,33 +301,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (elect_one()) {
+            const bool tr = g_gemm_trace_on && blockIdx.x == 0;
+            long long tr_wait = 0;
             uint32_t it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const long long w0 = tr ? gclk() : 0;
                     mbar_wait(empty + s, ph ^ 1);
+                    if (tr) tr_wait += gclk() - w0;
                     mbar_expect_tx(full + s, L::STAGE_BYTES);
                     uint8_t* a_dst = tiles + s * L::STAGE_BYTES;
                     tma_load_2d(a_dst, &tmA, full + s, kb * bk_elems, m0);
                     tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, full + s, kb * bk_elems, n0);
                 }
             }
+            if (tr) g_gemm_trace[3] += tr_wait;
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (elect_one()) {
+            const bool tr = g_gemm_trace_on && blockIdx.x == 0;
+            long long tr_full = 0, tr_acc = 0, tr_t0 = tr ? gclk() : 0;
             uint32_t it = 0, lt = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
                 const uint32_t acc = lt & 1;
+                long long w0 = tr ? gclk() : 0;
                 mbar_wait(tmem_empty + acc, ((lt >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+                if (tr) tr_acc += gclk() - w0;
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    w0 = tr ? gclk() : 0;
                     mbar_wait(full + s, ph);
+                    if (tr) tr_full += gclk() - w0;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
                     const uint32_t b_addr = a_addr + A_STAGE_BYTES;
@@ -312,6 +355,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_commit(tmem_full + acc);  // accumulator complete
             }
+            if (tr) {
+                g_gemm_trace[0] += gclk() - tr_t0;
+                g_gemm_trace[1] += tr_full;
+                g_gemm_trace[2] += tr_acc;
+            }
         }
         __syncwarp();
     } else {
@@ -321,6 +369,231 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ---------------------------------------------------------------- 2-CTA (cta_group::2) variant
+// A CTA pair (cluster of 2, same TPC) computes one 256 x BN output tile: CTA r owns rows [m0 + 128 r, + 128) of A and
+// of the accumulator (its own TMEM) and loads HALF of the B tile (BN / 2 weight rows); the leader's
+// tcgen05.mma.cta_group::2 (M = 256) reads both halves.  Per CTA and k-block the operands are 16 KB of A + BN/4 KB of
+// B instead of 16 + BN/2: a third less L2 -> SM traffic per FLOP, which is what bounds these GEMMs.
+//   full[s]   (leader's): both CTAs' TMA loads complete_tx on it; the leader's producer arms it for both
+//   empty[s]  (each CTA's own): tcgen05.commit.cta_group::2 with multicast to both CTAs
+//   tmem_full[a]  (each CTA's own): multicast commit;  tmem_empty[a] (leader's): 2 x 128 epilogue threads arrive
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into this CTA's shared memory, bytes counted on the barrier at shared::cluster address bar_cluster_addr
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const void* desc, uint32_t bar_cluster_addr, int32_t c0,
+                                                 int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive (count 1) on the barrier at this offset in every CTA of cta_mask when the issued MMAs retire
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    if (TF32)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}\n"
+            :
+            : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n"
+            :
+            : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// mbarrier wait with acquire at cluster scope (the arrivals come from the peer CTA's epilogue threads)
+__device__ __forceinline__ void mbar_wait_cluster_acq(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > AVS_SPIN_LIMIT) {
+            printf("avsum_b200: gemm accumulator wait timed out (block %d parity %u)\n", blockIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
+template <int BN, int STAGES>
+struct SmemLayout2 {
+    static constexpr int B_HALF_BYTES = (BN / 2) * 128;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
+    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int OUT_WARP_BYTES = 32 * BN * (BN == 256 ? 2 : 4);
+    static constexpr int OUT_BYTES = 4 * OUT_WARP_BYTES;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 8;
+    static constexpr int TOTAL = 1024 /*alignment slack*/ + TILE_BYTES + OUT_BYTES + BAR_BYTES;
+};
+
+template <int BN, int STAGES, bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, int M, int N, int k_blocks, int bk_elems, uint32_t idesc,
+                int tiles_n, int num_tiles, GemmEpilogue epi) {
+    using L = SmemLayout2<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + L::TILE_BYTES + L::OUT_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = static_cast<int>(blockIdx.x >> 1);
+    const int n_clusters = static_cast<int>(gridDim.x >> 1);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full + a, 1);
+            mbar_init(tmem_empty + a, 2 * EPI_WARPS * 32);   // the epilogue threads of both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2cta(tmem_slot, 2 * BN);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // the peer's barriers exist before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (elect_one()) {
+            const uint32_t full_leader = mapa_u32(smem_u32(full), 0);
+            const bool tr = g_gemm_trace_on && blockIdx.x == 0;
+            long long tr_wait = 0;
+            uint32_t it = 0;
+            for (int t = cluster_id; t < num_tiles; t += n_clusters) {
+                const int m0 = (t / tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+                const int n0 = (t % tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const long long w0 = tr ? gclk() : 0;
+                    mbar_wait(empty + s, ph ^ 1);
+                    if (tr) tr_wait += gclk() - w0;
+                    if (rank == 0) mbar_expect_tx(full + s, 2 * L::STAGE_BYTES);
+                    uint8_t* a_dst = tiles + s * L::STAGE_BYTES;
+                    tma_load_2d_2cta(a_dst, &tmA, full_leader + s * 8, kb * bk_elems, m0);
+                    tma_load_2d_2cta(a_dst + A_STAGE_BYTES, &tmB, full_leader + s * 8, kb * bk_elems, n0);
+                }
+            }
+            if (tr) g_gemm_trace[3] += tr_wait;
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && elect_one()) {
+            const bool tr = g_gemm_trace_on && blockIdx.x == 0;
+            long long tr_full = 0, tr_acc = 0, tr_t0 = tr ? gclk() : 0;
+            uint32_t it = 0, lt = 0;
+            for (int t = cluster_id; t < num_tiles; t += n_clusters, ++lt) {
+                const uint32_t acc = lt & 1;
+                long long w0 = tr ? gclk() : 0;
+                mbar_wait_cluster_acq(tmem_empty + acc, ((lt >> 1) & 1) ^ 1);   // both epilogues drained it
+                if (tr) tr_acc += gclk() - w0;
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    w0 = tr ? gclk() : 0;
+                    mbar_wait(full + s, ph);
+                    if (tr) tr_full += gclk() - w0;
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = umma_desc_sw128_kmajor(a_addr + k * 32);
+                        const uint64_t bd = umma_desc_sw128_kmajor(b_addr + k * 32);
+                        umma_ss_2cta<TF32>(tmem_acc, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    tc_commit_2cta(empty + s, 3);   // the slot is reusable in both CTAs once these MMAs retire
+                }
+                tc_commit_2cta(tmem_full + acc, 3);   // accumulator complete (both CTAs' epilogues)
+            }
+            if (tr) {
+                g_gemm_trace[0] += gclk() - tr_t0;
+                g_gemm_trace[1] += tr_full;
+                g_gemm_trace[2] += tr_acc;
+            }
+        }
+        __syncwarp();
+    } else {
+        gemm_epilogue<BN, L>(tiles, tmem_base, tmem_full, mapa_u32(smem_u32(tmem_empty), 0), tmC, M, N, tiles_n, num_tiles,
+                             cluster_id, n_clusters, 2 * BM, static_cast<int>(rank) * BM, epi, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // nobody leaves while the pair's MMAs / commits may still touch its memory
+    if (warp == 1) tmem_dealloc_2cta(tmem_base, 2 * BN);
 }
 
 // ---------------------------------------------------------------- host side
@@ -367,9 +640,70 @@ avs_status make_tmap(CUtensorMap* tm, const void* ptr, int dtype, int64_t rows, 
 
 }  // namespace
 
+static avs_status gemm_tc2(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, int64_t M, int N,
+                           int K, const GemmEpilogue& epi, cudaStream_t stream) {
+    constexpr int BN = 256;
+    const int esz = dtype_size(in_dtype);
+    const int bk_elems = 128 / esz;
+    const int k_blocks = (K + bk_elems - 1) / bk_elems;
+    const bool tf32 = in_dtype == DT_F32;
+    const uint32_t fmt = tf32 ? UMMA_FMT_TF32 : (in_dtype == DT_F16 ? UMMA_FMT_F16 : UMMA_FMT_BF16);
+    CUtensorMap tmA, tmB, tmC;
+    AVS_TRY(make_tmap(&tmA, A, in_dtype, M, K, lda, BM));
+    AVS_TRY(make_tmap(&tmB, W, in_dtype, N, K, ldw, BN / 2));
+    AVS_TRY(make_tmap(&tmC, epi.C, epi.out_dtype, M, N, epi.ldc, 32));
+    const int tiles_n = N / BN;
+    const int64_t tiles_total = ((M + 2 * BM - 1) / (2 * BM)) * tiles_n;
+    AVS_CHECK(tiles_total < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: too many tiles");
+    const int num_tiles = static_cast<int>(tiles_total);
+    static int num_pairs = 0;
+    if (num_pairs == 0) {
+        int dev = 0, sms = 0;
+        AVS_CUDA(cudaGetDevice(&dev));
+        AVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        num_pairs = sms / 2;
+    }
+    const int grid = 2 * (num_tiles < num_pairs ? num_tiles : num_pairs);
+    const uint32_t idesc = umma_idesc(fmt, 2 * BM, BN);
+#define AVS_GEMM2_LAUNCH(ST_, TF_)                                                                            \
+    do {                                                                                                     \
+        using L = SmemLayout2<BN, ST_>;                                                                      \
+        auto kern = gemm_tc2_kernel<BN, ST_, TF_>;                                                           \
+        static bool configured = false;                                                                      \
+        if (!configured) {                                                                                   \
+            AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));     \
+            configured = true;                                                                               \
+        }                                                                                                    \
+        kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, static_cast<int>(M), N, k_blocks,      \
+                                                       bk_elems, idesc, tiles_n, num_tiles, epi);            \
+    } while (0)
+    if (tf32) AVS_GEMM2_LAUNCH(5, true);
+    else AVS_GEMM2_LAUNCH(5, false);
+#undef AVS_GEMM2_LAUNCH
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
+
+// debugging aid: read and clear the pipeline trace (AVS_GEMM_TRACE=1)
+avs_status gemm_trace_read(unsigned long long* out8) {
+    AVS_CUDA(cudaDeviceSynchronize());
+    AVS_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_trace, 8 * sizeof(unsigned long long)));
+    unsigned long long zero[8] = {};
+    AVS_CUDA(cudaMemcpyToSymbol(g_gemm_trace, zero, sizeof(zero)));
+    return AVS_OK;
+}
+
 avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, int64_t M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t stream) {
     if (M == 0) return AVS_OK;
+    static bool trace_set = false;
+    if (!trace_set) {
+        trace_set = true;
+        if (getenv("AVS_GEMM_TRACE") != nullptr) {
+            const int on = 1;
+            AVS_CUDA(cudaMemcpyToSymbol(g_gemm_trace_on, &on, sizeof(on)));
+        }
+    }
     AVS_CHECK(M > 0 && N > 0 && K > 0, AVS_ERR_INVALID, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
     AVS_CHECK(M < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: M too large");
     // the bias / score epilogues read 16 columns at a time; a plain store only needs a 16-byte row pitch
@@ -392,6 +726,12 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     const int64_t m_tiles = (M + BM - 1) / BM;
     const bool wide_ok = N % 256 == 0 && epi.scores == nullptr && !(in_dtype == DT_F32) && m_tiles * (N / 256) >= 4 * 148;
     const int BN = wide_ok ? 256 : ((N % 128 == 0) ? 128 : 64);
+    // CTA pairs (256 x 256 tiles, cta_group::2) when the pair tiles still spread over the 74 SM pairs
+    static const bool no_pairs = getenv("AVS_GEMM_1CTA") != nullptr;
+    static const int pair_min = getenv("AVS_GEMM_PAIR_MIN") ? atoi(getenv("AVS_GEMM_PAIR_MIN")) : 2 * 74;   // test hook
+    const int64_t pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / 256);
+    if (!no_pairs && N % 256 == 0 && epi.scores == nullptr && pair_tiles >= pair_min)
+        return gemm_tc2(A, lda, W, ldw, in_dtype, M, N, K, epi, stream);
 
     CUtensorMap tmA, tmB, tmC;
     AVS_TRY(make_tmap(&tmA, A, in_dtype, M, K, lda, BM));

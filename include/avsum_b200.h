@@ -240,6 +240,12 @@ void avs_profile_read(double* ms, int64_t* calls);
  * next h landed), out8[7] = number of steps. */
 avs_status avs_debug_lstm_trace(uint64_t* out8);
 
+/* Debugging aid: clock64 totals of the tensor-core GEMM pipeline (block 0) since the last read, recorded when the
+ * environment variable AVS_GEMM_TRACE is set: out8[0] MMA thread span, [1] MMA waiting for operands, [2] MMA waiting
+ * for a drained accumulator, [3] producer waiting for a free stage, [4] epilogue warp waiting for an accumulator,
+ * [5] epilogue span, [6] tiles. */
+avs_status avs_debug_gemm_trace(uint64_t* out8);
+
 /* Debugging aid: timeline of the last pipelined host-space avs_forward_summarize call, recorded when the
  * environment variable AVS_E2E_TRACE is 1.  out20[0] = number of video groups G; out20[1..5] = host clock (ms after
  * entry) at entry / copies queued / groups queued / tail queued / synchronised; in ms after the first device

@@ -57,6 +57,25 @@ def test_linear_matches_torch(cuda_ready, prec, shape):
         assert err < {"tf32": 2e-3, "bf16": 1.5e-2, "fp32_simt": 2e-6}[prec], (shape, relu, err)
 
 
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("shape", [(38000, 512, 1024), (37999, 1024, 512), (20001, 2048, 128), (75777, 256, 96)])
+def test_linear_cta_pair_tiles(cuda_ready, prec, shape):
+    """Shapes large enough for the 2-CTA GEMM (256 x 256 tiles, cta_group::2): ragged M (the pair's second CTA partly
+    or wholly past the last row), several tiles per pair, short and long K."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    want = torch.nn.functional.linear(x, w, b).relu()          # fp32 cuBLAS reference, TF32 disabled by default
+    got = runtime.linear(x, w, b, relu=True, precision=prec)
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < {"tf32": 2e-3, "bf16": 1.5e-2}[prec], (shape, err)
+    # every row block individually (a swapped or dropped tile would pass a max-norm check only by accident)
+    blk = (got - want).abs().reshape(-1)[: (M // 128) * 128 * N].reshape(M // 128, -1).max(dim=1).values
+    assert float(blk.max()) < {"tf32": 2e-3, "bf16": 1.5e-2}[prec] * float(want.abs().max())
+
+
 def test_linear_without_bias_and_bad_shapes(cuda_ready):
     x = torch.randn(40, 64, device="cuda")
     w = torch.randn(32, 64, device="cuda")
