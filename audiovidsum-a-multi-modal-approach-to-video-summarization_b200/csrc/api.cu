@@ -338,7 +338,7 @@ avs_status upload_small(void* dst_dev, const void* src_host, size_t bytes, cudaS
         const int n = static_cast<int>(std::min<size_t>(words, 896));
         std::memcpy(p.w, src, static_cast<size_t>(n) * 4);
         upload_kernel<<<1, 256, 0, st>>>(p, dst, n);
-        AVS_CUDA(cudaGetLastError());
+        AVS_LAUNCH_CHECK();
         src += n;
         dst += n;
         words -= n;

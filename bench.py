@@ -177,7 +177,11 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("AVS_NCCL_DEBUG", "WARN")
+        # (also at WARN); NCCL logging is therefore off unless AVS_NCCL_DEBUG asks for it, and then goes to a file
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("AVS_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["AVS_NCCL_DEBUG"]
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/avs_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- workload: global batch sharded by video

@@ -36,7 +36,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("AVS_NCCL_DEBUG", "WARN")
+        # (also at WARN); NCCL logging is therefore off unless AVS_NCCL_DEBUG asks for it, and then goes to a file
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("AVS_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["AVS_NCCL_DEBUG"]
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/avs_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.videos, args.frames
     g = torch.Generator().manual_seed(100 + rank)
