@@ -80,6 +80,12 @@ class PendingSummary:
             self._model, self._keep = None, None
         return self._outputs
 
+    def __del__(self):   # a dropped handle must not leave its slot marked busy
+        try:
+            self.wait()
+        except Exception:
+            pass
+
 
 class NativeModel:
     """Owns one ``avs_model`` handle built from a reference-format state_dict."""

@@ -67,3 +67,41 @@ def gather_picks(local_ids: Sequence[int], local_picks: Sequence[np.ndarray], n_
             out[vid] = p[off:off + S].copy()
             off += S
     return out
+
+
+def bind_process_to_gpu_numa(device_index: int) -> str:
+    """One process per GPU: pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates
+    pinned host buffers, so that the batches it feeds across PCIe are first-touched in memory local to that GPU's
+    root complex (eight ranks streaming 50 GB/s each otherwise contend for one socket's memory and the inter-socket
+    link).  Best effort: returns a one-line description; a no-op when sysfs exposes no NUMA topology (single node,
+    containers without /sys/bus/pci), when the affinity call is not permitted, or when AVS_NO_NUMA_BIND is set.
+    """
+    import os
+    if os.environ.get("AVS_NO_NUMA_BIND"):
+        return "numa: binding disabled (AVS_NO_NUMA_BIND)"
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return f"numa: {bdf} reports node {node}, {len(nodes)} node(s) visible -- nothing to bind"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa: node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, cpus)
+        return f"numa: {bdf} -> node {node}, bound to {len(cpus)} CPUs ({cpulist})"
+    except Exception as e:   # sysfs layout, permissions, old torch: stay unbound
+        return f"numa: not bound ({type(e).__name__}: {e})"

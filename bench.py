@@ -174,6 +174,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: keep the pinned batches of this rank in the memory next to its GPU (no-op on one node)
+    print(f"[rank {rank}] " + sharding.bind_process_to_gpu_numa(local_rank), file=sys.stderr, flush=True)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO

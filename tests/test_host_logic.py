@@ -104,3 +104,35 @@ def test_feature_dir_dataset_and_packed_batches(tmp_path):
         for k, i in enumerate(b.indices):
             s, n = int(b.row_start[k]), int(b.lengths[k])
             assert torch.equal(b.visual[s:s + n], ds[i][0]["visual"]) and torch.equal(b.scores[s:s + n], ds[i][1])
+
+
+def test_shot_descriptors_pack_like_the_per_call_path():
+    """runtime.ShotDesc (packed once by the loader) holds exactly what the per-call path derives from lists."""
+    from avsum_b200.runtime import ShotDesc, _shots
+    vids = synth.config2()[:7]
+    sd = ShotDesc([v.n_frames for v in vids], [v.cps for v in vids])
+    assert sd.cps.dtype == np.int32 and sd.cps.shape[1] == 2 and sd.cps.flags["C_CONTIGUOUS"]
+    assert sd.cps_start[0] == 0 and list(np.diff(sd.cps_start)) == [len(v.cps) for v in vids]
+    assert np.array_equal(sd.cps, np.concatenate([np.asarray(v.cps, np.int32).reshape(-1, 2) for v in vids]))
+    assert list(np.diff(sd.summary_start)) == [v.n_frames for v in vids] and sd.summary_start.dtype == np.int64
+    assert _shots(None, sd) is sd
+    empty = ShotDesc([], [])
+    assert empty.cps.shape == (0, 2) and list(empty.cps_start) == [0] and list(empty.summary_start) == [0]
+    with pytest.raises(ValueError):
+        ShotDesc([100, 200], [vids[0].cps])
+
+
+def test_numa_binding_is_best_effort():
+    """One process per GPU binds itself next to its GPU when sysfs exposes the topology; without a GPU (here), with
+    one NUMA node or with AVS_NO_NUMA_BIND it must be a harmless no-op that says why."""
+    import os
+    from avsum_b200 import sharding
+    before = os.sched_getaffinity(0)
+    msg = sharding.bind_process_to_gpu_numa(0)
+    assert msg.startswith("numa:")
+    assert os.sched_getaffinity(0) == before or "bound to" in msg
+    os.environ["AVS_NO_NUMA_BIND"] = "1"
+    try:
+        assert "disabled" in sharding.bind_process_to_gpu_numa(0)
+    finally:
+        del os.environ["AVS_NO_NUMA_BIND"]
