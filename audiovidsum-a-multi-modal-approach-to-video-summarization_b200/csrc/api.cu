@@ -30,10 +30,11 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // Enabled by avs_profile(1); events are resolved lazily in avs_profile_read so the hot path
 // never synchronises because of profiling.
 enum Stage : int { ST_CONVERT = 0, ST_FC, ST_IH_PROJ, ST_LSTM, ST_QKV_PROJ, ST_ATTENTION, ST_OUT_PROJ, ST_SCORER,
-                   ST_POOL, ST_KNAPSACK, ST_COUNT };
+                   ST_POOL, ST_KNAPSACK, ST_FRONT, ST_COUNT };
 static const char* const kStageNames[ST_COUNT] = {"convert_tf32", "fc_gemm", "lstm_input_gemm", "lstm_recurrence",
                                                   "attn_in_proj_gemm", "attention_core", "attn_out_proj_gemm",
-                                                  "score_head_gemm", "shot_pool", "knapsack_select"};
+                                                  "score_head_gemm", "shot_pool", "knapsack_select",
+                                                  "frontend_gemms"};
 struct Profiler {
     bool enabled = false;
     std::vector<cudaEvent_t> pool;
@@ -228,6 +229,9 @@ struct avs_model {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
+    // the audio branch (audio_fc -> audio LSTM input projection) of group g runs beside the visual branch
+    cudaStream_t branch_stream[MAX_CHUNKS] = {};
+    cudaEvent_t ev_branch_in[MAX_CHUNKS] = {}, ev_branch_out[MAX_CHUNKS] = {};
 };
 
 namespace {
@@ -585,6 +589,11 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
         }
         for (int i = 0; i < avs_model::SLOTS && ce == cudaSuccess; ++i)
             ce = cudaEventCreateWithFlags(&m->ev_slot[i], cudaEventDisableTiming);
+        for (int i = 0; i < avs_model::MAX_CHUNKS && ce == cudaSuccess; ++i) {
+            ce = cudaStreamCreateWithFlags(&m->branch_stream[i], cudaStreamNonBlocking);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_branch_in[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_branch_out[i], cudaEventDisableTiming);
+        }
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&m->sum_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_sum_out, cudaEventDisableTiming);
         for (int i = 0; i < avs_model::SLOTS + 2 && ce == cudaSuccess; ++i)
@@ -629,6 +638,11 @@ void avs_model_destroy(avs_model* m) {
     }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->sum_stream) cudaStreamDestroy(m->sum_stream);
+    for (int i = 0; i < avs_model::MAX_CHUNKS; ++i) {
+        if (m->branch_stream[i]) cudaStreamDestroy(m->branch_stream[i]);
+        if (m->ev_branch_in[i]) cudaEventDestroy(m->ev_branch_in[i]);
+        if (m->ev_branch_out[i]) cudaEventDestroy(m->ev_branch_out[i]);
+    }
     if (m->ev_sum_out) cudaEventDestroy(m->ev_sum_out);
     for (int i = 0; i < avs_model::SLOTS + 2; ++i) {
         m->sum_ws[i].a.release();
@@ -949,30 +963,57 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         // that is a common factor of every product, removed exactly by scaling the accumulator with 1 + 2^-11
         // in the epilogue.  No separate rounding pass over the 4.6 KB/frame of features (weights are RN-rounded
         // once at pack time).
-        {
-            StageTimer tm(ST_FC, st);
-            GemmEpilogue e1;
-            e1.relu = 1;
-            e1.out_dtype = act;
-            e1.ldc = H;
-            if (!simt && !bf16) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
+        // The visual and the audio branch are independent until the recurrences: the audio branch runs on a side
+        // stream, so the tail of one GEMM (its last, partly filled round of tiles) overlaps the head of another.
+        static const bool two_branches = getenv("AVS_ONE_BRANCH_STREAM") == nullptr;
+        const int gidx = arena ? static_cast<int>(arena - m->ws_grp) + 1 : 0;
+        cudaStream_t sa = (two_branches && n_chunks == 1) ? m->branch_stream[gidx] : st;
+        GemmEpilogue e1;
+        e1.relu = 1;
+        e1.out_dtype = act;
+        e1.ldc = H;
+        if (!simt && !bf16) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
+        GemmEpilogue e2;
+        e2.ldc = 2 * G4;
+        if (sa != st) {
+            // concurrent kernels: per-kernel event pairs would count the overlap twice, so the four GEMMs are
+            // timed as ONE stage ("frontend_gemms": fork -> join on st)
+            StageTimer tm(ST_FRONT, st);
+            AVS_CUDA(cudaEventRecord(m->ev_branch_in[gidx], st));
+            AVS_CUDA(cudaStreamWaitEvent(sa, m->ev_branch_in[gidx], 0));
             e1.bias = m->fc_v_b;
             e1.C = v_emb + r0 * H * asz;
             AVS_TRY(run_gemm(precision, xv, in_dt, Dv, w_fc_v, 0, Dv, Rc, H, Dv, e1, st));
             e1.bias = m->fc_a_b;
             e1.C = a_emb + r0 * H * asz;
-            AVS_TRY(run_gemm(precision, xa, in_dt, Da, w_fc_a, 0, Da, Rc, H, Da, e1, st));
-        }
-        {
-            StageTimer tm(ST_IH_PROJ, st);
-            GemmEpilogue e2;
-            e2.ldc = 2 * G4;
+            AVS_TRY(run_gemm(precision, xa, in_dt, Da, w_fc_a, 0, Da, Rc, H, Da, e1, sa));
             e2.bias = m->ih_v_b;
             e2.C = xg_v + r0 * 2 * G4;
             AVS_TRY(run_gemm(precision, v_emb + r0 * H * asz, act, H, w_ih_v, 0, H, Rc, 2 * G4, H, e2, st));
             e2.bias = m->ih_a_b;
             e2.C = xg_a + r0 * 2 * G4;
-            AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, st));
+            AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, sa));
+            AVS_CUDA(cudaEventRecord(m->ev_branch_out[gidx], sa));
+            AVS_CUDA(cudaStreamWaitEvent(st, m->ev_branch_out[gidx], 0));
+        } else {
+            {
+                StageTimer tm(ST_FC, st);
+                e1.bias = m->fc_v_b;
+                e1.C = v_emb + r0 * H * asz;
+                AVS_TRY(run_gemm(precision, xv, in_dt, Dv, w_fc_v, 0, Dv, Rc, H, Dv, e1, st));
+                e1.bias = m->fc_a_b;
+                e1.C = a_emb + r0 * H * asz;
+                AVS_TRY(run_gemm(precision, xa, in_dt, Da, w_fc_a, 0, Da, Rc, H, Da, e1, st));
+            }
+            {
+                StageTimer tm(ST_IH_PROJ, st);
+                e2.bias = m->ih_v_b;
+                e2.C = xg_v + r0 * 2 * G4;
+                AVS_TRY(run_gemm(precision, v_emb + r0 * H * asz, act, H, w_ih_v, 0, H, Rc, 2 * G4, H, e2, st));
+                e2.bias = m->ih_a_b;
+                e2.C = xg_a + r0 * 2 * G4;
+                AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, st));
+            }
         }
     }
 

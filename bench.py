@@ -46,6 +46,8 @@ def stage_flops_per_frame(axis: str, mean_T: float):
         "attn_out_proj_gemm": 2 * 1024 * 1024,
         "score_head_gemm": 2 * (64 * 1024 + 64),
     }
+    # fc + LSTM-input GEMMs of both branches, timed as one stage when the audio branch runs on its side stream
+    f["frontend_gemms"] = f["fc_gemm"] + f["lstm_input_gemm"]
     return f
 
 
