@@ -257,9 +257,11 @@ avs_status check_dims(const avs_weights* w) {
     return AVS_OK;
 }
 
-avs_status pack_weights(avs_model* m, const avs_weights* w) {
+// lstm_only: just the four recurrences' tensors (what a training step changes and reads through the handle);
+// sync: wait for the packing kernels (model creation) -- otherwise the caller's stream orders them
+avs_status pack_weights(avs_model* m, const avs_weights* w, cudaStream_t st = 0, bool lstm_only = false,
+                        bool sync = true) {
     const int Dv = m->Dv, Da = m->Da;
-    cudaStream_t st = 0;
     // raw copies
     const size_t raw_elems = static_cast<size_t>(H) * (Dv + Da) + 2 * H + 4 * (static_cast<size_t>(G4) * H + G4 * HC + 2 * G4) +
                              3ull * E * E + 3 * E + static_cast<size_t>(E) * E + E + 64ull * E + 64 + 64 + 1;
@@ -270,15 +272,19 @@ avs_status pack_weights(avs_model* m, const avs_weights* w) {
         AVS_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDefault, st));
         return AVS_OK;
     };
-    float *r_fcv, *r_fca, *r_ih[4], *r_hh[4], *r_bih[4], *r_bhh[4], *r_inw, *r_outw, *r_sc0;
-    AVS_TRY(up(w->visual_fc_w, static_cast<size_t>(H) * Dv, &r_fcv));
-    AVS_TRY(up(w->audio_fc_w, static_cast<size_t>(H) * Da, &r_fca));
+    float *r_fcv = nullptr, *r_fca = nullptr, *r_ih[4], *r_hh[4], *r_bih[4], *r_bhh[4], *r_inw = nullptr,
+          *r_outw = nullptr, *r_sc0 = nullptr;
+    if (!lstm_only) {
+        AVS_TRY(up(w->visual_fc_w, static_cast<size_t>(H) * Dv, &r_fcv));
+        AVS_TRY(up(w->audio_fc_w, static_cast<size_t>(H) * Da, &r_fca));
+    }
     for (int i = 0; i < 4; ++i) {
         AVS_TRY(up(w->lstm_w_ih[i], static_cast<size_t>(G4) * H, &r_ih[i]));
         AVS_TRY(up(w->lstm_w_hh[i], static_cast<size_t>(G4) * HC, &r_hh[i]));
         AVS_TRY(up(w->lstm_b_ih[i], G4, &r_bih[i]));
         AVS_TRY(up(w->lstm_b_hh[i], G4, &r_bhh[i]));
     }
+    if (!lstm_only) {
     AVS_TRY(up(w->attn_in_w, 3ull * E * E, &r_inw));
     AVS_TRY(up(w->attn_out_w, static_cast<size_t>(E) * E, &r_outw));
     AVS_TRY(up(w->scorer0_w, 64ull * E, &r_sc0));
@@ -308,6 +314,7 @@ avs_status pack_weights(avs_model* m, const avs_weights* w) {
         AVS_TRY(convert_f32(r_outw, m->out_w_l[l], static_cast<int64_t>(E) * E, dt, 0, st));
         AVS_TRY(convert_f32(r_sc0, m->sc0_w_l[l], 64ll * E, dt, 0, st));
     }
+    }   // !lstm_only
     // LSTM: gate-interleaved row order so that cluster CTA r owns 128 contiguous gate columns
     for (int i = 0; i < 4; ++i) {
         const int mod = i >> 1, dir = i & 1;
@@ -328,7 +335,7 @@ avs_status pack_weights(avs_model* m, const avs_weights* w) {
         AVS_TRY(convert_f32(m->ih_v_x, m->ih_v_l[l], 2ll * G4 * H, dt, 0, st));
         AVS_TRY(convert_f32(m->ih_a_x, m->ih_a_l[l], 2ll * G4 * H, dt, 0, st));
     }
-    AVS_CUDA(cudaStreamSynchronize(st));
+    if (sync) AVS_CUDA(cudaStreamSynchronize(st));
     return AVS_OK;
 }
 
@@ -619,6 +626,16 @@ avs_status avs_model_update(avs_model* m, const avs_weights* w) {
     m->heads = w->num_heads;
     Guard g(m->device);
     return pack_weights(m, w);
+}
+
+avs_status avs_model_update_async(avs_model* m, const avs_weights* w, int lstm_only, void* cuda_stream) {
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_TRY(check_dims(w));
+    AVS_CHECK(w->visual_dim == m->Dv && w->audio_dim == m->Da, AVS_ERR_INVALID,
+              "avs_model_update_async: feature dims differ from the handle's");
+    m->heads = w->num_heads;
+    Guard g(m->device);
+    return pack_weights(m, w, static_cast<cudaStream_t>(cuda_stream), lstm_only != 0, false);
 }
 
 void avs_model_destroy(avs_model* m) {

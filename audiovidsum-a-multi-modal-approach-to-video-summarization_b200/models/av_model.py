@@ -45,14 +45,17 @@ class AVBiLSTMModel(nn.Module):
         self.precision = precision
         self._native: Optional[NativeModel] = None
         self._native_key = None
+        self._native_lstm_key = None
         self._train_in_eval = False   # set to differentiate through an eval-mode (dropout-free) forward
 
     # ------------------------------------------------------------------ native handle
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
 
-    def native(self) -> NativeModel:
-        """The packed device copy of the current parameters (re-packed when they change)."""
+    def native(self, for_training: bool = False) -> NativeModel:
+        """The packed device copy of the current parameters (re-packed when they change).  ``for_training``: the
+        caller is the autograd forward, which reads only the recurrences' tensors through the handle -- those are
+        re-packed without a host synchronisation, the rest when an inference call next needs them."""
         p0 = next(self.parameters())
         if not p0.is_cuda:
             raise RuntimeError(
@@ -64,10 +67,15 @@ class AVBiLSTMModel(nn.Module):
                 self._native.close()
             self._native = NativeModel(self.state_dict(), self.visual_dim, self.audio_dim, self.hidden_dim,
                                        self.attention.num_heads, device=p0.device.index)
-            self._native_key = key
+            self._native_key = self._native_lstm_key = key
+        elif for_training:
+            if key != self._native_lstm_key:
+                self._native.update(self.state_dict(), lstm_only=True, sync=False)
+                self._native_lstm_key = key
+                self._native_key = None      # everything else in the handle is stale now
         elif key != self._native_key:
             self._native.update(self.state_dict())
-            self._native_key = key
+            self._native_key = self._native_lstm_key = key
         return self._native
 
     # ------------------------------------------------------------------ forward
@@ -130,7 +138,7 @@ class AVBiLSTMModel(nn.Module):
             raise RuntimeError("AVBiLSTMModel (avsum_b200) trains only on a CUDA sm_100 device; there is no CPU fallback")
         lens = [T] * B if lengths is None else [int(x) for x in lengths]
         starts = [b * T for b in range(B)]
-        nat = self.native()
+        nat = self.native(for_training=True)
         xv = visual.reshape(B * T, -1).to(torch.float32)
         xa = audio.reshape(B * T, -1).to(torch.float32)
         relu, drop = torch.relu, torch.nn.functional.dropout

@@ -130,11 +130,21 @@ class NativeModel:
         w.scorer2_w, w.scorer2_b = ptr("scorer.2.weight", (1, 64)), ptr("scorer.2.bias", (1,))
         return w, keep
 
-    def update(self, state_dict):
+    def update(self, state_dict, lstm_only: bool = False, sync: bool = True):
+        """Re-pack after the parameters changed.  ``sync=False`` queues the packing kernels on the current stream
+        and returns (the training loop: the optimiser step that changed the parameters ran on the same stream);
+        ``lstm_only`` re-packs just the recurrences' tensors, the only ones a training step reads through the handle."""
         w, keep = self._weights_struct(state_dict)
-        _cabi.check(self.lib.avs_model_update(self._handle, C.byref(w)))
-        torch.cuda.synchronize(self.device)
-        del keep
+        if sync and not lstm_only:
+            _cabi.check(self.lib.avs_model_update(self._handle, C.byref(w)))
+            torch.cuda.synchronize(self.device)
+        else:
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.avs_model_update_async(self._handle, C.byref(w), int(lstm_only),
+                                                            _stream_ptr(self.device)))
+                if sync:
+                    torch.cuda.synchronize(self.device)
+        del keep   # temporaries (non-fp32 / non-contiguous sources) are freed in stream order by torch's allocator
 
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:

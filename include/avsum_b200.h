@@ -89,6 +89,11 @@ int avs_device_ok(void);
 avs_status avs_model_create(const avs_weights* w, int device, avs_model** out);
 /* Re-pack after the caller changed parameters (load_state_dict / optimizer step). */
 avs_status avs_model_update(avs_model* m, const avs_weights* w);
+/* The same without a host synchronisation: the packing kernels are queued on `cuda_stream`, so the source tensors
+ * must not change before the stream gets there (true for parameters updated by work on the same stream -- the
+ * training loop of scripts/train_av_model.py:94-96).  lstm_only != 0 re-packs only the four recurrences' tensors,
+ * the only ones a training step reads through the handle (avs_bilstm_pair_train / _bwd). */
+avs_status avs_model_update_async(avs_model* m, const avs_weights* w, int lstm_only, void* cuda_stream);
 void avs_model_destroy(avs_model* m);
 
 /* Replaces AVBiLSTMModel.forward (av_model.py:33-46) for a batch of n_videos videos.
