@@ -779,3 +779,28 @@ def test_streamed_batches_equal_synchronous_calls(cuda_ready):
         nat.score_and_summarize_rows(b[0], b[1], b[2], b[3], b[4], None, b[5], 0.15, "literal_b1", slot=0)
     out = p.wait()
     assert torch.equal(out[1], want[0][1])
+
+
+def test_device_space_video_groups_are_bit_identical(native):
+    """The video-group pipeline (used for host-space calls; a tuning switch for device-resident inputs) only changes
+    WHEN kernels run: scores must equal the single-group run bit for bit, whatever the split."""
+    vids = sorted(synth.config2(), key=lambda v: -v.T)
+    lens = [v.T for v in vids]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    vd = torch.cat([v.visual for v in vids]).cuda()
+    ad = torch.cat([v.audio for v in vids]).cuda()
+    os.environ.pop("AVS_DEV_GROUPS", None)
+    want = native.forward_rows(vd, ad, starts, lens, "temporal", "tf32").clone()
+    try:
+        for groups, shares in (("2", None), ("3", "20,70,100"), ("6", None)):
+            os.environ["AVS_DEV_GROUPS"] = groups
+            if shares:
+                os.environ["AVS_DEV_SHARES"] = shares
+            else:
+                os.environ.pop("AVS_DEV_SHARES", None)
+            got = native.forward_rows(vd, ad, starts, lens, "temporal", "tf32")
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), (groups, shares)
+    finally:
+        os.environ.pop("AVS_DEV_GROUPS", None)
+        os.environ.pop("AVS_DEV_SHARES", None)
