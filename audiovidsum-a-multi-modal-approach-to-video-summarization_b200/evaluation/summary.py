@@ -91,10 +91,14 @@ def summarize_stream(model, batches, proportion=0.15, attn_axis: Optional[str] =
     pending = []
     slot = 0
     for visual, audio, positions, row_start, lengths, shots in batches:
+        if depth == 1:     # nothing to overlap with: the synchronous call pipelines its own video groups more finely
+            yield nat.score_and_summarize_rows(visual, audio, positions, row_start, lengths, None, shots,
+                                               proportion, axis, model.precision)
+            continue
         if len(pending) == depth:
             yield pending.pop(0).wait()
         pending.append(nat.score_and_summarize_rows(visual, audio, positions, row_start, lengths, None, shots,
                                                     proportion, axis, model.precision, slot=slot))
-        slot = (slot + 1) % 2 if depth == 2 else 0
+        slot = (slot + 1) % 2
     while pending:
         yield pending.pop(0).wait()
