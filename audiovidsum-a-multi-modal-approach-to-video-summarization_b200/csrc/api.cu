@@ -285,36 +285,36 @@ avs_status pack_weights(avs_model* m, const avs_weights* w, cudaStream_t st = 0,
         AVS_TRY(up(w->lstm_b_hh[i], G4, &r_bhh[i]));
     }
     if (!lstm_only) {
-    AVS_TRY(up(w->attn_in_w, 3ull * E * E, &r_inw));
-    AVS_TRY(up(w->attn_out_w, static_cast<size_t>(E) * E, &r_outw));
-    AVS_TRY(up(w->scorer0_w, 64ull * E, &r_sc0));
-    // direct (unpacked) small tensors
-    AVS_CUDA(cudaMemcpyAsync(m->fc_v_b, w->visual_fc_b, H * sizeof(float), cudaMemcpyDefault, st));
-    AVS_CUDA(cudaMemcpyAsync(m->fc_a_b, w->audio_fc_b, H * sizeof(float), cudaMemcpyDefault, st));
-    AVS_CUDA(cudaMemcpyAsync(m->in_b, w->attn_in_b, 3 * E * sizeof(float), cudaMemcpyDefault, st));
-    AVS_CUDA(cudaMemcpyAsync(m->out_b, w->attn_out_b, E * sizeof(float), cudaMemcpyDefault, st));
-    AVS_CUDA(cudaMemcpyAsync(m->sc0_b, w->scorer0_b, 64 * sizeof(float), cudaMemcpyDefault, st));
-    AVS_CUDA(cudaMemcpyAsync(m->sc2_w, w->scorer2_w, 64 * sizeof(float), cudaMemcpyDefault, st));
-    AVS_CUDA(cudaMemcpyAsync(m->sc2_b, w->scorer2_b, sizeof(float), cudaMemcpyDefault, st));
-    // exact + tf32 copies of the GEMM weights
-    auto both = [&](const float* raw, size_t n, float* exact, float* tf) -> avs_status {
-        AVS_CUDA(cudaMemcpyAsync(exact, raw, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        return convert_f32(raw, tf, static_cast<int64_t>(n), DT_F32, 1, st);
-    };
-    AVS_TRY(both(r_fcv, static_cast<size_t>(H) * Dv, m->fc_v_w_x, m->fc_v_w_t));
-    AVS_TRY(both(r_fca, static_cast<size_t>(H) * Da, m->fc_a_w_x, m->fc_a_w_t));
-    AVS_TRY(both(r_inw, 3ull * E * E, m->in_w_x, m->in_w_t));
-    AVS_TRY(both(r_outw, static_cast<size_t>(E) * E, m->out_w_x, m->out_w_t));
-    AVS_TRY(both(r_sc0, 64ull * E, m->sc0_w_x, m->sc0_w_t));
-    for (int l = 0; l < 2; ++l) {
-        const int dt = l ? DT_BF16 : DT_F16;
-        AVS_TRY(convert_f32(r_fcv, m->fc_v_w_l[l], static_cast<int64_t>(H) * Dv, dt, 0, st));
-        AVS_TRY(convert_f32(r_fca, m->fc_a_w_l[l], static_cast<int64_t>(H) * Da, dt, 0, st));
-        AVS_TRY(convert_f32(r_inw, m->in_w_l[l], 3ll * E * E, dt, 0, st));
-        AVS_TRY(convert_f32(r_outw, m->out_w_l[l], static_cast<int64_t>(E) * E, dt, 0, st));
-        AVS_TRY(convert_f32(r_sc0, m->sc0_w_l[l], 64ll * E, dt, 0, st));
+        AVS_TRY(up(w->attn_in_w, 3ull * E * E, &r_inw));
+        AVS_TRY(up(w->attn_out_w, static_cast<size_t>(E) * E, &r_outw));
+        AVS_TRY(up(w->scorer0_w, 64ull * E, &r_sc0));
+        // direct (unpacked) small tensors
+        AVS_CUDA(cudaMemcpyAsync(m->fc_v_b, w->visual_fc_b, H * sizeof(float), cudaMemcpyDefault, st));
+        AVS_CUDA(cudaMemcpyAsync(m->fc_a_b, w->audio_fc_b, H * sizeof(float), cudaMemcpyDefault, st));
+        AVS_CUDA(cudaMemcpyAsync(m->in_b, w->attn_in_b, 3 * E * sizeof(float), cudaMemcpyDefault, st));
+        AVS_CUDA(cudaMemcpyAsync(m->out_b, w->attn_out_b, E * sizeof(float), cudaMemcpyDefault, st));
+        AVS_CUDA(cudaMemcpyAsync(m->sc0_b, w->scorer0_b, 64 * sizeof(float), cudaMemcpyDefault, st));
+        AVS_CUDA(cudaMemcpyAsync(m->sc2_w, w->scorer2_w, 64 * sizeof(float), cudaMemcpyDefault, st));
+        AVS_CUDA(cudaMemcpyAsync(m->sc2_b, w->scorer2_b, sizeof(float), cudaMemcpyDefault, st));
+        // exact + tf32 copies of the GEMM weights
+        auto both = [&](const float* raw, size_t n, float* exact, float* tf) -> avs_status {
+            AVS_CUDA(cudaMemcpyAsync(exact, raw, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            return convert_f32(raw, tf, static_cast<int64_t>(n), DT_F32, 1, st);
+        };
+        AVS_TRY(both(r_fcv, static_cast<size_t>(H) * Dv, m->fc_v_w_x, m->fc_v_w_t));
+        AVS_TRY(both(r_fca, static_cast<size_t>(H) * Da, m->fc_a_w_x, m->fc_a_w_t));
+        AVS_TRY(both(r_inw, 3ull * E * E, m->in_w_x, m->in_w_t));
+        AVS_TRY(both(r_outw, static_cast<size_t>(E) * E, m->out_w_x, m->out_w_t));
+        AVS_TRY(both(r_sc0, 64ull * E, m->sc0_w_x, m->sc0_w_t));
+        for (int l = 0; l < 2; ++l) {
+            const int dt = l ? DT_BF16 : DT_F16;
+            AVS_TRY(convert_f32(r_fcv, m->fc_v_w_l[l], static_cast<int64_t>(H) * Dv, dt, 0, st));
+            AVS_TRY(convert_f32(r_fca, m->fc_a_w_l[l], static_cast<int64_t>(H) * Da, dt, 0, st));
+            AVS_TRY(convert_f32(r_inw, m->in_w_l[l], 3ll * E * E, dt, 0, st));
+            AVS_TRY(convert_f32(r_outw, m->out_w_l[l], static_cast<int64_t>(E) * E, dt, 0, st));
+            AVS_TRY(convert_f32(r_sc0, m->sc0_w_l[l], 64ll * E, dt, 0, st));
+        }
     }
-    }   // !lstm_only
     // LSTM: gate-interleaved row order so that cluster CTA r owns 128 contiguous gate columns
     for (int i = 0; i < 4; ++i) {
         const int mod = i >> 1, dir = i & 1;
