@@ -804,3 +804,30 @@ def test_device_space_video_groups_are_bit_identical(native):
     finally:
         os.environ.pop("AVS_DEV_GROUPS", None)
         os.environ.pop("AVS_DEV_SHARES", None)
+
+
+def test_handle_follows_the_parameters_through_training_and_back_to_eval(cuda_ready):
+    """A training step re-packs only the recurrences' tensors in the native handle (without synchronising); the next
+    eval-mode forward must see EVERY updated parameter -- and a second training step the updated LSTM weights."""
+    vid = synth.make_video(64, 1024, 128, 777)
+    xv, xa = vid.visual[None].cuda(), vid.audio[None].cuda()
+    m = make_model(spread=True, attn_axis="literal_b1")
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)     # a step large enough to move the scores well beyond 1e-3
+    with torch.no_grad():
+        before = m.eval()(xv, xa).clone()
+    for _ in range(2):
+        m.train()
+        for seq in (m.visual_fc, m.audio_fc):
+            seq[2].p = 0.0
+        loss = ((m(xv, xa) - 0.9) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    m.eval()
+    with torch.no_grad():
+        got = m(xv, xa)
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
+    port.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    want = av_oracle_torch.run_videos(port, [(vid.visual, vid.audio)], "literal")[0]
+    assert float((got.cpu() - before.cpu()).abs().max()) > 5e-3, "the optimiser steps did not move the scores"
+    assert rel(got.cpu().numpy(), want.numpy()) < REL_TOL["tf32"]
