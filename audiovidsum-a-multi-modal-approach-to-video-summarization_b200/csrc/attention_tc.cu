@@ -36,7 +36,7 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_K = Q_BYTES;
 constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
 constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
-constexpr int N_BARS = 1 + 4 + 4 + 2 + 2 + 1;  // q, k_full/empty[2], v_full/empty[2], s[2], p[2], o
+constexpr int N_BARS = 1 + 4 + 4 + 2 + 2 + 1 + 1;  // q, k_full/empty[2], v_full/empty[2], s[2], p[2], o, done
 constexpr int SMEM_TOTAL = 1024 + OFF_BAR + N_BARS * 8 + 16;
 constexpr int ATT_THREADS = 192;
 constexpr uint32_t TM_O = 0, TM_S = 256;       // TMEM column offsets
@@ -83,6 +83,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
     uint64_t* bar_s = bars + 9;
     uint64_t* bar_p = bars + 11;
     uint64_t* bar_o = bars + 13;
+    uint64_t* bar_done = bars + 14;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,6 +99,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
             mbar_init(bar_p + i, 128);
         }
         mbar_init(bar_o, 1);
+        mbar_init(bar_done, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -168,6 +170,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
                 tc_commit(v_empty + st);
                 tc_commit(bar_o);          // phase j: O includes blocks 0..j
             }
+            tc_commit(bar_done);           // every product has retired: O is final
         }
         __syncwarp();
     } else {
@@ -243,7 +246,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, SeqDesc seqs, in
             mbar_arrive(bar_p + st);
         }
         // ---- epilogue: O / l -> ctx
-        mbar_wait(bar_o, (nblk - 1) & 1);
+        // bar_o completes one phase per key block and a parity wait can only tell ADJACENT phases apart: a warp
+        // that runs ahead of the slowest warp finishes its last block while P_{n-2} V_{n-2} may not even have been
+        // issued (the MMA thread still waits for the slow warp's P_{n-2}), and a wait on the last phase's parity
+        // would pass at once on the parity of phase n-3.  The end of the last product therefore has its own barrier.
+        mbar_wait(bar_done, 0);
         tc_fence_after();
         const float inv_l = 1.0f / l;
         const bool row_ok = row < len;

@@ -831,3 +831,25 @@ def test_handle_follows_the_parameters_through_training_and_back_to_eval(cuda_re
     want = av_oracle_torch.run_videos(port, [(vid.visual, vid.audio)], "literal")[0]
     assert float((got.cpu() - before.cpu()).abs().max()) > 5e-3, "the optimiser steps did not move the scores"
     assert rel(got.cpu().numpy(), want.numpy()) < REL_TOL["tf32"]
+
+
+def test_attention_core_is_repeatable_under_concurrent_load(cuda_ready):
+    """Regression test for a barrier-phase aliasing bug: with another kernel sharing the SMs, a softmax warp could run
+    a whole key block ahead of the slowest warp and pass the final "O complete" parity wait two phases early
+    (32-row blocks of wrong context, ~8 % of launches under load).  Every launch must reproduce the first bit for bit."""
+    vids = sorted(synth.config2(), key=lambda v: -v.T)[:30]
+    lens = [v.T for v in vids]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    g = torch.Generator().manual_seed(5)
+    qkv = (torch.randn(int(sum(lens)), 3072, generator=g) * 0.5).cuda()
+    side = torch.cuda.Stream()
+    a = torch.randn(4096, 4096, device="cuda")
+    ones = np.ones_like(starts)
+    ref = runtime.attention(qkv, 1024, 4, starts, ones, lens).clone()
+    for i in range(120):
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                torch.mm(a, a)
+        out = runtime.attention(qkv, 1024, 4, starts, ones, lens)
+        assert torch.equal(out, ref), f"launch {i} differs from the first"
+    torch.cuda.synchronize()
