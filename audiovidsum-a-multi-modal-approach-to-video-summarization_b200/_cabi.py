@@ -30,7 +30,7 @@ EXPORTS = [
     "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
     "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
     "avs_debug_e2e_trace", "avs_forward_summarize_async", "avs_slot_wait",
-    "avs_debug_gemm_trace", "avs_model_update_async",
+    "avs_debug_gemm_trace", "avs_model_update_async", "avs_host_alloc", "avs_host_free",
 ]
 
 
@@ -94,6 +94,10 @@ def lib() -> C.CDLL:
     L.avs_model_update.argtypes = [vp, C.POINTER(AvsWeights)]
     L.avs_model_update_async.restype = C.c_int
     L.avs_model_update_async.argtypes = [vp, C.POINTER(AvsWeights), C.c_int, vp]
+    L.avs_host_alloc.restype = C.c_int
+    L.avs_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t, C.c_int]
+    L.avs_host_free.restype = C.c_int
+    L.avs_host_free.argtypes = [vp]
     L.avs_model_destroy.restype = None
     L.avs_model_destroy.argtypes = [vp]
     L.avs_forward.restype = C.c_int

@@ -523,6 +523,21 @@ avs_status avs_debug_e2e_trace(double* out20) {
     return AVS_OK;
 }
 
+/* Page-locked host memory for the batches a caller feeds to the host-space entry points.  write_combined != 0 asks
+ * for write-combined pages: the CPU should only WRITE them (reads are uncached and slow), and device reads across
+ * PCIe do not snoop the CPU caches. */
+avs_status avs_host_alloc(void** out, size_t bytes, int write_combined) {
+    AVS_CHECK(out != nullptr, AVS_ERR_INVALID, "null pointer");
+    *out = nullptr;
+    if (bytes == 0) return AVS_OK;
+    AVS_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return AVS_OK;
+}
+avs_status avs_host_free(void* p) {
+    if (p != nullptr) AVS_CUDA(cudaFreeHost(p));
+    return AVS_OK;
+}
+
 int avs_device_ok(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

@@ -30,6 +30,40 @@ def _i32(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 
 
+class _HostBlock:
+    """Owner of one avs_host_alloc allocation (freed when the last tensor view of it dies)."""
+
+    def __init__(self, nbytes: int, write_combined: bool):
+        self.ptr = C.c_void_p()
+        _cabi.check(_cabi.lib().avs_host_alloc(C.byref(self.ptr), nbytes, int(write_combined)))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _cabi.lib().avs_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_like(t: torch.Tensor, write_combined: bool = False) -> torch.Tensor:
+    """A page-locked host copy of ``t`` allocated by the library (``avs_host_alloc``).  ``write_combined`` pages are
+    meant for buffers the CPU only writes (a loader packing batches): device reads across PCIe skip the CPU-cache
+    snoop, which matters when several GPUs of one box stream from host memory at once."""
+    _require_cuda()
+    src = t.detach().contiguous().cpu()
+    nbytes = src.numel() * src.element_size()
+    if nbytes == 0:
+        return src.pin_memory()
+    blk = _HostBlock(nbytes, write_combined)
+    buf = (C.c_byte * nbytes).from_address(blk.ptr.value)
+    out = torch.frombuffer(buf, dtype=src.dtype).reshape(src.shape)
+    out._avs_block = blk            # keeps the allocation alive as long as this tensor object
+    out.copy_(src)
+    return out
+
+
 class ShotDesc:
     """Host descriptors of the shots of a batch, packed once (by the loader) instead of on every call:
     ``n_frames`` int32 [n], ``cps`` int32 [sum S, 2] (inclusive change points), ``cps_start`` int32 [n + 1],

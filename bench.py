@@ -206,10 +206,16 @@ def main():
     model = model.to(dev)
     nat = model.native()
 
-    visual_h = torch.cat([v.visual for v in vids]).pin_memory()
-    audio_h = torch.cat([v.audio for v in vids]).pin_memory()
+    # pinned host batch, as a loader packs it.  AVS_BENCH_WC=1: write-combined pages (runtime.pinned_like)
+    from avsum_b200 import runtime as _rt
+    if os.environ.get("AVS_BENCH_WC"):
+        visual_h = _rt.pinned_like(torch.cat([v.visual for v in vids]), write_combined=True)
+        audio_h = _rt.pinned_like(torch.cat([v.audio for v in vids]), write_combined=True)
+    else:
+        visual_h = torch.cat([v.visual for v in vids]).pin_memory()
+        audio_h = torch.cat([v.audio for v in vids]).pin_memory()
     pos_h = torch.from_numpy(np.concatenate([v.positions for v in vids]).astype(np.int32)).pin_memory()
-    visual_d, audio_d, pos_d = visual_h.to(dev), audio_h.to(dev), pos_h.to(dev)
+    visual_d, audio_d, pos_d = torch.cat([v.visual for v in vids]).to(dev), torch.cat([v.audio for v in vids]).to(dev), pos_h.to(dev)
     n_frames = [v.n_frames for v in vids]
     cps_list = [v.cps for v in vids]
     from avsum_b200.evaluation.summary import summarize_stream

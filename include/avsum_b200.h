@@ -24,6 +24,7 @@
 #ifndef AVSUM_B200_H
 #define AVSUM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -244,6 +245,11 @@ void avs_profile_read(double* ms, int64_t* calls);
  * (h landed -> MMAs issued -> epilogue awake -> tcgen05.ld -> cell math -> fence+barrier -> copies issued ->
  * next h landed), out8[7] = number of steps. */
 avs_status avs_debug_lstm_trace(uint64_t* out8);
+
+/* Page-locked host buffers for the host-space entry points (the features a loader packs).  write_combined != 0:
+ * write-combined pages -- the CPU should only write them; device reads across PCIe then do not snoop CPU caches. */
+avs_status avs_host_alloc(void** out, size_t bytes, int write_combined);
+avs_status avs_host_free(void* p);
 
 /* Debugging aid: clock64 totals of the tensor-core GEMM pipeline (block 0) since the last read, recorded when the
  * environment variable AVS_GEMM_TRACE is set: out8[0] MMA thread span, [1] MMA waiting for operands, [2] MMA waiting
