@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavsum_b200.so")
+# AVS_LIB_PATH: load another build of the same library (A/B timing of kernel changes, tools/ab_lib.py)
+LIB_PATH = os.environ.get("AVS_LIB_PATH") or os.path.join(_HERE, "libavsum_b200.so")
 
 AVS_OK, AVS_ERR_INVALID, AVS_ERR_UNSUPPORTED, AVS_ERR_CUDA, AVS_ERR_OOM = range(5)
 AVS_HOST, AVS_DEVICE = 0, 1

@@ -256,12 +256,20 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         // ------------------------------------------------------------------ MMA issuer (one thread per chain)
         if (elect_one()) {
             const uint32_t idesc = umma_idesc(op_dtype == DT_BF16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, COLS, NB);
+            // The h operand descriptor of (buffer b, K block k) differs from that of (0, 0) only in its start-address
+            // field (low word, address >> 4), so the issue path after the wait is one add per MMA: everything the
+            // thread executes between "h has landed" and the 16th MMA is on the step's critical path (it used to
+            // rebuild all 16 descriptors there, ~100 scalar instructions).
+            const uint64_t d00 = umma_desc_noswz_kmajor(smem_u32(h_sm), S::H_LBO, 128);
+            const uint32_t d_hi = static_cast<uint32_t>(d00 >> 32), d_lo00 = static_cast<uint32_t>(d00);
+            constexpr uint32_t D_BUF = S::H_BYTES >> 4, D_K = (2 * S::H_LBO) >> 4;
             for (int s = 0; s < maxlen; ++s) {
                 const int b = s & 1;
+                const uint32_t d_lo = d_lo00 + b * D_BUF;
                 // arm the barrier that will collect h_{s+1}: 8 peers x SLICE_BYTES, one local arrival
                 if (s + 1 < maxlen) mbar_expect_tx(bar_h + (b ^ 1), CL * CHAIN_SLOTS * 64);   // 8 peers x 64 B per real video slot
                 if (s > 0) {
-                    mbar_wait_cluster(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
+                    mbar_wait_lean(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
                     fence_proxy_async();   // peers' st.async (generic proxy) -> visible to the tensor core's reads
                 }
                 tc_fence_after();
@@ -271,12 +279,9 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                     tA = clk64();
                     if (s > 0) tr_acc[6] += tA - tr_ts[1];   // copies issued -> all 8 slices of h landed
                 }
-                const uint32_t h_addr = smem_u32(h_sm + b * S::H_BYTES);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {  // K = 256 = 16 x 16; A from TMEM (8 columns per K step)
-                    const uint64_t bd = umma_desc_noswz_kmajor(h_addr + k * 2 * S::H_LBO, S::H_LBO, 128);
-                    umma_f16_ts(tmem_d, tmem_w + k * 8, bd, idesc, k != 0);
-                }
+                for (int k = 0; k < 16; ++k)   // K = 256 = 16 x 16; A from TMEM (8 columns per K step)
+                    umma_f16_ts_lohi(tmem_d, tmem_w + k * 8, d_lo + k * D_K, d_hi, idesc, k != 0);
                 tc_commit(bar_mma);
                 if (tr) {
                     const long long tB = clk64();
@@ -349,7 +354,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 xv2[k] = zero4;
                 if (s + 2 < len_r[k]) xv2[k] = __ldg(xg4 + static_cast<size_t>(row_r[k] + 2 * rstep) * XG_LD4);
             }
-            mbar_wait(bar_mma, s & 1);
+            mbar_wait_lean(bar_mma, s & 1);
             tc_fence_after();
             long long tC = 0, tD = 0;
             if (tracing && tid == 0) {

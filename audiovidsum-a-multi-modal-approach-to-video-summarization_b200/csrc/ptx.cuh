@@ -64,6 +64,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread in hardware; test_wait never does)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if (++spins > AVS_SPIN_LIMIT) {
+            printf("avsum_b200: mbarrier spin timed out (block %d,%d thread %d parity %u)\n", blockIdx.x,
+                   blockIdx.y, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+// Wait whose time-out path is a bare trap: a printf there is a function call, and a possible call inside a hot
+// loop makes the compiler re-materialise every uniform register after the wait (on the step's critical path).
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > AVS_SPIN_LIMIT) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -169,6 +201,23 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "}\n"
         :
         : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The same with the shared-memory descriptor passed as two 32-bit halves: a caller that steps through K keeps the
+// (constant) high word and adds to the low word (start address >> 4) -- one integer add per MMA instead of
+// rebuilding the 64-bit descriptor.
+__device__ __forceinline__ void umma_f16_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 d;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
