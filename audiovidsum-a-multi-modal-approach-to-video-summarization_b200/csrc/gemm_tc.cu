@@ -460,7 +460,9 @@ __device__ __forceinline__ void mbar_wait_cluster_acq(uint64_t* bar, uint32_t pa
             : "memory");
         if (ok) break;
         if (++spins > AVS_SPIN_LIMIT) {
+#ifdef AVS_DEBUG_WAITS
             printf("avsum_b200: gemm accumulator wait timed out (block %d parity %u)\n", blockIdx.x, parity);
+#endif
             __trap();
         }
     }

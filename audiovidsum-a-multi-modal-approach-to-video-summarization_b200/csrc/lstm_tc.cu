@@ -84,28 +84,6 @@ __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, const uin
                  "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster_addr)
                  : "memory");
 }
-// mbarrier wait with acquire at cluster scope (pairs with the release of remote st.async complete_tx)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    const uint32_t addr = smem_u32(bar);
-    while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, P;\n\t"
-            "}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (++spins > AVS_SPIN_LIMIT) {
-            printf("avsum_b200: lstm h-exchange wait timed out (block %d parity %u)\n", blockIdx.x, parity);
-            __trap();
-        }
-    }
-}
-
 // K-major, no swizzle: start address, LBO = K-direction core-matrix stride, SBO = 8-row-group stride.
 __device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -269,7 +247,11 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 // arm the barrier that will collect h_{s+1}: 8 peers x SLICE_BYTES, one local arrival
                 if (s + 1 < maxlen) mbar_expect_tx(bar_h + (b ^ 1), CL * CHAIN_SLOTS * 64);   // 8 peers x 64 B per real video slot
                 if (s > 0) {
-                    mbar_wait_lean(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
+                    // CTA-scope acquire: the payload is shared memory written by the peers' st.async, whose
+                    // complete_tx is performed after the data has landed; the reader is the tensor core behind the
+                    // proxy fence below.  (acquire.cluster adds a CCTL.IVALL -- an L1 invalidation that protects
+                    // nothing here -- to every step.)
+                    mbar_wait(bar_h + b, b ? ((s >> 1) & 1) : (((s >> 1) + 1) & 1));
                     fence_proxy_async();   // peers' st.async (generic proxy) -> visible to the tensor core's reads
                 }
                 tc_fence_after();
@@ -354,7 +336,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 xv2[k] = zero4;
                 if (s + 2 < len_r[k]) xv2[k] = __ldg(xg4 + static_cast<size_t>(row_r[k] + 2 * rstep) * XG_LD4);
             }
-            mbar_wait_lean(bar_mma, s & 1);
+            mbar_wait(bar_mma, s & 1);
             tc_fence_after();
             long long tC = 0, tD = 0;
             if (tracing && tid == 0) {

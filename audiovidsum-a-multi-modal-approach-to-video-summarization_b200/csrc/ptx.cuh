@@ -64,44 +64,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// non-blocking probe (try_wait may suspend the thread in hardware; test_wait never does)
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_test_wait(bar, parity)) {
-        if (++spins > AVS_SPIN_LIMIT) {
-            printf("avsum_b200: mbarrier spin timed out (block %d,%d thread %d parity %u)\n", blockIdx.x,
-                   blockIdx.y, threadIdx.x, parity);
-            __trap();
-        }
-    }
-}
-// Wait whose time-out path is a bare trap: a printf there is a function call, and a possible call inside a hot
-// loop makes the compiler re-materialise every uniform register after the wait (on the step's critical path).
-__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > AVS_SPIN_LIMIT) __trap();
-    }
-}
+// Bounded spin on a phase parity.  The time-out path is a bare trap (compile with -DAVS_DEBUG_WAITS for a message
+// naming the block / thread): a printf there is a function call, and a possible call inside a hot loop makes the
+// compiler re-materialise every uniform register after the wait -- on the LSTM recurrence that was ~100 scalar
+// instructions on each step's critical path.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > AVS_SPIN_LIMIT) {
+#ifdef AVS_DEBUG_WAITS
             printf("avsum_b200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x,
                    blockIdx.y, threadIdx.x, parity);
+#endif
             __trap();
         }
     }

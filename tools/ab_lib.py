@@ -36,6 +36,17 @@ for n in [int(x) for x in sys.argv[1:]]:
     ms = st["lstm_recurrence"][0] / 20
     print(f"  {n:3d} videos: lstm {ms:.4f} ms = {ms * 1e3 / max(lens):.4f} us/step, forward {e0.elapsed_time(e1) / 20:.4f} ms, "
           f"checksum {float(out.double().sum()):.9f}", flush=True)
+    if n == 50:
+        print("      stages (ms): " + ", ".join(f"{k} {v[0] / 20:.4f}" for k, v in st.items() if v[1]), flush=True)
+        for _ in range(3):
+            out = nat.forward_rows(v, a, starts, lens, "temporal", "tf32")
+        torch.cuda.synchronize()
+        _cabi.profile(2)
+        for _ in range(20):
+            out = nat.forward_rows(v, a, starts, lens, "temporal", "tf32")
+        st = _cabi.profile_read(); _cabi.profile(0)
+        print("      temporal stages (ms): " + ", ".join(f"{k} {v[0] / 20:.4f}" for k, v in st.items() if v[1])
+              + f", checksum {float(out.double().sum()):.9f}", flush=True)
 ''' % ROOT
 
 other = os.path.abspath(sys.argv[1])
