@@ -1507,7 +1507,8 @@ static avs_status bilstm_pair_impl(avs_model* m, const float* v_emb, const float
         xv = rv;
         xa = ra;
     }
-    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.host.data(), plan.host.size() * 4, cudaMemcpyHostToDevice, st));
+    // kernel-parameter upload: no pageable-memory copy (host-blocking, and not capturable in a CUDA graph)
+    AVS_TRY(upload_small(plan_dev, plan.host.data(), plan.host.size() * 4, st));
     const GemmW w_ih_v{m->ih_v_x, m->ih_v_t, m->ih_v_l}, w_ih_a{m->ih_a_x, m->ih_a_t, m->ih_a_l};
     GemmEpilogue e2;
     e2.ldc = 2 * G4;
@@ -1661,7 +1662,7 @@ avs_status avs_bilstm_pair_bwd(avs_model* m, const float* d_fused, const float* 
     float* wih_t = m->ws.take<float>(static_cast<size_t>(H) * 2 * G4);
     float* db_tmp = m->ws.take<float>(2 * G4);
     int32_t* plan_dev = m->ws.take<int32_t>(plan.size());
-    AVS_CUDA(cudaMemcpyAsync(plan_dev, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice, st));
+    AVS_TRY(upload_small(plan_dev, plan.data(), plan.size() * 4, st));
     AVS_CUDA(cudaMemsetAsync(d_xg_v, 0, 2 * uR * 2 * G4 * 4 + 256, st));   // rows no video owns contribute nothing
 
     LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, n_groups, nb};

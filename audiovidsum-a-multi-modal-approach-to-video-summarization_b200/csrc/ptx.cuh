@@ -194,7 +194,6 @@ __device__ __forceinline__ void umma_f16_ts_lohi(uint32_t tmem_d, uint32_t tmem_
         : "r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

@@ -601,6 +601,53 @@ def test_training_step_matches_reference_autograd(cuda_ready):
     assert float((out2 - out).abs().max()) > 0
 
 
+def test_graphed_training_step_equals_eager_steps(cuda_ready):
+    """training.GraphedTrainStep (forward + loss + backward + AdamW captured in one CUDA graph, replayed per batch)
+    follows the same parameter trajectory as the eager loop of scripts/train_av_model.py:86-96: the losses of five
+    consecutive steps on changing batches and the final parameters agree (dropout p = 0 on both sides)."""
+    from avsum_b200 import training
+    g = torch.Generator().manual_seed(7)
+    batches = [(torch.randn(4, 64, 1024, generator=g).cuda(), torch.randn(4, 64, 128, generator=g).cuda(),
+                torch.rand(4, 64, generator=g).cuda()) for _ in range(5)]
+    losses, finals = {}, {}
+    for mode in ("eager", "graph"):
+        m = make_model(spread=True, attn_axis="literal_b1").train()
+        m.visual_fc[2].p = 0.0
+        m.audio_fc[2].p = 0.0
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-3, capturable=True)
+        out = []
+        if mode == "graph":
+            # the warm-up steps inside the constructor train on the first batch: give the eager loop the same start
+            step = training.GraphedTrainStep(m, opt, torch.nn.functional.mse_loss, *batches[0], warmup=3)
+            out.append(float(step(*batches[0])))          # = the capture-time step replayed once: 5th step on batch 0
+            for v, a, t in batches[1:]:
+                out.append(float(step(v, a, t)))
+        else:
+            def eager(v, a, t):
+                opt.zero_grad(set_to_none=True)
+                loss = torch.nn.functional.mse_loss(m(v, a), t)
+                loss.backward()
+                opt.step()
+                return float(loss)
+            for _ in range(4):                            # 3 warm-up steps + the step executed during capture
+                eager(*batches[0])
+            out.append(eager(*batches[0]))
+            for v, a, t in batches[1:]:
+                out.append(eager(v, a, t))
+        losses[mode] = out
+        finals[mode] = {k: p.detach().clone() for k, p in m.named_parameters()}
+    print(losses)
+    for le, lg in zip(losses["eager"], losses["graph"]):
+        assert abs(le - lg) <= 1e-5 * abs(le), losses
+    for k in finals["eager"]:
+        assert float((finals["eager"][k] - finals["graph"][k]).abs().max()) <= 1e-5, k
+    # and the handle follows the graph-updated parameters back to eval
+    m.eval()
+    with torch.no_grad():
+        s = m(batches[0][0], batches[0][1])
+    assert s.shape == (4, 64) and bool(torch.isfinite(s).all())
+
+
 def test_training_rejects_unsupported_attention(cuda_ready):
     m = make_model(attn_axis="temporal").train()
     with pytest.raises(NotImplementedError):

@@ -1,7 +1,7 @@
 """A/B of two builds of libavsum_b200.so on the same box: runs tools/lstm_scaling.py-style timings (per-stage CUDA
 events inside the library) once per library, alternating, in fresh processes.
 
-    python tools/ab_lib.py build/libavsum_b200_old.so [n_videos ...]
+    python tools/ab_lib.py build/libavsum_b200_old.so [more.so ...] [n_videos ...]
 """
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -49,10 +49,10 @@ for n in [int(x) for x in sys.argv[1:]]:
               + f", checksum {float(out.double().sum()):.9f}", flush=True)
 ''' % ROOT
 
-other = os.path.abspath(sys.argv[1])
-ns = sys.argv[2:] or ["1", "8", "50"]
+others = [os.path.abspath(a) for a in sys.argv[1:] if a.endswith(".so")]
+ns = [a for a in sys.argv[1:] if not a.endswith(".so")] or ["1", "8", "50"]
 for rep in range(2):
-    for name, path in (("old", other), ("new", None)):
+    for name, path in [(os.path.basename(o), o) for o in others] + [("in-tree", None)]:
         env = dict(os.environ)
         env.pop("AVS_LIB_PATH", None)
         if path:

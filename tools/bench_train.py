@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--videos", type=int, default=8)
     ap.add_argument("--frames", type=int, default=320)
     ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (training.GraphedTrainStep)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -50,10 +51,16 @@ def main():
     model = AVBiLSTMModel(1024, 128, 512, attn_axis="literal_b1")
     model.load_state_dict(synth.seeded_state_dict())
     model = model.to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=args.graph)
     n_params = sum(p.numel() for p in model.parameters())
+    graphed = None
+    if args.graph:
+        graphed = training.GraphedTrainStep(model, opt, torch.nn.functional.mse_loss, visual, audio, target,
+                                            allreduce=world > 1, warmup=max(args.warmup, 3))
 
     def step():
+        if graphed is not None:
+            return graphed(visual, audio, target)
         preds = model(visual, audio)
         loss = torch.nn.functional.mse_loss(preds, target)
         opt.zero_grad(set_to_none=True)
@@ -82,7 +89,7 @@ def main():
         flops = 3 * (15_990_912) * B * T * world      # forward + ~2x backward (SURVEY 8d per-frame figure, literal mode)
         line = {"config": f"config5: {B} videos/GPU x T={T}, train mode (dropout 0.3), mse_loss, AdamW lr 1e-4, "
                           f"{n_params} parameters, flat fp32 gradient all-reduce ({n_params * 4 / 1e6:.1f} MB)",
-                "n_gpus": world, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "frames_per_s": B * T * world / (ms * 1e-3),
+                "n_gpus": world, "cuda_graph": bool(args.graph), "ms_per_step": ms, "steps_per_s": 1e3 / ms, "frames_per_s": B * T * world / (ms * 1e-3),
                 "approx_tflops": flops / (ms * 1e-3) / 1e12, "final_loss": float(loss)}
         if args.cpu_baseline and world == 1:
             import torch.nn as nn
