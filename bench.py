@@ -354,7 +354,7 @@ def main():
     drec = kernels[dom]
     # DRAM traffic per launch of the dominant kernel, from the committed ncu --set full capture of this workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01d_traffic.json")
     if world == 1 and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom)
     if "tflops" in drec:
