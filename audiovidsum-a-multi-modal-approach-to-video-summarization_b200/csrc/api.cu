@@ -1624,9 +1624,12 @@ avs_status avs_bilstm_pair_bwd(avs_model* m, const float* d_fused, const float* 
         if (lengths[b] > 0) order.push_back(b);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lengths[a] > lengths[b]; });
     const int B = static_cast<int>(order.size());
+    // Videos per cluster: as few as still fit the batch into ONE wave of clusters (4 recurrences x 8 CTAs per group,
+    // one CTA per SM: at most 4 groups on 148 SMs).  A CTA's work per step grows with its videos (128 FMAs per
+    // thread and video), so 8 videos as 4 groups of 2 on 128 SMs undo a step ~3x faster than 1 group of 8 on 32.
     int nb = 8;
     for (int c : {1, 2, 4, 8})
-        if (B <= c) { nb = c; break; }
+        if ((B + c - 1) / c <= 4) { nb = c; break; }
     const int n_groups = (B + nb - 1) / nb;
     const int slots = n_groups * nb;
     std::vector<int32_t> plan(2 * slots + n_groups + 2 * static_cast<size_t>(n_videos), 0);

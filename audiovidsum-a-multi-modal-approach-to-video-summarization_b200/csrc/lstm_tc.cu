@@ -72,19 +72,6 @@ struct Smem {
     static constexpr int TMEM_COLS = (W_TMEM_COLS + CHAINS * NB) <= 256 ? 256 : 512;
 };
 
-__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta_rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-    return r;
-}
-// 16-byte store into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16) (release at
-// cluster scope) when the data has landed.
-__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, const uint4& v, uint32_t mbar_cluster_addr) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                     dst_cluster_addr),
-                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster_addr)
-                 : "memory");
-}
 // K-major, no swizzle: start address, LBO = K-direction core-matrix stride, SBO = 8-row-group stride.
 __device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;

@@ -81,6 +81,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ----------------------------------------------------------------------- distributed shared memory
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+// 16-byte store into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16) (release at
+// cluster scope) when the data has landed.
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, const uint4& v, uint32_t mbar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     dst_cluster_addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster_addr)
+                 : "memory");
+}
+// mbarrier wait with acquire at CLUSTER scope: for consumers that read, with ordinary loads, data a peer CTA's
+// st.async delivered (pairs with the release of its complete_tx).  Costs a CCTL.IVALL per successful wait.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > AVS_SPIN_LIMIT) __trap();
+    }
+}
+
 // ----------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
