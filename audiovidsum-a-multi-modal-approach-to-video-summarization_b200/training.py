@@ -131,7 +131,7 @@ def allreduce_gradients(parameters, world_size: int = None, group=None) -> int:
 
 
 class GraphedTrainStep:
-    """The training step of scripts/train_av_model.py:86-96 (forward, loss, ``backward``, optional gradient all-reduce,
+    """The single-GPU training step of scripts/train_av_model.py:86-96 (forward, loss, ``backward``,
     ``optimizer.step``) captured ONCE in a CUDA graph and replayed: the eager step is host-bound (82 native launches
     plus torch's elementwise and optimiser kernels, ~3.3 ms for 8 x 320 frames), the replay is one graph launch.
 
@@ -150,6 +150,14 @@ class GraphedTrainStep:
         for g in optimizer.param_groups:
             if not g.get("capturable", False):
                 raise ValueError("build the optimiser with capturable=True to capture its step in a CUDA graph")
+        if allreduce:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # measured on 2 x B200: capturing the NCCL all-reduce together with the side-stream warm-up steps
+                # hangs; data-parallel training therefore uses the eager step (allreduce_gradients + optimizer.step)
+                raise NotImplementedError("GraphedTrainStep does not capture the gradient all-reduce (world size > 1): "
+                                          "use the eager step with training.allreduce_gradients")
+            allreduce = False
         self.model, self.optimizer, self.loss_fn, self.allreduce = model, optimizer, loss_fn, allreduce
         self.lengths = None if lengths is None else [int(x) for x in lengths]
         self.visual, self.audio, self.target = visual.clone(), audio.clone(), target.clone()

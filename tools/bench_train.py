@@ -54,6 +54,8 @@ def main():
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=args.graph)
     n_params = sum(p.numel() for p in model.parameters())
     graphed = None
+    if args.graph and world > 1:
+        raise SystemExit("--graph is single-GPU only: the captured step does not include the NCCL gradient all-reduce")
     if args.graph:
         graphed = training.GraphedTrainStep(model, opt, torch.nn.functional.mse_loss, visual, audio, target,
                                             allreduce=world > 1, warmup=max(args.warmup, 3))
