@@ -136,3 +136,14 @@ def test_numa_binding_is_best_effort():
         assert "disabled" in sharding.bind_process_to_gpu_numa(0)
     finally:
         del os.environ["AVS_NO_NUMA_BIND"]
+
+
+def test_graphed_train_step_needs_cuda_and_a_capturable_optimiser():
+    """training.GraphedTrainStep refuses host tensors (no CPU fallback) before it touches the model."""
+    import torch
+    from avsum_b200 import training
+    lin = torch.nn.Linear(4, 1)
+    opt = torch.optim.AdamW(lin.parameters(), lr=1e-3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        training.GraphedTrainStep(lin, opt, torch.nn.functional.mse_loss, torch.zeros(1, 2, 4), torch.zeros(1, 2, 4),
+                                  torch.zeros(1, 2))
