@@ -280,7 +280,6 @@ def main():
     launches = _cabi.launch_count() - launches0
     stage_ms = _cabi.profile_read()
     _cabi.profile(0)
-    clocks = sampler.stop() if sampler else None
     ms_local = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
     if world > 1:
@@ -315,6 +314,9 @@ def main():
     res = stream_host(args.steps)
     barrier()
     e2e_ms_local = (time.perf_counter() - e0) / args.steps * 1e3
+    # clocks / throttle reasons sampled over ALL timed regions (device-resident steps, single calls, streamed steps):
+    # the device-resident region alone lasts ~20 ms, less than two sampling periods
+    clocks = sampler.stop() if sampler else None
     t = torch.tensor([e2e_ms_local, call_ms_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
