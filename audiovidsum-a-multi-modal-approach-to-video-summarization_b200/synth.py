@@ -83,13 +83,20 @@ def config4(n_videos: int = 8, T: int = 8192, visual_dim=1024, audio_dim=128) ->
     return [make_video(T, visual_dim, audio_dim, 9000 + i) for i in range(n_videos)]
 
 
-def seeded_state_dict(visual_dim=1024, audio_dim=128, hidden_dim=512, seed=0, spread=False):
+PEAK_FACTOR = 30.0   # "peaked" weight set: q and k projections x30 -> attention logits x900 (sigma ~ 4.7 nats on config 1)
+
+
+def seeded_state_dict(visual_dim=1024, audio_dim=128, hidden_dim=512, seed=0, spread=False, peaked=False):
     """Reference-format state_dict with torch's default init under torch.manual_seed(seed).
 
     Builds the same torch.nn containers in the same order as the reference
     constructor (/root/reference/models/av_model.py:10-31), so the RNG stream --
     and therefore every weight -- equals ``torch.manual_seed(seed); AVBiLSTMModel(...)``.
     ``spread`` multiplies scorer.2.weight by 50 so scores leave the 0.52 +- 0.005 band.
+    ``peaked`` multiplies the q and k rows of attention.in_proj_weight by 30: with torch's default init the
+    attention logits have sigma ~ 0.005 (softmax == uniform weights, the context is mean(V) for every frame);
+    x900 gives sigma ~ 4.7 nats, per-row spans of ~30 log2 units and weights up to 0.94, so the temporal
+    branch depends on Q K^T, the running maximum and the rescaling of the flash-style kernel.
     """
     import torch.nn as nn
     torch.manual_seed(seed)
@@ -103,6 +110,10 @@ def seeded_state_dict(visual_dim=1024, audio_dim=128, hidden_dim=512, seed=0, sp
     sd = {k: v.detach().clone() for k, v in mods.state_dict().items()}
     if spread:
         sd["scorer.2.weight"] = sd["scorer.2.weight"] * 50.0
+    if peaked:
+        w = sd["attention.in_proj_weight"].clone()
+        w[:4 * hidden_dim] *= PEAK_FACTOR
+        sd["attention.in_proj_weight"] = w
     return sd
 
 

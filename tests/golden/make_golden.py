@@ -41,13 +41,15 @@ os.makedirs(OUT, exist_ok=True)
 torch.set_num_threads(8)
 
 
-def ref_model(vd, ad, hd=512, seed=0, spread=False):
+def ref_model(vd, ad, hd=512, seed=0, spread=False, peaked=False):
     torch.manual_seed(seed)
     m = AVBiLSTMModel(vd, ad, hd).eval()
-    if spread:
-        with torch.no_grad():
+    with torch.no_grad():
+        if spread:
             m.scorer[2].weight.mul_(50.0)
-    sd = synth.seeded_state_dict(vd, ad, hd, seed, spread)
+        if peaked:   # q and k projections x30: attention weights far from uniform (synth.PEAK_FACTOR)
+            m.attention.in_proj_weight[:4 * hd].mul_(synth.PEAK_FACTOR)
+    sd = synth.seeded_state_dict(vd, ad, hd, seed, spread, peaked)
     for k, v in m.state_dict().items():
         assert torch.equal(v, sd[k]), k
     return m, sd
@@ -77,12 +79,12 @@ def check_ports(m, sd, visual, audio, axis, want):
     return err
 
 
-def model_case(name, vd, ad, B, T, seed_in, spread=False):
-    m, sd = ref_model(vd, ad, spread=spread)
+def model_case(name, vd, ad, B, T, seed_in, spread=False, peaked=False):
+    m, sd = ref_model(vd, ad, spread=spread, peaked=peaked)
     g = torch.Generator().manual_seed(seed_in)
     visual = torch.randn(B, T, vd, generator=g)
     audio = torch.randn(B, T, ad, generator=g)
-    rec = dict(visual_dim=vd, audio_dim=ad, B=B, T=T, seed_in=seed_in, spread=int(spread),
+    rec = dict(visual_dim=vd, audio_dim=ad, B=B, T=T, seed_in=seed_in, spread=int(spread), peaked=int(peaked),
                weights_checksum=synth.state_dict_checksum(sd))
     for axis in ("literal", "temporal"):
         want = ref_forward(m, visual, audio, axis)
@@ -92,7 +94,50 @@ def model_case(name, vd, ad, B, T, seed_in, spread=False):
     np.savez(os.path.join(OUT, name + ".npz"), **rec)
 
 
+def attention_weight_stats(m, visual, audio):
+    """min / max softmax weight and logit sigma of head 0 of the TEMPORAL attention, from the reference's own modules."""
+    with torch.no_grad():
+        v_out, _ = m.visual_bilstm(m.visual_fc(visual))
+        a_out, _ = m.audio_bilstm(m.audio_fc(audio))
+        fused = torch.cat([v_out, a_out], dim=-1)[0]
+        qkv = torch.nn.functional.linear(fused, m.attention.in_proj_weight, m.attention.in_proj_bias)
+        s = qkv[:, :256] @ qkv[:, 1024:1280].T / 16.0
+        w = torch.softmax(s, dim=-1)
+    return float(w.min()), float(w.max()), float(s.std())
+
+
+def peaked_cases():
+    """Round 2: the "peaked" weight set (synth.seeded_state_dict(peaked=True)).  With the default init every
+    temporal-attention weight is within 2 % of 1/T, so the round-1 temporal fixtures only pin a masked mean of V;
+    these pin Q K^T, the softmax and P V."""
+    m, sd = ref_model(1024, 128, spread=True, peaked=True)
+    vid = synth.config1()
+    wmin, wmax, sig = attention_weight_stats(m, vid.visual[None], vid.audio[None])
+    assert wmax > 0.5 and sig > 3.0, (wmin, wmax, sig)
+    rec = dict(weights_checksum=synth.state_dict_checksum(sd), spread=1, peaked=1, attn_w_min=wmin, attn_w_max=wmax,
+               logit_sigma=sig)
+    for axis in ("literal", "temporal"):
+        want = ref_forward(m, vid.visual[None], vid.audio[None], axis)
+        err = check_ports(m, sd, vid.visual[None], vid.audio[None], axis, want)
+        rec["scores_" + axis] = want.numpy()
+        print(f"config1 peaked {axis:8s} range=[{want.min():.4f},{want.max():.4f}] numpy-oracle err={err:.2e} "
+              f"attention weights [{wmin:.2e}, {wmax:.3f}] logit sigma {sig:.2f}")
+    np.savez(os.path.join(OUT, "config1_peaked.npz"), **rec)
+    model_case("batch2_T130_peaked", 1024, 128, 2, 130, 81, spread=True, peaked=True)
+    vids = synth.config2()[:4]
+    rec = dict(weights_checksum=synth.state_dict_checksum(sd), lengths=np.asarray([v.T for v in vids]))
+    for axis in ("literal", "temporal"):
+        rec["scores_" + axis] = np.concatenate(
+            [ref_forward(m, v.visual[None], v.audio[None], axis).numpy().reshape(-1) for v in vids])
+    np.savez(os.path.join(OUT, "config2_first4_peaked.npz"), **rec)
+    print("config2_first4_peaked", rec["lengths"], "temporal range",
+          float(rec["scores_temporal"].min()), float(rec["scores_temporal"].max()))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "peaked":   # only the round-2 fixtures (the others are unchanged)
+        peaked_cases()
+        return
     # config 1 of BASELINE.json (layout [1, T, D] drawn as synth.make_video does: visual then audio, seed 1234)
     m, sd = ref_model(1024, 128)
     for spread in (False, True):
@@ -154,6 +199,7 @@ def main():
     assert abs(av_oracle.temporal_f1(pred, gt) - ref_tf1(pred, gt, 1000)) == 0
     assert np.array_equal(av_oracle.align_shots_to_annotations(shots, ann, 30.0), al.numpy())
     print("helpers ok; dtw dtype", dtw.dtype, "aligned dtype", al.dtype)
+    peaked_cases()
 
 
 if __name__ == "__main__":

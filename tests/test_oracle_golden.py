@@ -29,12 +29,31 @@ def test_config1_oracle_matches_reference(golden_dir, spread, axis):
     assert np.max(np.abs(got - g["scores_" + axis])) < TOL
 
 
-@pytest.mark.parametrize("name", ["batch3_T17", "batch2_T1", "batch1_T1", "default_dims_T40", "batch2_T130_spread"])
+@pytest.mark.parametrize("axis", ["literal", "temporal"])
+def test_config1_peaked_oracle_matches_reference(golden_dir, axis):
+    """The "peaked" weight set (q / k projections x30): temporal attention weights span [5e-13, 0.94] in the
+    reference, so this fixture pins Q K^T, the softmax and P V -- not just a mean of V."""
+    g = np.load(os.path.join(golden_dir, "config1_peaked.npz"))
+    sd = synth.seeded_state_dict(spread=True, peaked=True)
+    assert abs(synth.state_dict_checksum(sd) - float(g["weights_checksum"])) < 1e-6 * float(g["weights_checksum"])
+    assert float(g["attn_w_max"]) > 0.5 and float(g["attn_w_min"]) < 1e-9 and float(g["logit_sigma"]) > 3.0
+    vid = synth.config1()
+    got = av_oracle.forward(_np_sd(sd), vid.visual[None].numpy(), vid.audio[None].numpy(), 4, axis)
+    assert np.max(np.abs(got - g["scores_" + axis])) < TOL
+    assert g["scores_temporal"].max() - g["scores_temporal"].min() > 0.2    # the frames really differ
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
+    port.load_state_dict(sd)
+    with torch.no_grad():
+        assert np.array_equal(port(vid.visual[None], vid.audio[None], axis).numpy(), g["scores_" + axis])
+
+
+@pytest.mark.parametrize("name", ["batch3_T17", "batch2_T1", "batch1_T1", "default_dims_T40", "batch2_T130_spread",
+                                  "batch2_T130_peaked"])
 @pytest.mark.parametrize("axis", ["literal", "temporal"])
 def test_model_cases_oracle_matches_reference(golden_dir, name, axis):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     vd, ad, B, T = int(g["visual_dim"]), int(g["audio_dim"]), int(g["B"]), int(g["T"])
-    sd = synth.seeded_state_dict(vd, ad, 512, 0, bool(int(g["spread"])))
+    sd = synth.seeded_state_dict(vd, ad, 512, 0, bool(int(g["spread"])), bool(int(g["peaked"])) if "peaked" in g else False)
     assert abs(synth.state_dict_checksum(sd) - float(g["weights_checksum"])) < 1e-6 * max(1.0, float(g["weights_checksum"]))
     gen = torch.Generator().manual_seed(int(g["seed_in"]))
     visual = torch.randn(B, T, vd, generator=gen)
