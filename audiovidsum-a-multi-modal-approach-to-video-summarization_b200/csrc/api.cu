@@ -26,6 +26,17 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int device_sm_count() {
+    static std::atomic<int> cached[kMaxDevices] = {};
+    const int dev = current_device();
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 // ---- optional per-stage device timing (CUDA events on the launching stream) -------------
 // Enabled by avs_profile(1); events are resolved lazily in avs_profile_read so the hot path
 // never synchronises because of profiling.
@@ -259,8 +270,7 @@ avs_status check_dims(const avs_weights* w) {
 
 // lstm_only: just the four recurrences' tensors (what a training step changes and reads through the handle);
 // sync: wait for the packing kernels (model creation) -- otherwise the caller's stream orders them
-avs_status pack_weights(avs_model* m, const avs_weights* w, cudaStream_t st = 0, bool lstm_only = false,
-                        bool sync = true) {
+avs_status pack_weights(avs_model* m, const avs_weights* w, cudaStream_t st, bool lstm_only, bool sync) {
     const int Dv = m->Dv, Da = m->Da;
     // raw copies
     const size_t raw_elems = static_cast<size_t>(H) * (Dv + Da) + 2 * H + 4 * (static_cast<size_t>(G4) * H + G4 * HC + 2 * G4) +
@@ -599,10 +609,16 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
         *it.p = m->slab + off;
         off += align_up(it.bytes, 256);
     }
-    avs_status s = pack_weights(m, w);
+    // the packing kernels run on the handle's own stream: the caller guarantees that the parameters are complete
+    // (include/avsum_b200.h), nothing else is ordered against the legacy default stream
+    avs_status s = AVS_OK;
+    if (cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("creating the copy stream failed");
+        s = AVS_ERR_CUDA;
+    }
+    if (s == AVS_OK) s = pack_weights(m, w, m->copy_stream, false, true);
     if (s == AVS_OK) {
-        cudaError_t ce = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
-        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming);
+        cudaError_t ce = cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming);
         for (int i = 0; i < avs_model::MAX_CHUNKS && ce == cudaSuccess; ++i)
             ce = cudaEventCreateWithFlags(&m->ev_chunk[i], cudaEventDisableTiming);
         for (int i = 0; i < 5 && ce == cudaSuccess; ++i) {
@@ -640,7 +656,10 @@ avs_status avs_model_update(avs_model* m, const avs_weights* w) {
               "avs_model_update: feature dims differ from the handle's");
     m->heads = w->num_heads;
     Guard g(m->device);
-    return pack_weights(m, w);
+    // synchronous form: everything queued on this device (earlier asynchronous packs share the staging arena, the
+    // writer of the parameters may be any stream) finishes first, then the pack runs on the handle's own stream
+    AVS_CUDA(cudaDeviceSynchronize());
+    return pack_weights(m, w, m->copy_stream, false, true);
 }
 
 avs_status avs_model_update_async(avs_model* m, const avs_weights* w, int lstm_only, void* cuda_stream) {
@@ -1464,7 +1483,24 @@ avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t
     e.relu = relu;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     if (precision == AVS_PREC_FP32_SIMT) return gemm_simt(A, K, W, K, M, N, K, e, st);
-    if (precision == AVS_PREC_TF32) return gemm_tc(A, K, W, K, DT_F32, M, N, K, e, st);
+    if (precision == AVS_PREC_TF32) {
+        // ONE operand policy for kind::tf32 everywhere (avs_forward's fc layers use the same): the weight is rounded
+        // to nearest (a copy made for this call), the activation is read as it is -- the tensor core truncates its
+        // low 13 mantissa bits, x -> x (1 - d) with d in [0, 2^-10) -- and the -2^-11 mean of that truncation is
+        // scaled out of the accumulator.  Assumption: the low mantissa bits of A are uniformly distributed (any
+        // fp32 data that is not already exact in tf32); data that IS tf32-exact (fp16 / bf16 values upcast to fp32)
+        // sees +4.9e-4 relative on the product instead of 0, inside the 1e-3 budget
+        // (tests/test_gpu_parity.py::test_forward_with_fp16_exact_features).
+        AVS_CHECK(M >= 0 && N > 0 && K > 0, AVS_ERR_INVALID, "avs_linear: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+        if (M == 0) return AVS_OK;
+        float* w_rn = nullptr;
+        AVS_CUDA(cudaMallocAsync(&w_rn, static_cast<size_t>(N) * K * 4, st));
+        avs_status s = convert_f32(W, w_rn, static_cast<int64_t>(N) * K, DT_F32, 1, st);
+        e.acc_scale = 1.0f + 1.0f / 2048.0f;
+        if (s == AVS_OK) s = gemm_tc(A, K, w_rn, K, DT_F32, M, N, K, e, st);
+        cudaFreeAsync(w_rn, st);
+        return s;
+    }
     // bf16 operands: cast both sides for this call
     AVS_CHECK(M >= 0 && N > 0 && K > 0 && K % 8 == 0, AVS_ERR_UNSUPPORTED,
               "avs_linear[bf16]: K=%d must be a multiple of 8 (16-byte TMA row pitch)", K);

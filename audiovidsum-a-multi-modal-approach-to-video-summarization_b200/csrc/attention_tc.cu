@@ -317,10 +317,11 @@ avs_status attention_tc(const void* qkv_h, int in_dtype, int64_t rows, int E, in
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AVS_CHECK(r == CUDA_SUCCESS, AVS_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed with CUresult %d", static_cast<int>(r));
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    const int dev = current_device();
+    if (configured.needed(dev)) {
         AVS_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        configured = true;
+        configured.mark(dev);
     }
     dim3 grid((seqs.max_len + BM - 1) / BM, H, seqs.n_seqs);
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(DH));

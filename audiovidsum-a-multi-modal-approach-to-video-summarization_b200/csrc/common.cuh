@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libavsum_b200.so.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -43,6 +44,24 @@ void count_launch(int n = 1);
         ::avs::count_launch();            \
         AVS_CUDA(cudaGetLastError());     \
     } while (0)
+
+// ---- per-device one-time setup ------------------------------------------------
+// Function attributes (cudaFuncSetAttribute), __device__ symbols, streams, events and SM counts belong to ONE
+// device's context, and the API takes a device per handle: everything cached "once" is cached per device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+struct PerDeviceOnce {
+    std::atomic<bool> done[kMaxDevices] = {};
+    // true while the current device still needs the setup; call mark() after it succeeded (a concurrent second
+    // setup is harmless: the calls it guards are idempotent)
+    bool needed(int dev) const { return !done[dev].load(std::memory_order_acquire); }
+    void mark(int dev) { done[dev].store(true, std::memory_order_release); }
+};
+int device_sm_count();   // multiprocessors of the current device (cached per device)
 
 // ---- element types of GEMM operands / outputs -------------------------------
 enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };

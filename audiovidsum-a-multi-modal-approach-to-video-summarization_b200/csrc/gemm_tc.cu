@@ -658,23 +658,19 @@ static avs_status gemm_tc2(const void* A, int64_t lda, const void* W, int64_t ld
     const int64_t tiles_total = ((M + 2 * BM - 1) / (2 * BM)) * tiles_n;
     AVS_CHECK(tiles_total < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: too many tiles");
     const int num_tiles = static_cast<int>(tiles_total);
-    static int num_pairs = 0;
-    if (num_pairs == 0) {
-        int dev = 0, sms = 0;
-        AVS_CUDA(cudaGetDevice(&dev));
-        AVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        num_pairs = sms / 2;
-    }
+    const int num_pairs = device_sm_count() / 2;
+    AVS_CHECK(num_pairs > 0, AVS_ERR_CUDA, "gemm: could not read the SM count");
     const int grid = 2 * (num_tiles < num_pairs ? num_tiles : num_pairs);
     const uint32_t idesc = umma_idesc(fmt, 2 * BM, BN);
 #define AVS_GEMM2_LAUNCH(ST_, TF_)                                                                            \
     do {                                                                                                     \
         using L = SmemLayout2<BN, ST_>;                                                                      \
         auto kern = gemm_tc2_kernel<BN, ST_, TF_>;                                                           \
-        static bool configured = false;                                                                      \
-        if (!configured) {                                                                                   \
+        static PerDeviceOnce configured;                                                                     \
+        const int dev_ = current_device();                                                                   \
+        if (configured.needed(dev_)) {                                                                       \
             AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));     \
-            configured = true;                                                                               \
+            configured.mark(dev_);                                                                           \
         }                                                                                                    \
         kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, static_cast<int>(M), N, k_blocks,      \
                                                        bk_elems, idesc, tiles_n, num_tiles, epi);            \
@@ -698,13 +694,12 @@ avs_status gemm_trace_read(unsigned long long* out8) {
 avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, int64_t M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t stream) {
     if (M == 0) return AVS_OK;
-    static bool trace_set = false;
-    if (!trace_set) {
-        trace_set = true;
-        if (getenv("AVS_GEMM_TRACE") != nullptr) {
-            const int on = 1;
-            AVS_CUDA(cudaMemcpyToSymbol(g_gemm_trace_on, &on, sizeof(on)));
-        }
+    static const bool want_trace = getenv("AVS_GEMM_TRACE") != nullptr;
+    static PerDeviceOnce trace_set;
+    if (want_trace && trace_set.needed(current_device())) {
+        const int on = 1;
+        AVS_CUDA(cudaMemcpyToSymbol(g_gemm_trace_on, &on, sizeof(on)));
+        trace_set.mark(current_device());
     }
     AVS_CHECK(M > 0 && N > 0 && K > 0, AVS_ERR_INVALID, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
     AVS_CHECK(M < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: M too large");
@@ -744,12 +739,8 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     const int64_t tiles_total = static_cast<int64_t>((M + BM - 1) / BM) * tiles_n;
     AVS_CHECK(tiles_total < (1ll << 31), AVS_ERR_UNSUPPORTED, "gemm: too many tiles");
     const int num_tiles = static_cast<int>(tiles_total);
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        AVS_CUDA(cudaGetDevice(&dev));
-        AVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = device_sm_count();
+    AVS_CHECK(num_sms > 0, AVS_ERR_CUDA, "gemm: could not read the SM count");
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;   // persistent: one CTA per SM
     const uint32_t idesc = umma_idesc(fmt, BM, BN);
 
@@ -757,10 +748,11 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     do {                                                                                                     \
         using L = SmemLayout<BN_, ST_>;                                                                      \
         auto kern = gemm_tc_kernel<BN_, ST_, TF_>;                                                           \
-        static bool configured = false;                                                                      \
-        if (!configured) {                                                                                   \
+        static PerDeviceOnce configured;                                                                     \
+        const int dev_ = current_device();                                                                   \
+        if (configured.needed(dev_)) {                                                                       \
             AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));     \
-            configured = true;                                                                               \
+            configured.mark(dev_);                                                                           \
         }                                                                                                    \
         kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, static_cast<int>(M), N, k_blocks,      \
                                                        bk_elems, idesc, tiles_n, num_tiles, epi);            \

@@ -452,14 +452,15 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
     if (warp == EPI_WARPS) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
-// Streams / events for the split launch below (one set per process; the library serialises calls per handle).
+// Streams / events for the split launch below (one set per device; the library serialises calls per handle).
 struct SplitCtx {
     cudaStream_t aux = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     bool ok = false;
 };
 SplitCtx& split_ctx() {
-    static SplitCtx c;
+    static SplitCtx per_device[kMaxDevices];
+    SplitCtx& c = per_device[current_device()];
     if (!c.ok && c.aux == nullptr) {
         if (cudaStreamCreateWithFlags(&c.aux, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -481,11 +482,12 @@ avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, con
     auto kern = trace ? lstm_tc_kernel<NB, PARTS, CHAINS, NB == 16> : lstm_tc_kernel<NB, PARTS, CHAINS, false>;
     constexpr int SMEM = Smem<NB, CHAINS>::TOTAL;
     constexpr int SMEM_EXCLUSIVE = 200 * 1024;   // more than half an SM: no second CTA of either launch fits beside it
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    const int dev = current_device();
+    if (configured.needed(dev)) {
         AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       PARTS == 2 ? SMEM_EXCLUSIVE : SMEM));
-        configured = true;
+        configured.mark(dev);
     }
     const int threads = PARTS * 128 + CHAINS * 32;
     // The kernel lasts as long as the LONGEST group's chain of dependent steps, and a step is ~13 % slower on

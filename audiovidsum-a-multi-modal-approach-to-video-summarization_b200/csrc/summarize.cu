@@ -440,20 +440,21 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
         const size_t need = static_cast<size_t>(items) * 8 + 2 * (static_cast<size_t>(rows) + 1) * vsz +
                             static_cast<size_t>(items) * 8 + words_all * 4 + 64;
         if (need <= limit) {
-            static bool cfg32 = false, cfg64 = false;
+            static PerDeviceOnce cfg32, cfg64;
+            const int dev = current_device();
             if (narrow) {
-                if (!cfg32 && need > 48 * 1024) {
+                if (cfg32.needed(dev) && need > 48 * 1024) {
                     AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   static_cast<int>(limit)));
-                    cfg32 = true;
+                    cfg32.mark(dev);
                 }
                 knapsack_fast_kernel<int><<<b.n, KNAP_THREADS, need, stream>>>(b, scores, positions, seg_mean, picks,
                                                                                summary, rows, items);
             } else {
-                if (!cfg64 && need > 48 * 1024) {
+                if (cfg64.needed(dev) && need > 48 * 1024) {
                     AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<long long>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(limit)));
-                    cfg64 = true;
+                    cfg64.mark(dev);
                 }
                 knapsack_fast_kernel<long long><<<b.n, KNAP_THREADS, need, stream>>>(b, scores, positions, seg_mean,
                                                                                      picks, summary, rows, items);

@@ -58,8 +58,11 @@ def pinned_like(t: torch.Tensor, write_combined: bool = False) -> torch.Tensor:
         return src.pin_memory()
     blk = _HostBlock(nbytes, write_combined)
     buf = (C.c_byte * nbytes).from_address(blk.ptr.value)
+    # the allocation lives as long as the STORAGE: torch.frombuffer keeps a reference to ``buf`` for the lifetime of
+    # the storage it creates, and ``buf`` owns the block -- so views (slices, reshapes, torch.split pieces, whatever
+    # an in-flight asynchronous step keeps) hold the pinned memory alive after the first tensor object is gone
+    buf._avs_block = blk
     out = torch.frombuffer(buf, dtype=src.dtype).reshape(src.shape)
-    out._avs_block = blk            # keeps the allocation alive as long as this tensor object
     out.copy_(src)
     return out
 
@@ -132,6 +135,8 @@ class NativeModel:
         self.dims = (visual_dim, audio_dim, hidden_dim, num_heads)
         self._handle = C.c_void_p()
         w, keep = self._weights_struct(state_dict)
+        # avs_model_create packs on its own stream; the parameters were last written on torch's current stream
+        torch.cuda.current_stream(self.device).synchronize()
         _cabi.check(self.lib.avs_model_create(C.byref(w), self.device, C.byref(self._handle)))
         del keep
 
@@ -169,15 +174,13 @@ class NativeModel:
         and returns (the training loop: the optimiser step that changed the parameters ran on the same stream);
         ``lstm_only`` re-packs just the recurrences' tensors, the only ones a training step reads through the handle."""
         w, keep = self._weights_struct(state_dict)
-        if sync and not lstm_only:
-            _cabi.check(self.lib.avs_model_update(self._handle, C.byref(w)))
-            torch.cuda.synchronize(self.device)
-        else:
-            with torch.cuda.device(self.device):
-                _cabi.check(self.lib.avs_model_update_async(self._handle, C.byref(w), int(lstm_only),
-                                                            _stream_ptr(self.device)))
-                if sync:
-                    torch.cuda.synchronize(self.device)
+        # always on torch's CURRENT stream: that is where the optimiser step / load_state_dict that changed the
+        # parameters ran, and where earlier packs that share the handle's staging arena were queued
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.avs_model_update_async(self._handle, C.byref(w), int(lstm_only),
+                                                        _stream_ptr(self.device)))
+            if sync:
+                torch.cuda.current_stream(self.device).synchronize()
         del keep   # temporaries (non-fp32 / non-contiguous sources) are freed in stream order by torch's allocator
 
     def close(self):

@@ -12,8 +12,11 @@ parameters, the user's optimiser -- and supplies every heavy op of the step as a
                    dW_ih, dW_hh, d_emb)
 
 ReLU / dropout / sigmoid / MSE are left to torch's elementwise autograd ops (O(rows * 512) work, < 0.1 % of the
-step).  ``allreduce_gradients`` is the data-parallel collective of BASELINE configs[4]: one flat fp32 bucket
-(8,008,833 elements for the 1024/128 model), one NCCL all-reduce, averaged.
+step).  Data parallelism (BASELINE configs[4]): ``GradBuckets`` keeps ONE flat fp32 gradient buffer (8,008,833
+elements = 32 MB for the 1024/128 model) cut into buckets in the order the backward produces the gradients (score
+head and attention first, the recurrences next, the fc layers last); a bucket's NCCL all-reduce starts from the
+autograd hook of its last gradient and runs beside the rest of the backward.  ``allreduce_gradients`` is the
+unbucketed form (one flat bucket after the backward).  ``TrainStep`` runs / captures the whole step.
 """
 from __future__ import annotations
 
@@ -87,7 +90,8 @@ class _BiLSTMPairFn(torch.autograd.Function):
         dev = v_emb.device
         R = int(v_emb.shape[0])
         d_fused = d_fused.contiguous().to(torch.float32)
-        d_v, d_a = torch.empty_like(v_emb), torch.empty_like(a_emb)
+        # zeros: rows no video owns (and everything, when all lengths are 0) must carry no gradient
+        d_v, d_a = torch.zeros_like(v_emb), torch.zeros_like(a_emb)
         dW_ih = [torch.empty(1024, 512, dtype=torch.float32, device=dev) for _ in range(4)]
         dW_hh = [torch.empty(1024, 256, dtype=torch.float32, device=dev) for _ in range(4)]
         db = [torch.empty(1024, dtype=torch.float32, device=dev) for _ in range(4)]
@@ -130,66 +134,179 @@ def allreduce_gradients(parameters, world_size: int = None, group=None) -> int:
     return int(flat.numel())
 
 
-class GraphedTrainStep:
-    """The single-GPU training step of scripts/train_av_model.py:86-96 (forward, loss, ``backward``,
-    ``optimizer.step``) captured ONCE in a CUDA graph and replayed: the eager step is host-bound (82 native launches
-    plus torch's elementwise and optimiser kernels, ~3.3 ms for 8 x 320 frames), the replay is one graph launch.
+class GradBuckets:
+    """Bucketed, overlapped gradient averaging for data-parallel training (scripts/train_av_model.py:86-96 on N GPUs).
+
+    All gradients live in one flat fp32 buffer, parameters laid out in REVERSE registration order -- the order in
+    which the backward of AVBiLSTMModel finishes them (scorer, attention, the four recurrences, fc).  The buffer is
+    cut into buckets of about ``bucket_mb`` at parameter boundaries.  A post-accumulate-grad hook per parameter
+    moves the fresh gradient into its slice (``p.grad`` becomes a view of the flat buffer, so the optimiser reads
+    the averaged values in place) and, when the last gradient of a bucket has arrived, launches that bucket's
+    all-reduce with ``async_op=True``: torch's NCCL process group runs it on its own stream, ordered after the
+    producing kernels by an event, so the transfer overlaps the remaining backward kernels.  ``finish()`` launches
+    whatever has not been launched (parameters that received no gradient contribute zeros) and makes the current
+    stream wait for every bucket.  NCCL averages in the collective (ReduceOp.AVG); other backends (gloo in the CPU
+    tests) sum and divide.  Works under CUDA-graph capture: the collectives are captured with the step.
+    """
+
+    def __init__(self, parameters, bucket_mb: float = 12.0, group=None, world_size: int = None):
+        import torch.distributed as dist
+        self.params = [p for p in parameters if p.requires_grad]
+        if not self.params:
+            raise ValueError("no parameter requires a gradient")
+        self.group = group
+        self.dist = dist
+        self.active = dist.is_available() and dist.is_initialized()
+        self.world = world_size if world_size is not None else (dist.get_world_size(group) if self.active else 1)
+        dev, dt = self.params[0].device, self.params[0].dtype
+        order = list(reversed(self.params))
+        self.flat = torch.zeros(sum(p.numel() for p in order), dtype=dt, device=dev)
+        limit = max(int(bucket_mb * (1 << 20) / self.flat.element_size()), 1)
+        self.buckets = []            # [start, end, n_params]
+        self.slot = {}               # id(p) -> (view, bucket index)
+        off = start = count = 0
+        for p in order:
+            n = p.numel()
+            if count and off + n - start > limit:
+                self.buckets.append([start, off, count])
+                start, count = off, 0
+            self.slot[id(p)] = (self.flat[off:off + n].view_as(p), len(self.buckets))
+            off += n
+            count += 1
+        self.buckets.append([start, off, count])
+        self.avg_in_collective = self.active and dist.get_backend(group) == "nccl"
+        self._arrived = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+
+    def close(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def _launch(self, b):
+        self._launched[b] = True
+        if self.world <= 1 or not self.active:
+            return
+        s, e, _ = self.buckets[b]
+        op = self.dist.ReduceOp.AVG if self.avg_in_collective else self.dist.ReduceOp.SUM
+        self._works.append((self.dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True), b))
+
+    def _hook(self, p):
+        view, b = self.slot[id(p)]
+        if p.grad is not view:
+            view.copy_(p.grad)
+            p.grad = view
+        self._arrived[b] += 1
+        if self._arrived[b] == self.buckets[b][2] and not self._launched[b]:
+            self._launch(b)
+
+    def start(self):
+        """Call before the backward of a step (after ``zero_grad(set_to_none=True)``)."""
+        self._arrived = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+
+    def finish(self):
+        """Call after the backward: every gradient averaged and visible to the current stream."""
+        for p in self.params:                      # a parameter the loss does not depend on: zero gradient
+            view, b = self.slot[id(p)]
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+        for b in range(len(self.buckets)):
+            if not self._launched[b]:
+                self._launch(b)
+        for w, b in self._works:
+            w.wait()
+            if not self.avg_in_collective:
+                s, e, _ = self.buckets[b]
+                self.flat[s:e].div_(self.world)
+        self._works = []
+        return int(self.flat.numel())
+
+
+class TrainStep:
+    """The training step of scripts/train_av_model.py:86-96 -- forward, loss, ``backward``, gradient averaging over
+    the data-parallel ranks (``GradBuckets``: bucketed NCCL all-reduce overlapped with the backward), ``optimizer
+    .step`` -- launched eagerly or, with ``graph=True``, captured ONCE in a CUDA graph (collectives included) and
+    replayed: the eager step is host-bound (~100 small launches), the replay is one graph launch.
 
     The batch shape is fixed at capture (``visual [B, T, Dv]``, ``audio [B, T, Da]``, ``target`` as the loss function
-    takes it, optional ``lengths``); every call copies the new batch into the captured input buffers.  The
-    optimiser must be built with ``capturable=True`` (torch's requirement for optimiser steps inside a graph).
+    takes it, optional ``lengths``); every call copies the new batch (device or pinned host tensors) into the
+    captured input buffers.  A graphed step needs an optimiser built with ``capturable=True`` (torch's requirement).
     Launch plans and sequence descriptors travel as kernel parameters (no pageable-memory copies), the recurrences'
     weight re-pack after the optimiser step is part of the graph, and workspaces are grown during the warm-up
     steps, so nothing inside the captured region allocates through cudaMalloc or synchronises.
     """
 
-    def __init__(self, model, optimizer, loss_fn, visual, audio, target, lengths=None, allreduce: bool = False,
-                 warmup: int = 3):
+    def __init__(self, model, optimizer, loss_fn, visual, audio, target, lengths=None, world_size: int = None,
+                 graph: bool = True, warmup: int = 3, bucket_mb: float = 12.0):
         if not visual.is_cuda:
-            raise RuntimeError("GraphedTrainStep needs CUDA tensors (no CPU fallback)")
-        for g in optimizer.param_groups:
-            if not g.get("capturable", False):
-                raise ValueError("build the optimiser with capturable=True to capture its step in a CUDA graph")
-        if allreduce:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                # measured on 2 x B200: capturing the NCCL all-reduce together with the side-stream warm-up steps
-                # hangs; data-parallel training therefore uses the eager step (allreduce_gradients + optimizer.step)
-                raise NotImplementedError("GraphedTrainStep does not capture the gradient all-reduce (world size > 1): "
-                                          "use the eager step with training.allreduce_gradients")
-            allreduce = False
-        self.model, self.optimizer, self.loss_fn, self.allreduce = model, optimizer, loss_fn, allreduce
+            raise RuntimeError("TrainStep needs CUDA tensors (no CPU fallback)")
+        if graph:
+            for g in optimizer.param_groups:
+                if not g.get("capturable", False):
+                    raise ValueError("build the optimiser with capturable=True to capture its step in a CUDA graph")
+        import torch.distributed as dist
+        ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if ddp else 1
+        if world_size is not None and world_size != self.world:
+            raise ValueError(f"world_size={world_size} but torch.distributed reports {self.world} rank(s)")
+        self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
         self.lengths = None if lengths is None else [int(x) for x in lengths]
         self.visual, self.audio, self.target = visual.clone(), audio.clone(), target.clone()
-        side = torch.cuda.Stream(device=visual.device)
-        side.wait_stream(torch.cuda.current_stream(visual.device))
+        self.buckets = GradBuckets(model.parameters(), bucket_mb=bucket_mb) if ddp else None
+        self.allreduce_mode = (f"{len(self.buckets.buckets)} buckets, async all-reduce launched from autograd hooks "
+                               f"(overlaps the backward)" if ddp else "none (1 GPU)")
+        self.graphed = False
+        self.graph = None
+        dev = visual.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):      # grows the workspaces, sets kernel attributes, creates optimiser state
-                optimizer.zero_grad(set_to_none=True)
                 self._body()
-        torch.cuda.current_stream(visual.device).wait_stream(side)
-        torch.cuda.synchronize(visual.device)
-        self.graph = torch.cuda.CUDAGraph()
-        optimizer.zero_grad(set_to_none=True)
-        if hasattr(model, "_native_lstm_key"):
-            model._native_lstm_key = None      # the captured forward must contain the recurrences' weight re-pack
-        with torch.cuda.graph(self.graph):
-            self.loss = self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if graph:
+            if ddp:
+                dist.barrier()
+            self.graph = torch.cuda.CUDAGraph()
+            if hasattr(model, "_native_lstm_key"):
+                model._native_lstm_key = None      # the captured forward must contain the recurrences' weight re-pack
+            with torch.cuda.graph(self.graph):
+                self.loss = self._body()
+            self.graphed = True
 
     def _body(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        if self.buckets is not None:
+            self.buckets.start()
         preds = self.model(self.visual, self.audio) if self.lengths is None else \
             self.model(self.visual, self.audio, self.lengths)
         loss = self.loss_fn(preds, self.target)
         loss.backward()
-        if self.allreduce:
-            allreduce_gradients(self.model.parameters())
+        if self.buckets is not None:
+            self.buckets.finish()
         self.optimizer.step()
         return loss
 
     def __call__(self, visual, audio, target):
-        """Run one step on a new batch of the captured shape; returns the (captured) loss tensor."""
+        """Run one step on a new batch of the captured shape; returns the loss tensor (of the captured graph)."""
         self.visual.copy_(visual, non_blocking=True)
         self.audio.copy_(audio, non_blocking=True)
         self.target.copy_(target, non_blocking=True)
-        self.graph.replay()
-        return self.loss
+        if self.graph is not None:
+            self.graph.replay()
+            return self.loss
+        return self._body()
+
+
+class GraphedTrainStep(TrainStep):
+    """Round-1 name of the single-GPU captured step (kept for callers): ``TrainStep(graph=True)``."""
+
+    def __init__(self, model, optimizer, loss_fn, visual, audio, target, lengths=None, allreduce: bool = False,
+                 warmup: int = 3):
+        super().__init__(model, optimizer, loss_fn, visual, audio, target, lengths=lengths, graph=True, warmup=warmup)

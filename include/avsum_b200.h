@@ -86,9 +86,12 @@ int avs_device_ok(void);
 
 /* Replaces AVBiLSTMModel.__init__ + .cuda() (av_model.py:7-31; scripts/evaluate.py:13):
  * packs the weights for the kernels (gate interleave for the LSTM slices, tf32 rounding,
- * bf16 copies) on `device`. */
+ * bf16 copies) on `device`.  The packing runs on a stream of the handle: the weight tensors must be complete (the
+ * stream that wrote them synchronised) when this is called; it returns after the packing has finished.  Handles on
+ * several devices may coexist in one process (kernel attributes, SM counts and helper streams are kept per device). */
 avs_status avs_model_create(const avs_weights* w, int device, avs_model** out);
-/* Re-pack after the caller changed parameters (load_state_dict / optimizer step). */
+/* Re-pack after the caller changed parameters (load_state_dict / optimizer step).  Synchronous: waits for all work
+ * queued on the device (cudaDeviceSynchronize), packs, returns when the handle is up to date. */
 avs_status avs_model_update(avs_model* m, const avs_weights* w);
 /* The same without a host synchronisation: the packing kernels are queued on `cuda_stream`, so the source tensors
  * must not change before the stream gets there (true for parameters updated by work on the same stream -- the

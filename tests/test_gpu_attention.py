@@ -55,12 +55,13 @@ def make_qkv(T: int, kind: str, prec: str, seed: int):
         blk = torch.arange(T) // 64
         if kind == "staircase":
             jumps = sorted({min(1, nblk - 1), nblk // 2, max(nblk - 2, 0), nblk - 1} - {0})
-            step = sum((blk >= jb).to(torch.float32) for jb in jumps)
+            step = sum(((blk >= jb).to(torch.float32) for jb in jumps), torch.zeros(T))
         else:
             mid = max(nblk // 2, 1)
             up = sorted({min(1, mid), mid // 2, mid} - {0})
             down = sorted({min(mid + 1, nblk - 1), nblk - 1} - {0} - set(up))
-            step = sum((blk >= jb).to(torch.float32) for jb in up) - sum((blk >= jb).to(torch.float32) for jb in down)
+            step = sum(((blk >= jb).to(torch.float32) for jb in up), torch.zeros(T)) - \
+                sum(((blk >= jb).to(torch.float32) for jb in down), torch.zeros(T))
         gain = torch.tensor([12.0, -12.0, 3.0, 0.0])[torch.arange(T) % 4]
         ab = (16.0 / LOG2E) ** 0.5          # alpha * beta / 16 * log2(e) == 1 log2 unit per (gain x step)
         for h in range(H):

@@ -78,3 +78,54 @@ def test_two_rank_gradient_allreduce_averages_one_flat_bucket():
     want = [1.5 * (i + 1) for i in range(4)]          # mean of (1, 2) * (i + 1)
     assert ret[0][0] == ret[1][0] == 5 * 3 + 3 + 3 * 2 + 2
     assert ret[0][1] == want and ret[1][1] == want
+
+
+def _bucket_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from avsum_b200.training import GradBuckets
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Tanh(),
+                              torch.nn.Linear(4, 1))
+    unused = torch.nn.Parameter(torch.ones(3))             # never reaches the loss: must end with a zero gradient
+    params = list(net.parameters()) + [unused]
+    gb = GradBuckets(params, bucket_mb=30 * 4 / (1 << 20))    # ~30 elements per bucket -> several buckets
+    x = torch.randn(7, 6, generator=torch.Generator().manual_seed(10 + rank))
+    out = []
+    for _ in range(2):                                      # two steps: the hooks re-arm
+        for p in params:
+            p.grad = None
+        gb.start()
+        net(x).pow(2).mean().backward()
+        n = gb.finish()
+        out.append([p.grad.clone() for p in params])
+    ret[rank] = (n, len(gb.buckets), [[g.tolist() for g in step] for step in out],
+                 all(p.grad.data_ptr() == gb.slot[id(p)][0].data_ptr() for p in params))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_overlapped_allreduce_equals_the_mean_of_local_gradients():
+    """training.GradBuckets: gradients land in one flat buffer (reverse parameter order), buckets are all-reduced
+    asynchronously from the autograd hooks, finish() averages -- equal to the mean of the two ranks' local gradients,
+    on both ranks, for two consecutive steps; a parameter without gradient gets zeros."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_bucket_worker, args=(2, port, ret), nprocs=2, join=True)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Tanh(),
+                              torch.nn.Linear(4, 1))
+    local = []
+    for rank in range(2):
+        net.zero_grad()
+        x = torch.randn(7, 6, generator=torch.Generator().manual_seed(10 + rank))
+        net(x).pow(2).mean().backward()
+        local.append([p.grad.clone() for p in net.parameters()])
+    want = [(a + b) / 2 for a, b in zip(*local)] + [torch.zeros(3)]
+    assert ret[0][0] == ret[1][0] == sum(w.numel() for w in want)
+    assert ret[0][1] >= 3 and ret[0][3] and ret[1][3]       # several buckets; p.grad are views of the flat buffer
+    for rank in range(2):
+        for step in ret[rank][2]:
+            for g, w in zip(step, want):
+                assert torch.allclose(torch.tensor(g), w, rtol=1e-6, atol=1e-7)
