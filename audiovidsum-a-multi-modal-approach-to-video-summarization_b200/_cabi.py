@@ -18,6 +18,7 @@ AVS_OK, AVS_ERR_INVALID, AVS_ERR_UNSUPPORTED, AVS_ERR_CUDA, AVS_ERR_OOM = range(
 AVS_HOST, AVS_DEVICE = 0, 1
 AVS_ATTN_LITERAL, AVS_ATTN_TEMPORAL, AVS_ATTN_LITERAL_B1 = 0, 1, 2
 AVS_PREC_TF32, AVS_PREC_BF16, AVS_PREC_FP32_SIMT = 0, 1, 2
+AVS_FEAT_F32, AVS_FEAT_F16 = 0, 1
 
 ATTN_AXES = {"literal": AVS_ATTN_LITERAL, "temporal": AVS_ATTN_TEMPORAL, "literal_b1": AVS_ATTN_LITERAL_B1}
 PRECISIONS = {"tf32": AVS_PREC_TF32, "bf16": AVS_PREC_BF16, "fp32_simt": AVS_PREC_FP32_SIMT}
@@ -32,6 +33,7 @@ EXPORTS = [
     "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
     "avs_debug_e2e_trace", "avs_forward_summarize_async", "avs_slot_wait",
     "avs_debug_gemm_trace", "avs_model_update_async", "avs_host_alloc", "avs_host_free",
+    "avs_model_set_feature_format",
 ]
 
 
@@ -95,6 +97,8 @@ def lib() -> C.CDLL:
     L.avs_model_update.argtypes = [vp, C.POINTER(AvsWeights)]
     L.avs_model_update_async.restype = C.c_int
     L.avs_model_update_async.argtypes = [vp, C.POINTER(AvsWeights), C.c_int, vp]
+    L.avs_model_set_feature_format.restype = C.c_int
+    L.avs_model_set_feature_format.argtypes = [vp, C.c_int]
     L.avs_host_alloc.restype = C.c_int
     L.avs_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t, C.c_int]
     L.avs_host_free.restype = C.c_int

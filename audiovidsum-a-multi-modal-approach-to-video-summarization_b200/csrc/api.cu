@@ -133,6 +133,14 @@ constexpr int G4 = 4 * HC;  // 1024 gate rows per direction
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// feature buffers are fp32 or (avs_model_set_feature_format) fp16: pointer arithmetic in bytes
+inline const float* feat_at(const float* base, int64_t row, int dim, size_t fsz) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + static_cast<size_t>(row) * dim * fsz);
+}
+inline float* feat_at(float* base, int64_t row, int dim, size_t fsz) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + static_cast<size_t>(row) * dim * fsz);
+}
+
 struct Arena {
     char* base = nullptr;
     size_t cap = 0;
@@ -200,6 +208,7 @@ using namespace avs;
 struct avs_model {
     int device = 0;
     int Dv = 0, Da = 0, heads = 4;
+    int feat_f16 = 0;   // avs_model_set_feature_format: the caller's visual / audio buffers hold IEEE fp16, not fp32
     // packed parameters (one slab); *_x = exact fp32, *_t = tf32-rounded copies
     char* slab = nullptr;
     float *fc_v_w_x, *fc_v_w_t, *fc_a_w_x, *fc_a_w_t, *fc_v_b, *fc_a_b;
@@ -213,6 +222,7 @@ struct avs_model {
     uint16_t *fc_v_w_l[2], *fc_a_w_l[2], *ih_v_l[2], *ih_a_l[2], *in_w_l[2], *out_w_l[2], *sc0_w_l[2];
     Arena ws;       // activations
     Arena staging;  // raw weights during packing
+    Arena pack_ws;  // padded / sparse batches: the valid rows packed densely (features in, scores out)
     // device copies of host-space inputs when a call is pipelined by video group, and the pooling / knapsack
     // workspace; two slots so that avs_forward_summarize_async can stream batch i+1 while batch i finishes
     static constexpr int SLOTS = 2;
@@ -672,12 +682,25 @@ avs_status avs_model_update_async(avs_model* m, const avs_weights* w, int lstm_o
     return pack_weights(m, w, static_cast<cudaStream_t>(cuda_stream), lstm_only != 0, false);
 }
 
+avs_status avs_model_set_feature_format(avs_model* m, int format) {
+    AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
+    AVS_CHECK(format == AVS_FEAT_F32 || format == AVS_FEAT_F16, AVS_ERR_INVALID, "bad feature format %d", format);
+    AVS_CHECK(format == AVS_FEAT_F32 || (m->Dv % 8 == 0 && m->Da % 8 == 0), AVS_ERR_UNSUPPORTED,
+              "fp16 features need visual_dim / audio_dim that are multiples of 8 (16-byte TMA row pitch); got %d / %d",
+              m->Dv, m->Da);
+    for (int i = 0; i < avs_model::SLOTS; ++i)
+        AVS_CHECK(!m->slot_busy[i], AVS_ERR_INVALID, "slot %d is in flight: call avs_slot_wait first", i);
+    m->feat_f16 = format == AVS_FEAT_F16;
+    return AVS_OK;
+}
+
 void avs_model_destroy(avs_model* m) {
     if (!m) return;
     Guard g(m->device);
     cudaDeviceSynchronize();
     m->ws.release();
     m->staging.release();
+    m->pack_ws.release();
     for (int i = 0; i < avs_model::SLOTS; ++i) {
         m->host_in[i].release();
         if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
@@ -725,6 +748,52 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
     // video first (data/dataset.py packed_batches does) hide most of the compute behind the transfer.
     const bool per_video = attn_axis == AVS_ATTN_TEMPORAL || attn_axis == AVS_ATTN_LITERAL_B1;
     const bool host = space == AVS_HOST;
+    // Padded / sparse layouts (BASELINE configs[2]: [B, Tmax] rows with lengths[B]): every GEMM would process the rows
+    // no video owns -- 47 % of the rows of the SumMe-shaped batch.  The valid rows are packed densely first (one
+    // copy per video: device-to-device, or straight from the caller's host buffer, which also saves the PCIe bytes
+    // of the padding), the forward runs on the packed rows, and the scores are copied back to each video's rows.
+    // Rows no video owns are not written.
+    if (m != nullptr && (host || space == AVS_DEVICE) && per_video && visual && audio && scores && !scores_dev_out &&
+        row_start && lengths && n_videos >= 1 && total_rows >= 256 && total_rows < (1ll << 31) &&
+        getenv("AVS_NO_ROW_PACKING") == nullptr) {
+        int64_t covered = 0;
+        bool ok = true;
+        for (int b = 0; b < n_videos && ok; ++b) {
+            ok = lengths[b] >= 0 && row_start[b] >= 0 && static_cast<int64_t>(row_start[b]) + lengths[b] <= total_rows;
+            covered += ok ? lengths[b] : 0;
+        }
+        if (ok && covered > 0 && covered * 10 < total_rows * 9) {
+            AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
+            Guard gp(m->device);
+            cudaStream_t sp = static_cast<cudaStream_t>(cuda_stream);
+            const size_t C_ = static_cast<size_t>(covered), Dv_ = m->Dv, Da_ = m->Da, fsz = m->feat_f16 ? 2 : 4;
+            AVS_TRY(m->pack_ws.reserve(C_ * (Dv_ + Da_) * fsz + C_ * 4 + 4 * 256));
+            m->pack_ws.reset();
+            float* pv = reinterpret_cast<float*>(m->pack_ws.take<char>(C_ * Dv_ * fsz));
+            float* pa = reinterpret_cast<float*>(m->pack_ws.take<char>(C_ * Da_ * fsz));
+            float* ps = m->pack_ws.take<float>(C_);
+            std::vector<int32_t> prs(n_videos);
+            int64_t at = 0;
+            const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            for (int b = 0; b < n_videos; ++b) {
+                prs[b] = static_cast<int32_t>(at);
+                const size_t n = static_cast<size_t>(lengths[b]);
+                if (n) {
+                    AVS_CUDA(cudaMemcpyAsync(feat_at(pv, at, m->Dv, fsz), feat_at(visual, row_start[b], m->Dv, fsz), n * Dv_ * fsz, kin, sp));
+                    AVS_CUDA(cudaMemcpyAsync(feat_at(pa, at, m->Da, fsz), feat_at(audio, row_start[b], m->Da, fsz), n * Da_ * fsz, kin, sp));
+                }
+                at += lengths[b];
+            }
+            AVS_TRY(forward_entry(m, pv, pa, covered, n_videos, prs.data(), lengths, attn_axis, precision, ps, AVS_DEVICE,
+                                  cuda_stream, nullptr, nullptr, nullptr));
+            const cudaMemcpyKind kout = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+            for (int b = 0; b < n_videos; ++b)
+                if (lengths[b])
+                    AVS_CUDA(cudaMemcpyAsync(scores + row_start[b], ps + prs[b], static_cast<size_t>(lengths[b]) * 4, kout, sp));
+            if (host) AVS_CUDA(cudaStreamSynchronize(sp));
+            return AVS_OK;
+        }
+    }
     int n_groups = 1;
     if (m != nullptr && (host || space == AVS_DEVICE) && per_video && visual && audio && (scores || scores_dev_out) &&
         row_start && lengths && n_videos >= 2 && total_rows >= 4096 && total_rows < (1ll << 31)) {
@@ -762,16 +831,16 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
         AVS_CHECK(m && visual && audio && total_rows >= 0, AVS_ERR_INVALID, "avs_forward_summarize: bad arguments");
         Guard g1(m->device);
         cudaStream_t s1 = static_cast<cudaStream_t>(cuda_stream);
-        const size_t r1 = static_cast<size_t>(total_rows);
+        const size_t r1 = static_cast<size_t>(total_rows), fsz1 = m->feat_f16 ? 2 : 4;
         Arena& HI = m->host_in[slot];
-        AVS_TRY(HI.reserve(r1 * (m->Dv + m->Da + 2) * 4 + 5 * 256));
+        AVS_TRY(HI.reserve(r1 * (m->Dv + m->Da) * fsz1 + r1 * 8 + 5 * 256));
         HI.reset();
-        float* v1 = HI.take<float>(r1 * m->Dv);
-        float* a1 = HI.take<float>(r1 * m->Da);
+        float* v1 = reinterpret_cast<float*>(HI.take<char>(r1 * m->Dv * fsz1));
+        float* a1 = reinterpret_cast<float*>(HI.take<char>(r1 * m->Da * fsz1));
         float* sc1 = HI.take<float>(r1);
         int32_t* p1 = HI.take<int32_t>(r1);
-        AVS_CUDA(cudaMemcpyAsync(v1, visual, r1 * m->Dv * 4, cudaMemcpyHostToDevice, s1));
-        AVS_CUDA(cudaMemcpyAsync(a1, audio, r1 * m->Da * 4, cudaMemcpyHostToDevice, s1));
+        AVS_CUDA(cudaMemcpyAsync(v1, visual, r1 * m->Dv * fsz1, cudaMemcpyHostToDevice, s1));
+        AVS_CUDA(cudaMemcpyAsync(a1, audio, r1 * m->Da * fsz1, cudaMemcpyHostToDevice, s1));
         if (positions_host) AVS_CUDA(cudaMemcpyAsync(p1, positions_host, r1 * 4, cudaMemcpyHostToDevice, s1));
         *scores_dev_out = sc1;
         if (positions_dev_out) *positions_dev_out = p1;
@@ -783,17 +852,17 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
     Guard g(m->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int Dv = m->Dv, Da = m->Da;
-    const size_t uR = static_cast<size_t>(total_rows);
+    const size_t uR = static_cast<size_t>(total_rows), fsz = m->feat_f16 ? 2 : 4;
     const float* in_v = visual;
     const float* in_a = audio;
     float* sc_dev = scores;
     int32_t* pos_dev = nullptr;
     if (host) {
         Arena& HI = m->host_in[slot];
-        AVS_TRY(HI.reserve(uR * (Dv + Da + 2) * 4 + 5 * 256));
+        AVS_TRY(HI.reserve(uR * (Dv + Da) * fsz + uR * 8 + 5 * 256));
         HI.reset();
-        in_v = HI.take<float>(uR * Dv);
-        in_a = HI.take<float>(uR * Da);
+        in_v = reinterpret_cast<float*>(HI.take<char>(uR * Dv * fsz));
+        in_a = reinterpret_cast<float*>(HI.take<char>(uR * Da * fsz));
         sc_dev = HI.take<float>(uR);
         pos_dev = HI.take<int32_t>(uR);
     }
@@ -852,10 +921,10 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
         for (int gi = 0; gi < n_groups; ++gi) {
             const size_t rows = static_cast<size_t>(hi[gi] - lo[gi]);
             if (rows) {
-                AVS_CUDA(cudaMemcpyAsync(const_cast<float*>(in_v) + lo[gi] * Dv, visual + lo[gi] * Dv, rows * Dv * 4,
-                                         cudaMemcpyHostToDevice, m->copy_stream));
-                AVS_CUDA(cudaMemcpyAsync(const_cast<float*>(in_a) + lo[gi] * Da, audio + lo[gi] * Da, rows * Da * 4,
-                                         cudaMemcpyHostToDevice, m->copy_stream));
+                AVS_CUDA(cudaMemcpyAsync(feat_at(const_cast<float*>(in_v), lo[gi], Dv, fsz), feat_at(visual, lo[gi], Dv, fsz),
+                                         rows * Dv * fsz, cudaMemcpyHostToDevice, m->copy_stream));
+                AVS_CUDA(cudaMemcpyAsync(feat_at(const_cast<float*>(in_a), lo[gi], Da, fsz), feat_at(audio, lo[gi], Da, fsz),
+                                         rows * Da * fsz, cudaMemcpyHostToDevice, m->copy_stream));
             }
             AVS_CUDA(cudaEventRecord(m->ev_chunk[gi], m->copy_stream));
             if (trace) cudaEventRecord(g_e2e.chunk[gi], m->copy_stream);
@@ -874,7 +943,7 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
         cudaStream_t gs = gi == 0 ? st : m->grp_stream[gi - 1];
         if (gi > 0 && !async) AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_start, 0));   // not before earlier work on st is done
         if (host) AVS_CUDA(cudaStreamWaitEvent(gs, m->ev_chunk[gi], 0));
-        AVS_TRY(forward_impl(m, in_v + lo[gi] * Dv, in_a + lo[gi] * Da, hi[gi] - lo[gi], nv, rs.data(),
+        AVS_TRY(forward_impl(m, feat_at(in_v, lo[gi], Dv, fsz), feat_at(in_a, lo[gi], Da, fsz), hi[gi] - lo[gi], nv, rs.data(),
                              lengths + first[gi], attn_axis, precision, sc_dev + lo[gi], AVS_DEVICE, gs,
                              gi == 0 ? nullptr : &m->ws_grp[gi - 1], (!host && gi == 0) ? 0 : -1));
         if (trace) cudaEventRecord(g_e2e.grp[gi], gs);
@@ -926,7 +995,14 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     // saturating) and feeds kind::f16.  AVS_PREC_BF16: bf16 everywhere.  Accumulation, gate pre-activations,
     // cell state, softmax statistics and the score head stay fp32 in all modes.
     const int act = simt ? DT_F32 : (bf16 ? DT_BF16 : DT_F16);   // internal activations
-    const int in_dt = bf16 ? DT_BF16 : DT_F32;                   // what the fc GEMMs read
+    // fp16 feature format (avs_model_set_feature_format): the caller's buffers already hold 16-bit operands -- half
+    // the PCIe / HBM bytes; they feed kind::f16 GEMMs against the fp16 weight copies directly (exact operands, no
+    // truncation to compensate).  Only with the default precision (fp16 activations).
+    const bool f16_in = m->feat_f16 != 0;
+    AVS_CHECK(!f16_in || precision == AVS_PREC_TF32, AVS_ERR_UNSUPPORTED,
+              "fp16 feature buffers need the default precision mode (AVS_PREC_TF32: fp16 operands behind the fc layers)");
+    const size_t fsz = f16_in ? 2 : 4;
+    const int in_dt = bf16 ? DT_BF16 : (f16_in ? DT_F16 : DT_F32);   // what the fc GEMMs read
     const size_t asz = dtype_size(act);
 
     bool literal_rows = attn_axis == AVS_ATTN_LITERAL_B1 || (attn_axis == AVS_ATTN_LITERAL && n_videos == 1);
@@ -943,13 +1019,13 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     const bool tc_attn = !simt && attn_axis == AVS_ATTN_TEMPORAL && E == m->heads * 256;
     const int qkv_dt = tc_attn ? act : DT_F32;
     const size_t uR = static_cast<size_t>(R);
-    const size_t bytes = uR * (Dv + Da) * 4 + (bf16 ? uR * (Dv + Da) * 2 : 0) + 2 * uR * H * asz + 2 * uR * 2 * G4 * 4 +
+    const size_t bytes = uR * (Dv + Da) * fsz + (bf16 ? uR * (Dv + Da) * 2 : 0) + 2 * uR * H * asz + 2 * uR * 2 * G4 * 4 +
                          3 * uR * E * asz + (literal_rows ? 0 : uR * 3 * E * dtype_size(qkv_dt)) + uR * 4 +
                          (plan.host.size() + 3 * static_cast<size_t>(n_seqs)) * 4 + 64 * 256;
     AVS_TRY(WS.reserve(bytes));
     WS.reset();
-    float* in_v = WS.take<float>(uR * Dv);
-    float* in_a = WS.take<float>(uR * Da);
+    float* in_v = reinterpret_cast<float*>(WS.take<char>(uR * Dv * fsz));
+    float* in_a = reinterpret_cast<float*>(WS.take<char>(uR * Da * fsz));
     uint16_t* in_v16 = bf16 ? WS.take<uint16_t>(uR * Dv) : nullptr;
     uint16_t* in_a16 = bf16 ? WS.take<uint16_t>(uR * Da) : nullptr;
     char* v_emb = WS.take<char>(uR * H * asz);
@@ -982,10 +1058,10 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         for (int c = 0; c < n_chunks; ++c) {
             const int64_t r0 = c * chunk_rows, r1 = std::min<int64_t>(R, r0 + chunk_rows);
             if (r0 >= r1) break;
-            AVS_CUDA(cudaMemcpyAsync(in_v + r0 * Dv, visual + r0 * Dv, static_cast<size_t>(r1 - r0) * Dv * 4,
-                                     cudaMemcpyHostToDevice, m->copy_stream));
-            AVS_CUDA(cudaMemcpyAsync(in_a + r0 * Da, audio + r0 * Da, static_cast<size_t>(r1 - r0) * Da * 4,
-                                     cudaMemcpyHostToDevice, m->copy_stream));
+            AVS_CUDA(cudaMemcpyAsync(feat_at(in_v, r0, Dv, fsz), feat_at(visual, r0, Dv, fsz),
+                                     static_cast<size_t>(r1 - r0) * Dv * fsz, cudaMemcpyHostToDevice, m->copy_stream));
+            AVS_CUDA(cudaMemcpyAsync(feat_at(in_a, r0, Da, fsz), feat_at(audio, r0, Da, fsz),
+                                     static_cast<size_t>(r1 - r0) * Da * fsz, cudaMemcpyHostToDevice, m->copy_stream));
             AVS_CUDA(cudaEventRecord(m->ev_chunk[c], m->copy_stream));
         }
     }
@@ -993,18 +1069,18 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         const int64_t r0 = c * chunk_rows, r1 = std::min<int64_t>(R, r0 + chunk_rows);
         if (r0 >= r1) break;
         const int64_t Rc = r1 - r0;
-        const float* src_v = (space == AVS_HOST ? in_v : visual) + r0 * Dv;
-        const float* src_a = (space == AVS_HOST ? in_a : audio) + r0 * Da;
+        const float* src_v = feat_at(space == AVS_HOST ? in_v : visual, r0, Dv, fsz);
+        const float* src_a = feat_at(space == AVS_HOST ? in_a : audio, r0, Da, fsz);
         if (space == AVS_HOST) AVS_CUDA(cudaStreamWaitEvent(st, m->ev_chunk[c], 0));
         // the GEMMs read the features through TMA, which needs 16-byte aligned rows: a caller-owned device buffer
         // that is not (never the case for a torch tensor) is staged in the workspace first
         if (space == AVS_DEVICE && !simt && (reinterpret_cast<uintptr_t>(src_v) & 15)) {
-            AVS_CUDA(cudaMemcpyAsync(in_v + r0 * Dv, src_v, static_cast<size_t>(Rc) * Dv * 4, cudaMemcpyDeviceToDevice, st));
-            src_v = in_v + r0 * Dv;
+            AVS_CUDA(cudaMemcpyAsync(feat_at(in_v, r0, Dv, fsz), src_v, static_cast<size_t>(Rc) * Dv * fsz, cudaMemcpyDeviceToDevice, st));
+            src_v = feat_at(in_v, r0, Dv, fsz);
         }
         if (space == AVS_DEVICE && !simt && (reinterpret_cast<uintptr_t>(src_a) & 15)) {
-            AVS_CUDA(cudaMemcpyAsync(in_a + r0 * Da, src_a, static_cast<size_t>(Rc) * Da * 4, cudaMemcpyDeviceToDevice, st));
-            src_a = in_a + r0 * Da;
+            AVS_CUDA(cudaMemcpyAsync(feat_at(in_a, r0, Da, fsz), src_a, static_cast<size_t>(Rc) * Da * fsz, cudaMemcpyDeviceToDevice, st));
+            src_a = feat_at(in_a, r0, Da, fsz);
         }
         const void* xv = src_v;
         const void* xa = src_a;
@@ -1032,7 +1108,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         e1.relu = 1;
         e1.out_dtype = act;
         e1.ldc = H;
-        if (!simt && !bf16) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
+        if (!simt && !bf16 && !f16_in) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
         GemmEpilogue e2;
         e2.ldc = 2 * G4;
         if (sa != st) {

@@ -218,15 +218,23 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_kernel(SummaryBatch b,
 //     two loads + one store, in int32 when the total value fits (S <= 127 shots of <= 2^24 each),
 //   * the keyshot bitmap is produced 16 bytes per thread with one binary search per block.
 // Bit-exact against the same oracle as the general kernel above (which remains for oversized videos).
-constexpr int KNAP_CPT = 4;   // DP cells per thread
+constexpr int KNAP_CPT = 4;   // DP cells per thread (fast path)
+// Long videos (BASELINE configs[3]: T = 8192 -> 122,880 frames, capacity 18,432, ~750 shots): the same scheme with
+// 512 threads x up to 40 register-resident cells.  One DP row no longer fits twice in shared memory (2 x 147 KB), so
+// the row is published into a SINGLE buffer (two barriers per item instead of one), the keep bits (S x words x 4 B =
+// 1.7 MB) go to the global workspace, and the back-trace stages them back through the (then free) row buffer in
+// chunks of ~60 items, so that the single-thread walk reads shared memory instead of 750 dependent L2 round trips.
+// Measured on B200, 8 videos x T = 8192: 5.46 ms (general kernel: DP rows in L2) -> see DESIGN.md.
+constexpr int KNAP_BIG_THREADS = 512;
+constexpr int KNAP_BIG_CPT = 40;
 
-template <typename V>
-__global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatch b, const float* __restrict__ scores,
-                                                                     const int32_t* __restrict__ positions,
-                                                                     long long* __restrict__ seg_mean_out,
-                                                                     uint8_t* __restrict__ picks,
-                                                                     uint8_t* __restrict__ summary, int rows_cap,
-                                                                     int items_cap) {
+template <typename V, int CPT, int NT, bool BIG>
+__global__ void __launch_bounds__(NT) knapsack_fast_kernel(SummaryBatch b, const float* __restrict__ scores,
+                                                           const int32_t* __restrict__ positions,
+                                                           long long* __restrict__ seg_mean_out,
+                                                           uint8_t* __restrict__ picks,
+                                                           uint8_t* __restrict__ summary, int rows_cap,
+                                                           int items_cap, uint32_t* __restrict__ keep_bits) {
     extern __shared__ long long fsm[];
     const int v = blockIdx.x;
     const int tid = threadIdx.x;
@@ -239,12 +247,13 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatc
 
     long long* item_val = fsm;                                           // [items_cap]  sums, then pooled values
     V* buf_a = reinterpret_cast<V*>(item_val + items_cap);               // [rows_cap]
-    V* buf_b = buf_a + rows_cap + (rows_cap & 1);                        // [rows_cap]  (kept 8-byte aligned)
+    V* buf_b = BIG ? buf_a : buf_a + rows_cap + (rows_cap & 1);          // [rows_cap]  (kept 8-byte aligned)
     int* item_beg = reinterpret_cast<int*>(buf_b + rows_cap + (rows_cap & 1));   // [items_cap] first frame of the shot
     int* item_len = item_beg + items_cap;                                // [items_cap] frames; negated once not picked
-    uint32_t* keep = reinterpret_cast<uint32_t*>(item_len + items_cap);  // [S][words]
+    uint32_t* keep = BIG ? keep_bits + b.keep_start[v]                   // [S][words]: global workspace (BIG) ...
+                         : reinterpret_cast<uint32_t*>(item_len + items_cap);   // ... or shared memory
 
-    for (int s = tid; s < S; s += KNAP_THREADS) {
+    for (int s = tid; s < S; s += NT) {
         const int2 seg = cps[s];
         item_beg[s] = seg.x;
         item_len[s] = seg.y - seg.x + 1;
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatc
     {
         const int row0 = b.row_start[v], T = b.lengths[v];
         unsigned long long* acc = reinterpret_cast<unsigned long long*>(item_val);
-        for (int i = tid; i < T; i += KNAP_THREADS) {
+        for (int i = tid; i < T; i += NT) {
             const long long q = quantize_score(scores[row0 + i]);
             const int lo = positions[row0 + i];
             const int hi = (i + 1 < T) ? positions[row0 + i + 1] : nf;
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatc
         }
     }
     __syncthreads();
-    for (int s = tid; s < S; s += KNAP_THREADS) {
+    for (int s = tid; s < S; s += NT) {
         const int wt = item_len[s];
         const unsigned long long sum = static_cast<unsigned long long>(item_val[s]);
         const long long val = wt > 0 ? static_cast<long long>((2ull * sum + wt) / (2ull * wt)) : 0ll;
@@ -282,23 +291,23 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatc
         item_val[s] = val;
     }
     // ---- K8: DP with register-resident cells
-    V mine[KNAP_CPT];
+    V mine[CPT];
 #pragma unroll
-    for (int c = 0; c < KNAP_CPT; ++c) {
+    for (int c = 0; c < CPT; ++c) {
         mine[c] = 0;
-        const int w = tid + c * KNAP_THREADS;
+        const int w = tid + c * NT;
         if (w <= cap) buf_a[w] = 0;
     }
     __syncthreads();
     for (int s = 0; s < S; ++s) {
         const int wt = item_len[s];
         const V val = static_cast<V>(item_val[s]);
-        const V* rd = (s & 1) ? buf_b : buf_a;
-        V* wr = (s & 1) ? buf_a : buf_b;
+        const V* rd = (BIG || !(s & 1)) ? buf_a : buf_b;
+        V* wr = (BIG || (s & 1)) ? buf_a : buf_b;
 #pragma unroll
-        for (int c = 0; c < KNAP_CPT; ++c) {
-            const int w = tid + c * KNAP_THREADS;
-            if (c * KNAP_THREADS <= cap) {   // warp-uniform
+        for (int c = 0; c < CPT; ++c) {
+            const int w = tid + c * NT;
+            if (c * NT <= cap) {   // warp-uniform
                 bool better = false;
                 if (w <= cap) {
                     const V old = mine[c];
@@ -311,21 +320,56 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatc
                         better = true;
                     }
                     mine[c] = better ? cand : old;
-                    wr[w] = mine[c];
+                    if (!BIG) wr[w] = mine[c];
                 }
                 const uint32_t bits = __ballot_sync(0xffffffffu, better);
-                if ((tid & 31) == 0 && (w >> 5) < words) keep[s * words + (w >> 5)] = bits;
+                if ((tid & 31) == 0 && (w >> 5) < words) keep[static_cast<size_t>(s) * words + (w >> 5)] = bits;
             }
         }
         __syncthreads();
+        if (BIG) {   // single buffer: everybody has read row s - 1, now publish row s
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int w = tid + c * NT;
+                if (w <= cap) wr[w] = mine[c];
+            }
+            __syncthreads();
+        }
     }
-    if (tid == 0) {
-        int w = cap;
-        for (int s = S - 1; s >= 0; --s) {
-            const int take = (keep[s * words + (w >> 5)] >> (w & 31)) & 1;
-            picks[s0 + s] = static_cast<uint8_t>(take);
-            if (take) w -= item_len[s];
-            else item_len[s] = -item_len[s];          // the bitmap pass reads the selection from the sign
+    if (!BIG) {
+        if (tid == 0) {
+            int w = cap;
+            for (int s = S - 1; s >= 0; --s) {
+                const int take = (keep[s * words + (w >> 5)] >> (w & 31)) & 1;
+                picks[s0 + s] = static_cast<uint8_t>(take);
+                if (take) w -= item_len[s];
+                else item_len[s] = -item_len[s];          // the bitmap pass reads the selection from the sign
+            }
+        }
+    } else {
+        // back-trace in chunks of items whose keep rows fit in the row buffer (the DP values are no longer needed)
+        __threadfence_block();
+        uint32_t* stage = reinterpret_cast<uint32_t*>(buf_a);
+        const int chunk = max(1, static_cast<int>((static_cast<size_t>(rows_cap) * sizeof(V)) / (static_cast<size_t>(words) * 4)));
+        __shared__ int w_cursor;
+        if (tid == 0) w_cursor = cap;
+        for (int hi = S; hi > 0; hi -= chunk) {
+            const int lo = max(0, hi - chunk);
+            __syncthreads();   // stage free (and, first time, every keep word written)
+            const size_t n_words = static_cast<size_t>(hi - lo) * words;
+            const uint32_t* src = keep + static_cast<size_t>(lo) * words;
+            for (size_t i = tid; i < n_words; i += NT) stage[i] = src[i];
+            __syncthreads();
+            if (tid == 0) {
+                int w = w_cursor;
+                for (int s = hi - 1; s >= lo; --s) {
+                    const int take = (stage[static_cast<size_t>(s - lo) * words + (w >> 5)] >> (w & 31)) & 1;
+                    picks[s0 + s] = static_cast<uint8_t>(take);
+                    if (take) w -= item_len[s];
+                    else item_len[s] = -item_len[s];
+                }
+                w_cursor = w;
+            }
         }
     }
     if (summary == nullptr) return;
@@ -349,12 +393,12 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatc
     const uintptr_t addr = reinterpret_cast<uintptr_t>(out);
     const int head = min(nf, static_cast<int>((16 - (addr & 15)) & 15));
     const int body = (nf - head) / 16;
-    for (int f = tid; f < head; f += KNAP_THREADS) {
+    for (int f = tid; f < head; f += NT) {
         int s = shot_of(f);
         out[f] = static_cast<uint8_t>(bit_at(f, s));
     }
     uint4* o4 = reinterpret_cast<uint4*>(out + head);
-    for (int i = tid; i < body; i += KNAP_THREADS) {
+    for (int i = tid; i < body; i += NT) {
         const int f0 = head + 16 * i;
         int s = shot_of(f0);
         uint32_t wv[4];
@@ -367,7 +411,7 @@ __global__ void __launch_bounds__(KNAP_THREADS) knapsack_fast_kernel(SummaryBatc
         }
         o4[i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     }
-    for (int f = head + body * 16 + tid; f < nf; f += KNAP_THREADS) {
+    for (int f = head + body * 16 + tid; f < nf; f += NT) {
         int s = shot_of(f);
         out[f] = static_cast<uint8_t>(bit_at(f, s));
     }
@@ -444,21 +488,40 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
             const int dev = current_device();
             if (narrow) {
                 if (cfg32.needed(dev) && need > 48 * 1024) {
-                    AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  static_cast<int>(limit)));
+                    AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<int, KNAP_CPT, KNAP_THREADS, false>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(limit)));
                     cfg32.mark(dev);
                 }
-                knapsack_fast_kernel<int><<<b.n, KNAP_THREADS, need, stream>>>(b, scores, positions, seg_mean, picks,
-                                                                               summary, rows, items);
+                knapsack_fast_kernel<int, KNAP_CPT, KNAP_THREADS, false><<<b.n, KNAP_THREADS, need, stream>>>(
+                    b, scores, positions, seg_mean, picks, summary, rows, items, nullptr);
             } else {
                 if (cfg64.needed(dev) && need > 48 * 1024) {
-                    AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<long long>,
+                    AVS_CUDA(cudaFuncSetAttribute(knapsack_fast_kernel<long long, KNAP_CPT, KNAP_THREADS, false>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(limit)));
                     cfg64.mark(dev);
                 }
-                knapsack_fast_kernel<long long><<<b.n, KNAP_THREADS, need, stream>>>(b, scores, positions, seg_mean,
-                                                                                     picks, summary, rows, items);
+                knapsack_fast_kernel<long long, KNAP_CPT, KNAP_THREADS, false><<<b.n, KNAP_THREADS, need, stream>>>(
+                    b, scores, positions, seg_mean, picks, summary, rows, items, nullptr);
             }
+            AVS_LAUNCH_CHECK();
+            return AVS_OK;
+        }
+    }
+    // ---- long videos: register-resident DP cells, ONE row buffer in shared memory, keep bits in the workspace
+    if (scores != nullptr && b.max_cap + 1 <= KNAP_BIG_CPT * KNAP_BIG_THREADS && keep_bits != nullptr) {
+        const int rows = b.max_cap + 1, items = std::max(b.max_S, 1);
+        const size_t need = static_cast<size_t>(items) * 8 + (static_cast<size_t>(rows) + 1) * 8 +
+                            static_cast<size_t>(items) * 8 + 64;
+        if (need <= limit) {
+            static PerDeviceOnce cfg;
+            const int dev = current_device();
+            auto kern = knapsack_fast_kernel<long long, KNAP_BIG_CPT, KNAP_BIG_THREADS, true>;
+            if (cfg.needed(dev)) {
+                AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(limit)));
+                cfg.mark(dev);
+            }
+            kern<<<b.n, KNAP_BIG_THREADS, need, stream>>>(b, scores, positions, seg_mean, picks, summary, rows, items,
+                                                          keep_bits);
             AVS_LAUNCH_CHECK();
             return AVS_OK;
         }

@@ -45,21 +45,30 @@ class PackedBatch:
 
     def __init__(self, indices, visual, audio, scores, row_start, lengths):
         self.indices = indices          # dataset indices of the videos, in batch order
-        self.visual = visual            # fp32 [sum T, Dv] pinned
-        self.audio = audio              # fp32 [sum T, Da] pinned
+        self.visual = visual            # fp32 (or fp16, feature_dtype="fp16") [sum T, Dv] pinned
+        self.audio = audio              # fp32 (or fp16) [sum T, Da] pinned
         self.scores = scores            # [sum T] pinned (dtype of scores.npy)
         self.row_start = row_start      # int32 [n]
         self.lengths = lengths          # int32 [n]
 
 
 def packed_batches(dataset, max_frames: int = 32768, max_videos: int = 64, bucket: bool = True,
-                   pin: Optional[bool] = None) -> Iterator[PackedBatch]:
+                   pin: Optional[bool] = None, feature_dtype: str = "fp32") -> Iterator[PackedBatch]:
     """Yield PackedBatch objects covering the dataset once.
+
+    ``feature_dtype="fp16"`` (opt-in) packs the features as IEEE half: the batch is half as large on its way across
+    PCIe -- the end-to-end step of a streamed evaluation is transfer-bound -- and the library reads it directly
+    (``avs_model_set_feature_format``; the fc layers of the default precision mode consume 11-bit significands either
+    way).  Values must fit the fp16 range (|x| < 65504; CNN / VGGish features do); the default stays float32, the
+    reference's on-disk type (``data/dataset.py:25-28``).
 
     Videos are sorted by length (longest first) when ``bucket`` is set, so that the videos of one batch -- which
     share LSTM clusters whose run time is set by their longest member -- have similar lengths; a batch closes
     when adding a video would exceed ``max_frames`` rows or ``max_videos`` videos.
     """
+    if feature_dtype not in ("fp32", "fp16"):
+        raise ValueError("feature_dtype must be 'fp32' or 'fp16'")
+    fdt = torch.float16 if feature_dtype == "fp16" else torch.float32
     pin = torch.cuda.is_available() if pin is None else pin
     items = [dataset[i] for i in range(len(dataset))]
     order = list(range(len(items)))
@@ -71,8 +80,8 @@ def packed_batches(dataset, max_frames: int = 32768, max_videos: int = 64, bucke
     def flush(idxs):
         lens = np.asarray([int(items[i][0]["visual"].shape[0]) for i in idxs], dtype=np.int32)
         starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
-        visual = torch.cat([items[i][0]["visual"].to(torch.float32) for i in idxs])
-        audio = torch.cat([items[i][0]["audio"].to(torch.float32) for i in idxs])
+        visual = torch.cat([items[i][0]["visual"].to(fdt) for i in idxs])
+        audio = torch.cat([items[i][0]["audio"].to(fdt) for i in idxs])
         scores = torch.cat([items[i][1].reshape(-1) for i in idxs])
         if pin:
             visual, audio, scores = visual.pin_memory(), audio.pin_memory(), scores.pin_memory()

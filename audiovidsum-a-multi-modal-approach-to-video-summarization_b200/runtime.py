@@ -134,6 +134,7 @@ class NativeModel:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.dims = (visual_dim, audio_dim, hidden_dim, num_heads)
         self._handle = C.c_void_p()
+        self._feat_f16 = False
         w, keep = self._weights_struct(state_dict)
         # avs_model_create packs on its own stream; the parameters were last written on torch's current stream
         torch.cuda.current_stream(self.device).synchronize()
@@ -194,6 +195,18 @@ class NativeModel:
         except Exception:
             pass
 
+    def _features(self, visual: torch.Tensor, audio: torch.Tensor):
+        """Feature buffers as the library will read them: both tensors float16 -> the opt-in 16-bit feature format
+        (avs_model_set_feature_format, half the bytes per frame); anything else -> float32, as in the reference."""
+        f16 = visual.dtype == torch.float16 and audio.dtype == torch.float16
+        if f16 != self._feat_f16:
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.avs_model_set_feature_format(
+                    self._handle, _cabi.AVS_FEAT_F16 if f16 else _cabi.AVS_FEAT_F32))
+            self._feat_f16 = f16
+        dt = torch.float16 if f16 else torch.float32
+        return visual.to(dt).contiguous(), audio.to(dt).contiguous()
+
     # -- forward ----------------------------------------------------------------
     def forward_rows(self, visual: torch.Tensor, audio: torch.Tensor, row_start, lengths, attn_axis: str = "literal",
                      precision: str = "tf32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -206,8 +219,7 @@ class NativeModel:
         if visual.device != audio.device:
             raise ValueError("visual and audio must live on the same device")
         R = int(visual.shape[0])
-        visual = visual.to(torch.float32).contiguous()
-        audio = audio.to(torch.float32).contiguous()
+        visual, audio = self._features(visual, audio)
         rs, ln = _i32(row_start), _i32(lengths)
         if rs.shape != ln.shape or rs.ndim != 1:
             raise ValueError("row_start and lengths must be 1-D arrays of equal size")
@@ -277,8 +289,7 @@ class NativeModel:
         if not (visual.device == audio.device == positions.device):
             raise ValueError("visual, audio and positions must live on the same device")
         R = int(visual.shape[0])
-        visual = visual.to(torch.float32).contiguous()
-        audio = audio.to(torch.float32).contiguous()
+        visual, audio = self._features(visual, audio)
         positions = positions.to(torch.int32).contiguous()
         frac = _fraction(proportion)
         rs, ln = _i32(row_start), _i32(lengths)

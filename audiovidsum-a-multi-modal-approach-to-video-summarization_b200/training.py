@@ -262,6 +262,7 @@ class TrainStep:
                                f"(overlaps the backward)" if ddp else "none (1 GPU)")
         self.graphed = False
         self.graph = None
+        self.launches_per_replay = 0
         dev = visual.device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -276,8 +277,10 @@ class TrainStep:
             self.graph = torch.cuda.CUDAGraph()
             if hasattr(model, "_native_lstm_key"):
                 model._native_lstm_key = None      # the captured forward must contain the recurrences' weight re-pack
+            n0 = _cabi.launch_count()
             with torch.cuda.graph(self.graph):
                 self.loss = self._body()
+            self.launches_per_replay = _cabi.launch_count() - n0   # native kernels inside one replay
             self.graphed = True
 
     def _body(self):

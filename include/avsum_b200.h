@@ -60,6 +60,13 @@ enum { AVS_ATTN_LITERAL = 0, AVS_ATTN_TEMPORAL = 1, AVS_ATTN_LITERAL_B1 = 2 };
  * AVS_PREC_FP32_SIMT : CUDA-core fp32 contractions (slow; exact-order debugging aid). */
 enum { AVS_PREC_TF32 = 0, AVS_PREC_BF16 = 1, AVS_PREC_FP32_SIMT = 2 };
 
+/* Element type of the caller's visual / audio feature buffers (avs_model_set_feature_format).
+ * AVS_FEAT_F32 (default): float32, what the reference's data/dataset.py:19-32 loads.
+ * AVS_FEAT_F16: IEEE half -- an opt-in 16-bit feature cache (half the PCIe / HBM bytes per frame).  The fc layers
+ *   then run kind::f16 on the stored values against fp16 weights (11-bit significands on both sides, exactly what
+ *   the default mode's tf32 operands carry); needs AVS_PREC_TF32 and feature dims that are multiples of 8. */
+enum { AVS_FEAT_F32 = 0, AVS_FEAT_F16 = 1 };
+
 /* fp32 parameters in the reference's state_dict layout (av_model.py:10-31).
  * lstm_*[i]: i = 0 visual fwd, 1 visual reverse, 2 audio fwd, 3 audio reverse.
  * Pointers may be host or device memory (copied with cudaMemcpyDefault). */
@@ -98,6 +105,12 @@ avs_status avs_model_update(avs_model* m, const avs_weights* w);
  * training loop of scripts/train_av_model.py:94-96).  lstm_only != 0 re-packs only the four recurrences' tensors,
  * the only ones a training step reads through the handle (avs_bilstm_pair_train / _bwd). */
 avs_status avs_model_update_async(avs_model* m, const avs_weights* w, int lstm_only, void* cuda_stream);
+/* How the `visual` / `audio` arguments of avs_forward, avs_forward_summarize and avs_forward_summarize_async are
+ * read from now on: AVS_FEAT_F32 (the declared `const float*`) or AVS_FEAT_F16 (the same pointers address IEEE half
+ * values, row pitch visual_dim / audio_dim halves).  The reference has no such switch (its features are float32
+ * .npy files, data/dataset.py:25-28); this is the 16-bit host feature cache of data.dataset.packed_batches.
+ * No asynchronous step may be in flight. */
+avs_status avs_model_set_feature_format(avs_model* m, int format);
 void avs_model_destroy(avs_model* m);
 
 /* Replaces AVBiLSTMModel.forward (av_model.py:33-46) for a batch of n_videos videos.

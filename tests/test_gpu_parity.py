@@ -177,6 +177,76 @@ def test_forward_with_fp16_exact_features(cuda_ready):
             assert rel(got, want) < 1e-3, (peaked, axis, rel(got, want))
 
 
+def test_fp16_feature_format_matches_reference(cuda_ready):
+    """Opt-in 16-bit host feature cache (avs_model_set_feature_format / packed_batches(feature_dtype="fp16")): the
+    features travel and are read as IEEE half; scores vs the CPU port ON THE ORIGINAL fp32 FEATURES within 1e-3
+    (config 2, first 12 videos, both attention axes), through host (pinned) and device buffers, streamed and not;
+    switching back to fp32 buffers restores the default path bit for bit."""
+    from avsum_b200.evaluation.summary import summarize_videos
+    vids = sorted(synth.config2()[:12], key=lambda v: -v.T)
+    port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
+    port.load_state_dict(synth.seeded_state_dict(spread=True))
+    for axis, cpu_axis in (("literal_b1", "literal"), ("temporal", "temporal")):
+        want = av_oracle_torch.run_videos(port, [(v.visual, v.audio) for v in vids], cpu_axis)
+        m = make_model(spread=True, attn_axis=axis)
+        base = m.score_videos([(v.visual.cuda(), v.audio.cuda()) for v in vids])
+        for space in ("cuda", "cpu"):
+            got = m.score_videos([(v.visual.half().to(space), v.audio.half().to(space)) for v in vids])
+            worst = max(rel(a.cpu().numpy(), b.numpy()) for a, b in zip(got, want))
+            assert worst < 1e-3, (axis, space, worst)
+        half_vids = [synth.Video(v.visual.half().pin_memory(), v.audio.half().pin_memory(), v.n_frames, v.positions, v.cps)
+                     for v in vids]
+        res = summarize_videos(m, half_vids)
+        for v, r, w in zip(vids, res, want):
+            assert rel(r.scores.numpy(), w.numpy()) < 1e-3
+            wp, ws, _ = av_oracle.generate_summary(r.scores.numpy(), v.cps, v.n_frames, v.positions)
+            assert np.array_equal(wp, r.picks) and np.array_equal(ws, r.summary)
+        again = m.score_videos([(v.visual.cuda(), v.audio.cuda()) for v in vids])
+        assert all(torch.equal(a, b) for a, b in zip(again, base))
+    with pytest.raises(_cabi.AvsUnsupported):      # bf16 operand mode reads bf16 copies of fp32 features only
+        mb = make_model(precision="bf16")
+        mb(vids[0].visual.half()[None].cuda(), vids[0].audio.half()[None].cuda())
+
+
+def test_padded_batch_rows_are_packed_before_the_gemms(cuda_ready):
+    """BASELINE configs[2] layout ([B, Tmax] + lengths): the library packs the valid rows densely before the GEMMs
+    (csrc/api.cu forward_entry); the result must equal the unpacked path (AVS_NO_ROW_PACKING) bit for bit, in device
+    and host space, and padding (NaN) must never reach a valid frame."""
+    lens = [300, 12, 700, 129, 0, 64]
+    T = max(lens)
+    g = torch.Generator().manual_seed(21)
+    visual, audio = torch.randn(len(lens), T, 1024, generator=g), torch.randn(len(lens), T, 128, generator=g)
+    for b, n in enumerate(lens):
+        visual[b, n:] = float("nan")
+    m = make_model(spread=True, attn_axis="temporal")
+    nat = m.native()
+    starts = [b * T for b in range(len(lens))]
+    v2, a2 = visual.reshape(-1, 1024), audio.reshape(-1, 128)
+    outs = {}
+    for space in ("cuda", "cpu"):
+        for packing in (True, False):
+            if packing:
+                os.environ.pop("AVS_NO_ROW_PACKING", None)
+            else:
+                os.environ["AVS_NO_ROW_PACKING"] = "1"
+            try:
+                out = nat.forward_rows(v2.to(space), a2.to(space), starts, lens, "temporal", "tf32",
+                                       out=torch.zeros(len(lens) * T, device=space))
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("AVS_NO_ROW_PACKING", None)
+            outs[(space, packing)] = out.cpu().reshape(len(lens), T)
+    ref = outs[("cuda", False)]
+    for key, out in outs.items():
+        for b, n in enumerate(lens):
+            assert torch.equal(out[b, :n], ref[b, :n]), (key, b)
+            assert bool(torch.isfinite(out[b, :n]).all())
+    for b, n in enumerate(lens):       # and each video equals its own B = 1 run
+        if n:
+            alone = nat.forward_rows(visual[b, :n].cuda(), audio[b, :n].cuda(), [0], [n], "temporal", "tf32")
+            assert torch.equal(alone.cpu(), ref[b, :n])
+
+
 def test_training_forward_equals_eval_forward(cuda_ready):
     """One operand policy on both paths: the autograd forward (avs_linear per layer) and the inference forward
     (avs_forward) of the same weights agree to the tolerance of their operand formats (fp32 vs fp16 activations
