@@ -191,6 +191,23 @@ __global__ void upload_kernel(UploadPayload p, uint32_t* __restrict__ dst, int n
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = p.w[i];
 }
 
+// Row packing of padded / sparse batches: rows [src_start[v], + len[v]) of src -> rows [dst_start[v], + len[v]) of dst
+// for every video v (blockIdx.y), ROWS rows per block, 16-byte (features) or 4-byte (scores) elements.
+// desc = src_start[n] | dst_start[n] | len[n].
+template <typename T>
+__global__ void copy_video_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, const int32_t* __restrict__ desc,
+                                       int n, int row_elems, int rows_per_block) {
+    const int v = blockIdx.y;
+    const int len = desc[2 * n + v];
+    const int r0 = blockIdx.x * rows_per_block;
+    if (r0 >= len) return;
+    const int rows = min(rows_per_block, len - r0);
+    const T* s = src + (static_cast<size_t>(desc[v]) + r0) * row_elems;
+    T* d = dst + (static_cast<size_t>(desc[n + v]) + r0) * row_elems;
+    const size_t total = static_cast<size_t>(rows) * row_elems;
+    for (size_t i = threadIdx.x; i < total; i += blockDim.x) d[i] = s[i];
+}
+
 __global__ void permute_gate_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                          float* __restrict__ dst) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -762,34 +779,71 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
             ok = lengths[b] >= 0 && row_start[b] >= 0 && static_cast<int64_t>(row_start[b]) + lengths[b] <= total_rows;
             covered += ok ? lengths[b] : 0;
         }
-        if (ok && covered > 0 && covered * 10 < total_rows * 9) {
+        // device space gathers with 16-byte vectors: unaligned caller buffers (a raw C-ABI caller) take the unpacked path
+        const size_t fsz0 = m->feat_f16 ? 2 : 4;
+        const bool vec_ok = host || ((reinterpret_cast<uintptr_t>(visual) & 15) == 0 && (reinterpret_cast<uintptr_t>(audio) & 15) == 0 &&
+                                     (m->Dv * fsz0) % 16 == 0 && (m->Da * fsz0) % 16 == 0);
+        if (ok && vec_ok && covered > 0 && covered * 10 < total_rows * 9) {
             AVS_CHECK(precision_ok(precision), AVS_ERR_INVALID, "bad precision %d", precision);
             Guard gp(m->device);
             cudaStream_t sp = static_cast<cudaStream_t>(cuda_stream);
             const size_t C_ = static_cast<size_t>(covered), Dv_ = m->Dv, Da_ = m->Da, fsz = m->feat_f16 ? 2 : 4;
-            AVS_TRY(m->pack_ws.reserve(C_ * (Dv_ + Da_) * fsz + C_ * 4 + 4 * 256));
+            AVS_TRY(m->pack_ws.reserve(C_ * (Dv_ + Da_) * fsz + C_ * 4 + 6 * static_cast<size_t>(n_videos) * 4 + 8 * 256));
             m->pack_ws.reset();
             float* pv = reinterpret_cast<float*>(m->pack_ws.take<char>(C_ * Dv_ * fsz));
             float* pa = reinterpret_cast<float*>(m->pack_ws.take<char>(C_ * Da_ * fsz));
             float* ps = m->pack_ws.take<float>(C_);
-            std::vector<int32_t> prs(n_videos);
+            int32_t* desc_dev = m->pack_ws.take<int32_t>(3 * static_cast<size_t>(n_videos));
+            std::vector<int32_t> prs(n_videos), desc(3 * static_cast<size_t>(n_videos));
             int64_t at = 0;
-            const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            int max_len = 0;
             for (int b = 0; b < n_videos; ++b) {
                 prs[b] = static_cast<int32_t>(at);
-                const size_t n = static_cast<size_t>(lengths[b]);
-                if (n) {
-                    AVS_CUDA(cudaMemcpyAsync(feat_at(pv, at, m->Dv, fsz), feat_at(visual, row_start[b], m->Dv, fsz), n * Dv_ * fsz, kin, sp));
-                    AVS_CUDA(cudaMemcpyAsync(feat_at(pa, at, m->Da, fsz), feat_at(audio, row_start[b], m->Da, fsz), n * Da_ * fsz, kin, sp));
-                }
+                desc[b] = row_start[b];
+                desc[n_videos + b] = prs[b];
+                desc[2 * n_videos + b] = lengths[b];
+                max_len = std::max(max_len, lengths[b]);
                 at += lengths[b];
+            }
+            if (host) {   // straight from the caller's (pinned) buffer: one DMA copy per video, padding never crosses PCIe
+                for (int b = 0; b < n_videos; ++b) {
+                    const size_t n = static_cast<size_t>(lengths[b]);
+                    if (!n) continue;
+                    AVS_CUDA(cudaMemcpyAsync(feat_at(pv, prs[b], m->Dv, fsz), feat_at(visual, row_start[b], m->Dv, fsz),
+                                             n * Dv_ * fsz, cudaMemcpyHostToDevice, sp));
+                    AVS_CUDA(cudaMemcpyAsync(feat_at(pa, prs[b], m->Da, fsz), feat_at(audio, row_start[b], m->Da, fsz),
+                                             n * Da_ * fsz, cudaMemcpyHostToDevice, sp));
+                }
+            } else {      // device space: ONE gather kernel per tensor (per-video copies cost more than the padding)
+                AVS_TRY(upload_small(desc_dev, desc.data(), desc.size() * 4, sp));
+                constexpr int ROWS = 8;
+                const dim3 grid((max_len + ROWS - 1) / ROWS, n_videos);
+                copy_video_rows_kernel<uint4><<<grid, 256, 0, sp>>>(reinterpret_cast<const uint4*>(visual),
+                                                                    reinterpret_cast<uint4*>(pv), desc_dev, n_videos,
+                                                                    static_cast<int>(Dv_ * fsz / 16), ROWS);
+                AVS_LAUNCH_CHECK();
+                copy_video_rows_kernel<uint4><<<grid, 256, 0, sp>>>(reinterpret_cast<const uint4*>(audio),
+                                                                    reinterpret_cast<uint4*>(pa), desc_dev, n_videos,
+                                                                    static_cast<int>(Da_ * fsz / 16), ROWS);
+                AVS_LAUNCH_CHECK();
             }
             AVS_TRY(forward_entry(m, pv, pa, covered, n_videos, prs.data(), lengths, attn_axis, precision, ps, AVS_DEVICE,
                                   cuda_stream, nullptr, nullptr, nullptr));
-            const cudaMemcpyKind kout = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-            for (int b = 0; b < n_videos; ++b)
-                if (lengths[b])
-                    AVS_CUDA(cudaMemcpyAsync(scores + row_start[b], ps + prs[b], static_cast<size_t>(lengths[b]) * 4, kout, sp));
+            if (host) {
+                for (int b = 0; b < n_videos; ++b)
+                    if (lengths[b])
+                        AVS_CUDA(cudaMemcpyAsync(scores + row_start[b], ps + prs[b], static_cast<size_t>(lengths[b]) * 4,
+                                                 cudaMemcpyDeviceToHost, sp));
+            } else {
+                // scatter: packed scores -> each video's rows (descriptor roles swapped: src = packed, dst = caller's)
+                std::vector<int32_t> back(desc);
+                for (int b = 0; b < n_videos; ++b) std::swap(back[b], back[n_videos + b]);
+                int32_t* back_dev = m->pack_ws.take<int32_t>(back.size());
+                AVS_TRY(upload_small(back_dev, back.data(), back.size() * 4, sp));
+                const dim3 grid((max_len + 255) / 256, n_videos);
+                copy_video_rows_kernel<float><<<grid, 256, 0, sp>>>(ps, scores, back_dev, n_videos, 1, 256);
+                AVS_LAUNCH_CHECK();
+            }
             if (host) AVS_CUDA(cudaStreamSynchronize(sp));
             return AVS_OK;
         }
@@ -1299,7 +1353,7 @@ static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, co
         AVS_CHECK(cap < (1ll << 30), AVS_ERR_UNSUPPORTED, "video %d: capacity too large", v);
         max_cap = std::max(max_cap, static_cast<int>(cap));
         const int S = cps_start[v + 1] - cps_start[v];
-        off[v + 1] = off[v] + static_cast<int64_t>(S) * ((cap + 32) >> 5);
+        off[v + 1] = off[v] + static_cast<int64_t>(S) * knapsack_keep_words(cap);
         off[n + 1 + v + 1] = off[n + 1 + v] + 2 * (cap + 1);
         if (want_summary) AVS_CHECK(summary_start[v + 1] - summary_start[v] >= n_frames[v], AVS_ERR_INVALID,
                                     "summary_start leaves fewer than n_frames bytes for video %d", v);

@@ -180,6 +180,7 @@ avs_status shot_pool(const float* scores, const int32_t* positions, const Summar
 // scores / positions non-null (and knapsack_can_fuse_pool(b)): the kernel pools the frame scores itself (fused K7)
 // and seg_sum is not read.
 bool knapsack_can_fuse_pool(const SummaryBatch& b);
+int64_t knapsack_keep_words(long long cap);   // keep-bit words per item the workspace must hold for this capacity
 avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_sum, long long* seg_mean,
                            uint8_t* picks, uint8_t* summary, uint32_t* keep_bits, long long* dp_ws,
                            cudaStream_t stream, const float* scores = nullptr, const int32_t* positions = nullptr);

@@ -250,8 +250,12 @@ __global__ void __launch_bounds__(NT) knapsack_fast_kernel(SummaryBatch b, const
     V* buf_b = BIG ? buf_a : buf_a + rows_cap + (rows_cap & 1);          // [rows_cap]  (kept 8-byte aligned)
     int* item_beg = reinterpret_cast<int*>(buf_b + rows_cap + (rows_cap & 1));   // [items_cap] first frame of the shot
     int* item_len = item_beg + items_cap;                                // [items_cap] frames; negated once not picked
-    uint32_t* keep = BIG ? keep_bits + b.keep_start[v]                   // [S][words]: global workspace (BIG) ...
-                         : reinterpret_cast<uint32_t*>(item_len + items_cap);   // ... or shared memory
+    uint32_t* keep = BIG ? keep_bits + b.keep_start[v]                   // [S][kwords]: global workspace (BIG) ...
+                         : reinterpret_cast<uint32_t*>(item_len + items_cap);   // ... or shared memory [S][words]
+    // BIG: every thread owns cpt_pad cells (a multiple of 4); row buffer and keep rows are padded accordingly, so the
+    // item loop needs no per-cell bounds checks (cells beyond the capacity hold values nobody reads)
+    const int cpt_pad = BIG ? (((cap + NT) / NT + 3) & ~3) : CPT;
+    const int kwords = BIG ? cpt_pad * (NT / 32) : words;
 
     for (int s = tid; s < S; s += NT) {
         const int2 seg = cps[s];
@@ -296,34 +300,94 @@ __global__ void __launch_bounds__(NT) knapsack_fast_kernel(SummaryBatch b, const
     for (int c = 0; c < CPT; ++c) {
         mine[c] = 0;
         const int w = tid + c * NT;
-        if (w <= cap) buf_a[w] = 0;
+        if (BIG ? (c < cpt_pad) : (w <= cap)) buf_a[w] = 0;
     }
     __syncthreads();
-    for (int s = 0; s < S; ++s) {
+    if constexpr (BIG) {
+        // ---- long videos: branch-free cells.  Per cell: clamp the source index, one 64-bit shared load, add, 64-bit
+        // compare, two selects, a ballot and (lane 0) one keep word -- ~13 instructions; the first version, with bounds
+        // checks and divergent branches per cell, executed 43 and was instruction bound (ncu: 1,566 warp
+        // instructions per item and warp).
+        uint32_t* keep_w = keep + (tid >> 5);          // this warp's word of cell block c is keep_w[c * (NT / 32)]
+        const bool lane0 = (tid & 31) == 0;
+        for (int s = 0; s < S; ++s) {
+            const int wt = item_len[s];
+            const V val = static_cast<V>(item_val[s]);
+            uint32_t* krow = keep_w + static_cast<size_t>(s) * kwords;
+            const int base = tid - wt;
+            const bool bump = wt == 0 && val > 0;      // defensive: validated shots have wt >= 1
+#pragma unroll
+            for (int c0 = 0; c0 < CPT; c0 += 4) {
+                if (c0 < cpt_pad) {   // uniform
+                    V prev[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) prev[k] = buf_a[max(base + (c0 + k) * NT, 0)];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = c0 + k;
+                        const V cand = (bump ? mine[c] : prev[k]) + val;
+                        const bool better = bump || (wt > 0 && base + c * NT >= 0 && cand > mine[c]);
+                        mine[c] = better ? cand : mine[c];
+                        const uint32_t bits = __ballot_sync(0xffffffffu, better);
+                        if (lane0) krow[c * (NT / 32)] = bits;
+                    }
+                }
+            }
+            __syncthreads();   // everybody has read row s - 1
+#pragma unroll
+            for (int c0 = 0; c0 < CPT; c0 += 4) {
+                if (c0 < cpt_pad) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) buf_a[tid + (c0 + k) * NT] = mine[c0 + k];
+                }
+            }
+            __syncthreads();   // row s published
+        }
+    }
+    for (int s = 0; s < (BIG ? 0 : S); ++s) {
         const int wt = item_len[s];
         const V val = static_cast<V>(item_val[s]);
         const V* rd = (BIG || !(s & 1)) ? buf_a : buf_b;
         V* wr = (BIG || (s & 1)) ? buf_a : buf_b;
+        // cells in batches of KB: first all shared-memory loads of a batch (independent, unconditional: the address
+        // is clamped and the value discarded when the shot does not fit), then the compares / ballots -- with one
+        // branch per cell in front of its load the 36 cells of a long video were 36 serialised load latencies
+        constexpr int KB = CPT < 8 ? CPT : 8;
+        static_assert(CPT % KB == 0, "cells per thread must be a multiple of the batch");
+        const bool shift = wt > 0;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const int w = tid + c * NT;
-            if (c * NT <= cap) {   // warp-uniform
-                bool better = false;
-                if (w <= cap) {
-                    const V old = mine[c];
-                    V cand = old;
-                    if (wt > 0 && w >= wt) {
-                        cand = rd[w - wt] + val;
-                        better = cand > old;
-                    } else if (wt == 0 && val > 0) {
-                        cand = old + val;
-                        better = true;
-                    }
-                    mine[c] = better ? cand : old;
-                    if (!BIG) wr[w] = mine[c];
+        for (int c0 = 0; c0 < CPT; c0 += KB) {
+            if (c0 * NT <= cap) {   // warp-uniform
+                V prev[KB];
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    const int w = tid + (c0 + k) * NT;
+                    const int src = w - wt;
+                    prev[k] = rd[(shift && src >= 0 && w <= cap) ? src : 0];
                 }
-                const uint32_t bits = __ballot_sync(0xffffffffu, better);
-                if ((tid & 31) == 0 && (w >> 5) < words) keep[static_cast<size_t>(s) * words + (w >> 5)] = bits;
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    const int c = c0 + k;
+                    const int w = tid + c * NT;
+                    if (c * NT <= cap) {   // warp-uniform
+                        bool better = false;
+                        if (w <= cap) {
+                            const V old = mine[c];
+                            V cand = old;
+                            if (shift && w >= wt) {
+                                cand = prev[k] + val;
+                                better = cand > old;
+                            } else if (wt == 0 && val > 0) {
+                                cand = old + val;
+                                better = true;
+                            }
+                            mine[c] = better ? cand : old;
+                            if (!BIG) wr[w] = mine[c];
+                        }
+                        const uint32_t bits = __ballot_sync(0xffffffffu, better);
+                        if ((tid & 31) == 0 && (w >> 5) < words) keep[static_cast<size_t>(s) * words + (w >> 5)] = bits;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -350,20 +414,21 @@ __global__ void __launch_bounds__(NT) knapsack_fast_kernel(SummaryBatch b, const
         // back-trace in chunks of items whose keep rows fit in the row buffer (the DP values are no longer needed)
         __threadfence_block();
         uint32_t* stage = reinterpret_cast<uint32_t*>(buf_a);
-        const int chunk = max(1, static_cast<int>((static_cast<size_t>(rows_cap) * sizeof(V)) / (static_cast<size_t>(words) * 4)));
+        const int chunk = max(1, static_cast<int>((static_cast<size_t>(rows_cap) * sizeof(V)) / (static_cast<size_t>(kwords) * 4)));
         __shared__ int w_cursor;
         if (tid == 0) w_cursor = cap;
         for (int hi = S; hi > 0; hi -= chunk) {
             const int lo = max(0, hi - chunk);
             __syncthreads();   // stage free (and, first time, every keep word written)
-            const size_t n_words = static_cast<size_t>(hi - lo) * words;
-            const uint32_t* src = keep + static_cast<size_t>(lo) * words;
+            const size_t n_words = static_cast<size_t>(hi - lo) * kwords;
+            const uint32_t* src = keep + static_cast<size_t>(lo) * kwords;
+#pragma unroll 8
             for (size_t i = tid; i < n_words; i += NT) stage[i] = src[i];
             __syncthreads();
             if (tid == 0) {
                 int w = w_cursor;
                 for (int s = hi - 1; s >= lo; --s) {
-                    const int take = (stage[static_cast<size_t>(s - lo) * words + (w >> 5)] >> (w & 31)) & 1;
+                    const int take = (stage[static_cast<size_t>(s - lo) * kwords + (w >> 5)] >> (w & 31)) & 1;
                     picks[s0 + s] = static_cast<uint8_t>(take);
                     if (take) w -= item_len[s];
                     else item_len[s] = -item_len[s];
@@ -462,6 +527,14 @@ avs_status shot_pool(const float* scores, const int32_t* positions, const Summar
     return AVS_OK;
 }
 
+// keep-bit words per item that the planner must reserve for a video of this capacity: the long-video kernel pads
+// its keep rows to whole groups of 4 cells per thread
+int64_t knapsack_keep_words(long long cap) {
+    const long long plain = (cap + 32) >> 5;
+    const long long padded = (cap + 4 * KNAP_BIG_THREADS) / (4 * KNAP_BIG_THREADS) * (4 * KNAP_BIG_THREADS) / 32;
+    return std::max(plain, padded);
+}
+
 bool knapsack_can_fuse_pool(const SummaryBatch& b) {
     // the fused pooling needs every video's items in shared memory (see the budget below)
     const size_t limit = 200 * 1024;
@@ -509,7 +582,10 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
     }
     // ---- long videos: register-resident DP cells, ONE row buffer in shared memory, keep bits in the workspace
     if (scores != nullptr && b.max_cap + 1 <= KNAP_BIG_CPT * KNAP_BIG_THREADS && keep_bits != nullptr) {
-        const int rows = b.max_cap + 1, items = std::max(b.max_S, 1);
+        // row buffer padded to whole groups of 4 cells per thread (see the kernel); the keep rows in the workspace
+        // are padded the same way by the host planner (knapsack_keep_words)
+        const int rows = (b.max_cap + 4 * KNAP_BIG_THREADS) / (4 * KNAP_BIG_THREADS) * (4 * KNAP_BIG_THREADS);
+        const int items = std::max(b.max_S, 1);
         const size_t need = static_cast<size_t>(items) * 8 + (static_cast<size_t>(rows) + 1) * 8 +
                             static_cast<size_t>(items) * 8 + 64;
         if (need <= limit) {

@@ -101,10 +101,22 @@ def check(got: torch.Tensor, want: np.ndarray, prec: str, what):
     return worst
 
 
+@pytest.fixture(params=["auto", "tmem", "smem"])
+def q_mode(request):
+    """The kernel has two variants -- Q in tensor memory (TS product, chosen for max length >= 1024) and Q in shared
+    memory (SS product, short sequences); AVS_ATTN_Q forces one, so every case below runs through both."""
+    if request.param == "auto":
+        os.environ.pop("AVS_ATTN_Q", None)
+    else:
+        os.environ["AVS_ATTN_Q"] = request.param
+    yield request.param
+    os.environ.pop("AVS_ATTN_Q", None)
+
+
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 @pytest.mark.parametrize("kind", ["random", "staircase", "mid_peak"])
 @pytest.mark.parametrize("T", [65, 200, 700, 1000])
-def test_attention_core_matches_oracle_all_heads(cuda_ready, T, kind, prec):
+def test_attention_core_matches_oracle_all_heads(cuda_ready, q_mode, T, kind, prec):
     qkv = make_qkv(T, kind, prec, seed=T * 3 + len(kind))
     want = oracle_ctx(qkv, [T], [0])
     if kind == "staircase":   # the construction really forces what it claims: late maxima, wide spans
@@ -118,7 +130,7 @@ def test_attention_core_matches_oracle_all_heads(cuda_ready, T, kind, prec):
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
-def test_attention_core_long_sequence_T8192(cuda_ready, prec):
+def test_attention_core_long_sequence_T8192(cuda_ready, q_mode, prec):
     """BASELINE configs[3]: 128 key blocks, 64 query tiles per head; rescaling rows at blocks 1, 64, 126 and 127."""
     T = 8192
     qkv = make_qkv(T, "staircase", prec, seed=8192)
@@ -128,7 +140,7 @@ def test_attention_core_long_sequence_T8192(cuda_ready, prec):
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
-def test_attention_core_packed_varlen_batch(cuda_ready, prec):
+def test_attention_core_packed_varlen_batch(cuda_ready, q_mode, prec):
     """Packed rows, ragged lengths: the 64-key K / V tiles of a video's last block cover rows of the NEXT video
     (masked), the 128-query Q tile of its last block too (not stored); a zero-length video; lengths of 1, 64, 65."""
     lens = [130, 65, 700, 1, 0, 64, 257, 1000, 63]
@@ -151,13 +163,22 @@ def test_attention_core_packed_varlen_batch(cuda_ready, prec):
         assert torch.equal(got2[s2:s2 + lens[i]], got[starts[i]:starts[i] + lens[i]]), i
 
 
-def test_attention_rescale_branch_is_repeatable_under_concurrent_load(cuda_ready):
+@pytest.mark.parametrize("q_force", ["tmem", "smem"])
+def test_attention_rescale_branch_is_repeatable_under_concurrent_load(cuda_ready, q_force):
     """The O-rescale branch waits for "P_{j-1} V_{j-1} has landed" on a per-key-block barrier by phase parity
     (attention_tc.cu, softmax warps, j > 0).  A parity wait only separates adjacent phases; the argument why it is
     safe there (S_j can only be ready after P_{j-2} V_{j-2} was committed, so the barrier is at most one phase behind)
     is checked here the way the bar_done bug of round 1 was found: another kernel shares the SMs, the staircase input
     makes every fourth row rescale at four late blocks, and every launch must reproduce the oracle-checked first one
     bit for bit."""
+    os.environ["AVS_ATTN_Q"] = q_force
+    try:
+        _rescale_repeatability()
+    finally:
+        os.environ.pop("AVS_ATTN_Q", None)
+
+
+def _rescale_repeatability():
     lens = [700, 650, 1000, 333, 512, 200]
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
     qkv = torch.cat([make_qkv(n, "staircase", "tf32", seed=500 + i) for i, n in enumerate(lens)], dim=0)
