@@ -124,14 +124,53 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_global_batch(n_gpus: int, config: str = "infer"):
-    vids = []
+def global_batch_spec(n_gpus: int, config: str = "infer"):
+    """(T, seed) of every video of the global batch: 50 TVSum-length videos (config 2) or 8 x T=8192 (config 4) per
+    GPU.  Cheap -- every rank needs all lengths / shot counts for the sharding, but features only for its shard."""
+    spec = []
     for c in range(n_gpus):
         if config == "long":
-            vids += [synth.make_video(8192, 1024, 128, 9000 + 100 * c + i) for i in range(8)]
+            spec += [(8192, 9000 + 100 * c + i) for i in range(8)]
         else:
-            vids += synth.video_batch(50, 200, 700, length_seed=c, seed0=1234 + 1000 * c)
-    return vids
+            lengths = np.random.default_rng(c).integers(200, 701, 50)
+            spec += [(int(t), 1234 + 1000 * c + i) for i, t in enumerate(lengths)]
+    return spec
+
+
+def n_shots(T: int, seed: int) -> int:
+    return int(synth.make_change_points(synth.SAMPLE_STRIDE * T, seed=100000 + seed).shape[0])
+
+
+def build_global_batch(n_gpus: int, config: str = "infer"):
+    return [synth.make_video(T, 1024, 128, seed) for T, seed in global_batch_spec(n_gpus, config)]
+
+
+class _StdoutToStderr:
+    """NCCL prints its version banner with a bare printf to stdout when a communicator is created (NCCL_DEBUG=VERSION
+    or INFO); stdout must hold only the JSON line, so file descriptor 1 points at stderr while the process group is
+    set up -- the banner and every NCCL_DEBUG line stay visible to whoever reads stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def finish(world, dist):
+    """Leave without tearing NCCL down: destroy_process_group() after a CUDA graph with captured collectives was
+    observed to hang (2 x B200, r02e); every rank has synchronised and rank 0 has printed, so exit directly."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------ reference arm
@@ -223,7 +262,11 @@ def setup_dist(world, dev):
         # log to stdout by default, which must hold only the JSON line -> send it to stderr unless told otherwise
         if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
             os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)            # the communicator (and NCCL's banner) exist before anything is printed
+            torch.cuda.synchronize()
     return dist
 
 
@@ -363,16 +406,17 @@ def run_infer(args, rank, world, local_rank):
     axis = "temporal" if cfg == "long" else args.axis
 
     # ---- workload: global batch sharded by video
-    vids_all = build_global_batch(max(world, 1), cfg)
-    shards = sharding.shard_videos([v.T for v in vids_all], world)
+    spec = global_batch_spec(max(world, 1), cfg)
+    shards = sharding.shard_videos([t for t, _ in spec], world)
     # batch composition as data/dataset.py packed_batches builds it: longest video first (the host-space call
     # pipelines the batch by video group, and a group's recurrence lasts as long as its longest video)
-    mine = sorted(shards[rank], key=lambda i: -vids_all[i].T)
-    vids = [vids_all[i] for i in mine]
+    mine = sorted(shards[rank], key=lambda i: -spec[i][0])
+    vids = [synth.make_video(spec[i][0], 1024, 128, spec[i][1]) for i in mine]
     lens = [v.T for v in vids]
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
     R = int(sum(lens))
-    frames_global = sum(v.T for v in vids_all)
+    frames_global = sum(t for t, _ in spec)
+    n_videos_global = len(spec)
 
     sd = synth.seeded_state_dict()
     model = AVBiLSTMModel(1024, 128, 512, attn_axis=axis).eval()
@@ -395,7 +439,7 @@ def run_infer(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     # result gather (the only collective of the inference path): every rank knows every shard's shot count
     # from the host-side change points, so one padded all_gather of the keyshot picks per step suffices
-    shots_per_rank = [sum(len(vids_all[i].cps) for i in sh) for sh in shards]
+    shots_per_rank = [sum(n_shots(*spec[i]) for i in sh) for sh in shards]
     pad = torch.zeros(max(shots_per_rank), dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * pad.numel(), dtype=torch.uint8, device=dev)
 
@@ -520,8 +564,7 @@ def run_infer(args, rank, world, local_rank):
         attention = attention_probe(sd, dev, peaks, world, dist)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world, dist)
         return
 
     # ---- roofline of the dominant kernel (CUDA events inside the library, same timed region)
@@ -535,9 +578,9 @@ def run_infer(args, rank, world, local_rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": WORKLOADS[cfg], "videos_per_gpu": len(vids), "frames_per_gpu": R,
-                   "global_videos": len(vids_all), "attn_axis": axis, "l2": "256 MiB flush between timed steps",
+                   "global_videos": n_videos_global, "attn_axis": axis, "l2": "256 MiB flush between timed steps",
                    "batch_order": "longest video first (packed_batches)", "parallelism": f"dp{world} by video"},
-        "videos_per_s": len(vids_all) / (ms_per_step * 1e-3),
+        "videos_per_s": n_videos_global / (ms_per_step * 1e-3),
         "e2e": {"value": frames_global / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "h2d_floor_ms": floor_ms,
@@ -574,7 +617,7 @@ def run_infer(args, rank, world, local_rank):
         torch.set_num_threads(cores)
         port = av_oracle_torch.RefPortModel(1024, 128, 512).eval()
         port.load_state_dict(sd)
-        base_vids = vids if cfg == "long" else build_global_batch(1, cfg)
+        base_vids = build_global_batch(1, cfg)
         cpu_axis = "temporal" if axis == "temporal" else "literal"
         cpu_out = {}
 
@@ -611,8 +654,7 @@ def run_infer(args, rank, world, local_rank):
             worst16 = max(worst16, float(np.max(np.abs(got_s.astype(np.float64) - cpu_out[i][0]) / np.abs(cpu_out[i][0]))))
         line["e2e_fp16_features"]["parity_max_rel_err"] = worst16
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world, dist)
 
 
 # ------------------------------------------------------------------------------------ our arm: training config
@@ -657,11 +699,11 @@ def run_train(args, rank, world, local_rank):
     ms = max_over_ranks([e0.elapsed_time(e1) / args.steps], dev, world, dist)[0]
     # end to end: the batch comes from pinned host memory every step, the loss goes back to the host
     for _ in range(2):
-        float(stepper(visual_h, audio_h, target_h))
+        float(stepper(visual_h, audio_h, target_h).detach())
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        last = float(stepper(visual_h, audio_h, target_h))
+        last = float(stepper(visual_h, audio_h, target_h).detach())
     barrier()
     e2e_ms = max_over_ranks([(time.perf_counter() - t0) / args.steps * 1e3], dev, world, dist)[0]
     clocks = sampler.stop() if sampler else None
@@ -687,8 +729,7 @@ def run_train(args, rank, world, local_rank):
                 "final_loss": float(loss), "last_e2e_loss": last,
                 "comm": {"backend": "nccl" if world > 1 else None, "nranks": world}}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world, dist)
 
 
 def main():
