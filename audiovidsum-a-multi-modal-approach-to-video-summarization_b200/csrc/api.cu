@@ -41,11 +41,11 @@ int device_sm_count() {
 // Enabled by avs_profile(1); events are resolved lazily in avs_profile_read so the hot path
 // never synchronises because of profiling.
 enum Stage : int { ST_CONVERT = 0, ST_FC, ST_IH_PROJ, ST_LSTM, ST_QKV_PROJ, ST_ATTENTION, ST_OUT_PROJ, ST_SCORER,
-                   ST_POOL, ST_KNAPSACK, ST_FRONT, ST_COUNT };
+                   ST_POOL, ST_KNAPSACK, ST_FRONT, ST_FRONT_LSTM, ST_COUNT };
 static const char* const kStageNames[ST_COUNT] = {"convert_tf32", "fc_gemm", "lstm_input_gemm", "lstm_recurrence",
                                                   "attn_in_proj_gemm", "attention_core", "attn_out_proj_gemm",
                                                   "score_head_gemm", "shot_pool", "knapsack_select",
-                                                  "frontend_gemms"};
+                                                  "frontend_gemms", "frontend_lstm_pipelined"};
 struct Profiler {
     bool enabled = false;
     std::vector<cudaEvent_t> pool;
@@ -270,6 +270,11 @@ struct avs_model {
     // the audio branch (audio_fc -> audio LSTM input projection) of group g runs beside the visual branch
     cudaStream_t branch_stream[MAX_CHUNKS] = {};
     cudaEvent_t ev_branch_in[MAX_CHUNKS] = {}, ev_branch_out[MAX_CHUNKS] = {};
+    // pipelined front: the recurrence of video group k starts (on its own high-priority stream) as soon as the input
+    // projections of its rows exist, while the GEMMs of the following groups still run
+    static constexpr int PIPE_SEGS = 5;
+    cudaStream_t pipe_stream[PIPE_SEGS] = {};
+    cudaEvent_t ev_pipe_front[PIPE_SEGS] = {}, ev_pipe_done[PIPE_SEGS] = {};
 };
 
 namespace {
@@ -659,6 +664,13 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_branch_in[i], cudaEventDisableTiming);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_branch_out[i], cudaEventDisableTiming);
         }
+        int prio_lo = 0, prio_hi = 0;
+        if (ce == cudaSuccess) ce = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        for (int i = 0; i < avs_model::PIPE_SEGS && ce == cudaSuccess; ++i) {
+            ce = cudaStreamCreateWithPriority(&m->pipe_stream[i], cudaStreamNonBlocking, prio_hi);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_pipe_front[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_pipe_done[i], cudaEventDisableTiming);
+        }
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&m->sum_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_sum_out, cudaEventDisableTiming);
         for (int i = 0; i < avs_model::SLOTS + 2 && ce == cudaSuccess; ++i)
@@ -729,6 +741,11 @@ void avs_model_destroy(avs_model* m) {
     }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->sum_stream) cudaStreamDestroy(m->sum_stream);
+    for (int i = 0; i < avs_model::PIPE_SEGS; ++i) {
+        if (m->pipe_stream[i]) cudaStreamDestroy(m->pipe_stream[i]);
+        if (m->ev_pipe_front[i]) cudaEventDestroy(m->ev_pipe_front[i]);
+        if (m->ev_pipe_done[i]) cudaEventDestroy(m->ev_pipe_done[i]);
+    }
     for (int i = 0; i < avs_model::MAX_CHUNKS; ++i) {
         if (m->branch_stream[i]) cudaStreamDestroy(m->branch_stream[i]);
         if (m->ev_branch_in[i]) cudaEventDestroy(m->ev_branch_in[i]);
@@ -1104,8 +1121,100 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     // -> K2a LSTM input projections for both directions (av_model.py:39-40).  In host space chunk c+1 is in
     // flight on the copy stream while chunk c is being computed.
     AVS_TRY(upload_small(plan_dev, plan.host.data(), plan.host.size() * 4, st));
-    const int n_chunks = (space == AVS_HOST && R >= 2048) ? avs_model::MAX_CHUNKS : 1;
-    const int64_t chunk_rows = ((R + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+    // ---- pipelined front (device-resident batches ordered longest video first, the order packed_batches produces):
+    // the recurrence is a chain of max(T) dependent steps that leaves most of every SM idle, and it cannot start before
+    // the input projections of its rows exist.  Instead of ALL front GEMMs followed by ALL recurrences, the rows are
+    // processed group by group (a group = the videos of one recurrence cluster): as soon as the GEMMs of group k are
+    // done its recurrence starts on its own high-priority stream, and the GEMMs of groups k+1.. run beside it on the
+    // SMs the running recurrences leave free (their persistent grids are sized for those).  The longest videos come
+    // first, so the critical chain starts after ~1/4 of the GEMM work instead of all of it.
+    // MEASURED (B200, config 2, profiles/r02f_pipeline_ab.log): front + recurrences 0.749 ms pipelined vs 0.174 + 0.481 =
+    // 0.655 ms one after the other -- the GEMMs lose the SMs the recurrence clusters hold (and wait for clusters to be
+    // placed), the second-longest group becomes the critical chain and starts later than it does today.  Same
+    // conclusion as round 1's video-group experiment: OFF by default, AVS_PIPELINE=1 turns it on.
+    bool pipelined = false;
+    if (!simt && space == AVS_DEVICE && arena == nullptr && lstm_excl == 0 && plan.nb == 8 && plan.n_groups >= 3 &&
+        getenv("AVS_PIPELINE") != nullptr && !(reinterpret_cast<uintptr_t>(visual) & 15) &&
+        !(reinterpret_cast<uintptr_t>(audio) & 15)) {
+        const int G = plan.n_groups, nbp = plan.nb, slots = G * nbp;
+        std::vector<int64_t> glo(G), ghi(G);
+        bool ordered = true;
+        for (int gq = 0; gq < G && ordered; ++gq) {
+            int64_t lo = INT64_MAX, hi = 0, sum = 0;
+            for (int i = 0; i < nbp; ++i) {
+                const int64_t len = plan.host[slots + gq * nbp + i], rs0 = plan.host[gq * nbp + i];
+                if (len > 0) {
+                    lo = std::min(lo, rs0);
+                    hi = std::max(hi, rs0 + len);
+                    sum += len;
+                }
+            }
+            ordered = sum > 0 && sum == hi - lo && lo == (gq ? ghi[gq - 1] : 0);
+            glo[gq] = lo;
+            ghi[gq] = hi;
+        }
+        ordered = ordered && ghi[G - 1] == R;
+        if (ordered) {
+            pipelined = true;
+            const int n_seg = std::min(G, avs_model::PIPE_SEGS);   // groups 0 .. n_seg-2 alone, the rest together
+            const int n_excl = lstm_exclusive_groups(G);
+            const int sms = device_sm_count();
+            const int slots_all = G * nbp;
+            LstmBatch lb{plan_dev, plan_dev + slots_all, plan_dev + 2 * slots_all, G, nbp, 0};
+            cudaStream_t sa = m->branch_stream[0];
+            StageTimer tm(ST_FRONT_LSTM, st);
+            int busy = 0;   // SMs held by the recurrences launched so far (exclusive: 32 per group, shared: 16)
+            for (int k = 0; k < n_seg; ++k) {
+                const int g_lo = k, g_hi = (k == n_seg - 1) ? G : k + 1;
+                const int64_t r0 = glo[g_lo], Rc = ghi[g_hi - 1] - r0;
+                GemmEpilogue e1;
+                e1.relu = 1;
+                e1.out_dtype = act;
+                e1.ldc = H;
+                if (!bf16 && !f16_in) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
+                GemmEpilogue e2;
+                e2.ldc = 2 * G4;
+                e1.max_ctas = e2.max_ctas = busy ? std::max(sms - busy, 16) : 0;
+                const void* xv = feat_at(visual, r0, Dv, fsz);
+                const void* xa = feat_at(audio, r0, Da, fsz);
+                if (bf16) {
+                    void* dv = in_v16 + r0 * Dv;
+                    void* da = in_a16 + r0 * Da;
+                    AVS_TRY(convert_f32(static_cast<const float*>(xv), dv, Rc * Dv, in_dt, 0, st));
+                    AVS_TRY(convert_f32(static_cast<const float*>(xa), da, Rc * Da, in_dt, 0, st));
+                    xv = dv;
+                    xa = da;
+                }
+                AVS_CUDA(cudaEventRecord(m->ev_branch_in[0], st));
+                AVS_CUDA(cudaStreamWaitEvent(sa, m->ev_branch_in[0], 0));
+                e1.bias = m->fc_v_b;
+                e1.C = v_emb + r0 * H * asz;
+                AVS_TRY(run_gemm(precision, xv, in_dt, Dv, w_fc_v, 0, Dv, Rc, H, Dv, e1, st));
+                e1.bias = m->fc_a_b;
+                e1.C = a_emb + r0 * H * asz;
+                AVS_TRY(run_gemm(precision, xa, in_dt, Da, w_fc_a, 0, Da, Rc, H, Da, e1, sa));
+                e2.bias = m->ih_v_b;
+                e2.C = xg_v + r0 * 2 * G4;
+                AVS_TRY(run_gemm(precision, v_emb + r0 * H * asz, act, H, w_ih_v, 0, H, Rc, 2 * G4, H, e2, st));
+                e2.bias = m->ih_a_b;
+                e2.C = xg_a + r0 * 2 * G4;
+                AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, sa));
+                AVS_CUDA(cudaEventRecord(m->ev_branch_out[0], sa));
+                AVS_CUDA(cudaStreamWaitEvent(st, m->ev_branch_out[0], 0));
+                AVS_CUDA(cudaEventRecord(m->ev_pipe_front[k], st));
+                AVS_CUDA(cudaStreamWaitEvent(m->pipe_stream[k], m->ev_pipe_front[k], 0));
+                // ONE launch per segment (kernels on one stream would run one after the other); only single-group
+                // segments can be exclusive
+                const int excl = (g_hi - g_lo == 1 && g_lo < n_excl) ? 1 : 0;
+                AVS_TRY(lstm_recurrence_tc_groups(xg_v, xg_a, m->whh, lb, g_lo, g_hi, excl, act, fused, act, m->pipe_stream[k]));
+                busy += (g_hi - g_lo) * (excl ? 32 : 16);
+                AVS_CUDA(cudaEventRecord(m->ev_pipe_done[k], m->pipe_stream[k]));
+            }
+            for (int k = 0; k < n_seg; ++k) AVS_CUDA(cudaStreamWaitEvent(st, m->ev_pipe_done[k], 0));
+        }
+    }
+    const int n_chunks = pipelined ? 0 : ((space == AVS_HOST && R >= 2048) ? avs_model::MAX_CHUNKS : 1);
+    const int64_t chunk_rows = ((R + std::max(n_chunks, 1) - 1) / std::max(n_chunks, 1) + 127) / 128 * 128;
     if (space == AVS_HOST) {
         AVS_CUDA(cudaEventRecord(m->ev_start, st));              // the workspace is free once prior work on st is done
         AVS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
@@ -1208,7 +1317,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     }
 
     // ---- K2b: recurrences; writes [v_fwd | v_bwd | a_fwd | a_bwd] = torch.cat of av_model.py:43
-    {
+    if (!pipelined) {
         const int slots = plan.n_groups * plan.nb;
         LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb, lstm_excl};
         int64_t covered = 0;

@@ -98,6 +98,10 @@ struct GemmEpilogue {
     const float* score_w2 = nullptr;
     const float* score_b2 = nullptr;   // device pointer to 1 float
     float* scores = nullptr;
+    // host-side launch hint: at most this many CTAs of the persistent grid (0 = one per SM).  Used when part of the
+    // GPU is known to be occupied by concurrently running recurrence clusters: CTAs of a statically scheduled
+    // persistent kernel that cannot be placed at once would delay their share of the tiles.
+    int max_ctas = 0;
 };
 
 // tcgen05 / TMA path.  in_dtype: DT_F32 (kind::tf32), DT_F16 or DT_BF16 (kind::f16).
@@ -136,6 +140,14 @@ avs_status lstm_recurrence(const float* xg_v, const float* xg_a, const float* wh
 avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
                               int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream,
                               void* save_pre = nullptr, float* save_c = nullptr);
+// The 8-slot variant (batch.nb == 8) for groups [g_lo, g_hi) only, on `stream`, with (exclusive != 0) or without an
+// SM-exclusive shared-memory request: the pipelined forward launches the groups one by one as their input
+// projections become available.  lstm_exclusive_groups: how many leading groups the one-launch policy would give
+// exclusive SMs for this group count.
+avs_status lstm_recurrence_tc_groups(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
+                                     int g_lo, int g_hi, int exclusive, int op_dtype, void* fused, int out_dtype,
+                                     cudaStream_t stream);
+int lstm_exclusive_groups(int n_groups);
 
 // BPTT through the four recurrences (CUDA-core fp32, cluster of 8 CTAs, DSMEM reduce-scatter of dh):
 // d_fused [rows, 1024] -> d_xg_v / d_xg_a [rows, 2048] (gate gradients in the packed column order of xg).

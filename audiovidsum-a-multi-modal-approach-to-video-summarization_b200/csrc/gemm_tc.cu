@@ -18,6 +18,7 @@
 // Tile 128 x BN x 128 B of K per stage (32 tf32 or 64 half elements), 4 MMAs (K = 32 B) per stage.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -660,7 +661,9 @@ static avs_status gemm_tc2(const void* A, int64_t lda, const void* W, int64_t ld
     const int num_tiles = static_cast<int>(tiles_total);
     const int num_pairs = device_sm_count() / 2;
     AVS_CHECK(num_pairs > 0, AVS_ERR_CUDA, "gemm: could not read the SM count");
-    const int grid = 2 * (num_tiles < num_pairs ? num_tiles : num_pairs);
+    int pairs_avail = num_pairs;
+    if (epi.max_ctas > 0) pairs_avail = std::max(1, std::min(num_pairs, epi.max_ctas / 2));
+    const int grid = 2 * (num_tiles < pairs_avail ? num_tiles : pairs_avail);
     const uint32_t idesc = umma_idesc(fmt, 2 * BM, BN);
 #define AVS_GEMM2_LAUNCH(ST_, TF_)                                                                            \
     do {                                                                                                     \
@@ -741,7 +744,9 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     const int num_tiles = static_cast<int>(tiles_total);
     const int num_sms = device_sm_count();
     AVS_CHECK(num_sms > 0, AVS_ERR_CUDA, "gemm: could not read the SM count");
-    const int grid = num_tiles < num_sms ? num_tiles : num_sms;   // persistent: one CTA per SM
+    int sms_avail = num_sms;
+    if (epi.max_ctas > 0) sms_avail = std::max(1, std::min(num_sms, epi.max_ctas));
+    const int grid = num_tiles < sms_avail ? num_tiles : sms_avail;   // persistent: one CTA per SM
     const uint32_t idesc = umma_idesc(fmt, BM, BN);
 
 #define AVS_GEMM_LAUNCH(BN_, ST_, TF_)                                                                       \

@@ -502,8 +502,7 @@ avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, con
     SplitCtx& sc = split_ctx();
     int n_excl = 0;
     if (PARTS == 2 && !no_split && batch.excl >= 0) {
-        static const int kExclusive[8] = {0, 1, 2, 3, 3, 2, 1, 1};
-        n_excl = batch.n_groups <= 7 ? kExclusive[batch.n_groups] : 0;
+        n_excl = lstm_exclusive_groups(batch.n_groups);
         if (n_excl < batch.n_groups && !sc.ok) n_excl = 0;
     }
     if (n_excl == 0 || n_excl == batch.n_groups) {
@@ -526,6 +525,34 @@ avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, con
 }
 
 }  // namespace
+
+int lstm_exclusive_groups(int n_groups) {
+    static const int kExclusive[8] = {0, 1, 2, 3, 3, 2, 1, 1};
+    return (n_groups >= 0 && n_groups <= 7) ? kExclusive[n_groups] : 0;
+}
+
+avs_status lstm_recurrence_tc_groups(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch_in,
+                                     int g_lo, int g_hi, int exclusive, int op_dtype, void* fused, int out_dtype,
+                                     cudaStream_t stream) {
+    AVS_CHECK(batch_in.nb == 8 && g_lo >= 0 && g_lo < g_hi && g_hi <= batch_in.n_groups, AVS_ERR_INVALID,
+              "lstm_recurrence_tc_groups: bad group range [%d, %d) of %d (8-slot variant only)", g_lo, g_hi, batch_in.n_groups);
+    AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
+    LstmBatch batch = batch_in;
+    batch.lane_map = 1;
+    auto kern = lstm_tc_kernel<16, 2, 2, false>;
+    constexpr int SMEM = Smem<16, 2>::TOTAL;
+    constexpr int SMEM_EXCLUSIVE = 200 * 1024;
+    static PerDeviceOnce configured;
+    const int dev = current_device();
+    if (configured.needed(dev)) {
+        AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_EXCLUSIVE));
+        configured.mark(dev);
+    }
+    kern<<<(g_hi - g_lo) * 4 * CL, 2 * 128 + 2 * 32, exclusive ? SMEM_EXCLUSIVE : SMEM, stream>>>(
+        xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, 0, nullptr, nullptr, g_lo);
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
 
 // debugging aid: the phase trace of the last traced launch (8 values, see g_lstm_trace)
 avs_status lstm_trace_read(unsigned long long* out8) {

@@ -66,8 +66,8 @@ def stage_flops_per_frame(axis: str, mean_T: float):
     f["frontend_gemms"] = f["fc_gemm"] + f["lstm_input_gemm"]
     # out_proj with the score head fused into its epilogue
     f["out_proj_score_gemm"] = f["attn_out_proj_gemm"] + f["score_head_gemm"]
-    # the recurrence with the input projection fused in
-    f["lstm_fused"] = f["lstm_input_gemm"] + f["lstm_recurrence"]
+    # pipelined front: fc + LSTM-input GEMMs of group k+1.. run beside the recurrence of groups ..k; one timed stage
+    f["frontend_lstm_pipelined"] = f["frontend_gemms"] + f["lstm_recurrence"]
     return f
 
 
