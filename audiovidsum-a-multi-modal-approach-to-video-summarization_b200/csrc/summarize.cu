@@ -347,58 +347,31 @@ __global__ void __launch_bounds__(NT) knapsack_fast_kernel(SummaryBatch b, const
     for (int s = 0; s < (BIG ? 0 : S); ++s) {
         const int wt = item_len[s];
         const V val = static_cast<V>(item_val[s]);
-        const V* rd = (BIG || !(s & 1)) ? buf_a : buf_b;
-        V* wr = (BIG || (s & 1)) ? buf_a : buf_b;
-        // cells in batches of KB: first all shared-memory loads of a batch (independent, unconditional: the address
-        // is clamped and the value discarded when the shot does not fit), then the compares / ballots -- with one
-        // branch per cell in front of its load the 36 cells of a long video were 36 serialised load latencies
-        constexpr int KB = CPT < 8 ? CPT : 8;
-        static_assert(CPT % KB == 0, "cells per thread must be a multiple of the batch");
-        const bool shift = wt > 0;
+        const V* rd = (s & 1) ? buf_b : buf_a;
+        V* wr = (s & 1) ? buf_a : buf_b;
 #pragma unroll
-        for (int c0 = 0; c0 < CPT; c0 += KB) {
-            if (c0 * NT <= cap) {   // warp-uniform
-                V prev[KB];
-#pragma unroll
-                for (int k = 0; k < KB; ++k) {
-                    const int w = tid + (c0 + k) * NT;
-                    const int src = w - wt;
-                    prev[k] = rd[(shift && src >= 0 && w <= cap) ? src : 0];
-                }
-#pragma unroll
-                for (int k = 0; k < KB; ++k) {
-                    const int c = c0 + k;
-                    const int w = tid + c * NT;
-                    if (c * NT <= cap) {   // warp-uniform
-                        bool better = false;
-                        if (w <= cap) {
-                            const V old = mine[c];
-                            V cand = old;
-                            if (shift && w >= wt) {
-                                cand = prev[k] + val;
-                                better = cand > old;
-                            } else if (wt == 0 && val > 0) {
-                                cand = old + val;
-                                better = true;
-                            }
-                            mine[c] = better ? cand : old;
-                            if (!BIG) wr[w] = mine[c];
-                        }
-                        const uint32_t bits = __ballot_sync(0xffffffffu, better);
-                        if ((tid & 31) == 0 && (w >> 5) < words) keep[static_cast<size_t>(s) * words + (w >> 5)] = bits;
+        for (int c = 0; c < CPT; ++c) {
+            const int w = tid + c * NT;
+            if (c * NT <= cap) {   // warp-uniform
+                bool better = false;
+                if (w <= cap) {
+                    const V old = mine[c];
+                    V cand = old;
+                    if (wt > 0 && w >= wt) {
+                        cand = rd[w - wt] + val;
+                        better = cand > old;
+                    } else if (wt == 0 && val > 0) {
+                        cand = old + val;
+                        better = true;
                     }
+                    mine[c] = better ? cand : old;
+                    wr[w] = mine[c];
                 }
+                const uint32_t bits = __ballot_sync(0xffffffffu, better);
+                if ((tid & 31) == 0 && (w >> 5) < words) keep[s * words + (w >> 5)] = bits;
             }
         }
         __syncthreads();
-        if (BIG) {   // single buffer: everybody has read row s - 1, now publish row s
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int w = tid + c * NT;
-                if (w <= cap) wr[w] = mine[c];
-            }
-            __syncthreads();
-        }
     }
     if (!BIG) {
         if (tid == 0) {

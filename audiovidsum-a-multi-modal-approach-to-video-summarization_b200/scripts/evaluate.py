@@ -15,6 +15,17 @@ import torch
 
 def evaluate(model, dataset, return_per_video: bool = False):
     model.eval()
+    from ..data.dataset import DeviceDataset
+    if isinstance(dataset, DeviceDataset):      # packed once, already on the GPU: no per-call H2D at all
+        if len(dataset) == 0:
+            nan = float("nan")
+            return {"f1": nan, "spearman": nan, "kendall": nan}
+        with torch.no_grad():
+            axis = "literal_b1" if model.attn_axis == "literal" else model.attn_axis
+            pred = model.native().forward_rows(dataset.visual, dataset.audio, dataset.row_start, dataset.lengths, axis,
+                                               model.precision)
+        return _metrics(pred, dataset.scores, dataset.row_start, dataset.lengths,
+                        torch.float64 if dataset.scores.dtype == torch.float64 else torch.float32, return_per_video)
     visuals, audios, targets = [], [], []
     for features, scores in dataset:
         visuals.append(torch.as_tensor(features["visual"]))
@@ -35,6 +46,10 @@ def evaluate(model, dataset, return_per_video: bool = False):
                                            model.precision)
     tgt_dtype = torch.float64 if any(t.dtype == torch.float64 for t in targets) else torch.float32
     target = torch.cat([t.to(tgt_dtype) for t in targets]).to(dev)
+    return _metrics(pred, target, starts, lens, tgt_dtype, return_per_video)
+
+
+def _metrics(pred, target, starts, lens, tgt_dtype, return_per_video):
     from .. import runtime
     metrics, counts = runtime.eval_metrics_rows(pred, target, starts, lens)
     # scipy.stats.kendalltau returns the correlation in the dtype of its inputs when both are float32

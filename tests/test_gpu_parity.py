@@ -587,6 +587,26 @@ def test_evaluate_drop_in_matches_reference_loop(cuda_ready):
     assert abs(float(got["kendall"]) - np.mean([r[2] for r in ref])) < 5e-3
 
 
+def test_evaluate_on_a_device_resident_dataset(cuda_ready):
+    """data.dataset.DeviceDataset: the dataset packed once into device memory gives the same metrics as the per-call
+    upload path, bit for bit (same kernels, same data); the fp16 feature cache stays within the score tolerance."""
+    from avsum_b200.scripts.evaluate import evaluate
+    from avsum_b200.data.dataset import DeviceDataset
+    vids = synth.config2()[:7]
+    rng = np.random.default_rng(6)
+    dataset = [({"visual": v.visual, "audio": v.audio}, torch.from_numpy(rng.random(v.T).astype(np.float32)))
+               for v in vids]
+    m = make_model(spread=True)
+    want = evaluate(m, dataset)
+    cached = DeviceDataset(dataset)
+    assert len(cached) == 7 and cached.visual.is_cuda and cached[2][0]["visual"].shape == (vids[2].T, 1024)
+    for _ in range(2):
+        got = evaluate(m, cached)
+        assert got["f1"] == want["f1"] and got["spearman"] == want["spearman"] and got["kendall"] == want["kendall"]
+    half = evaluate(m, DeviceDataset(dataset, feature_dtype="fp16"))
+    assert abs(half["spearman"] - want["spearman"]) < 5e-3 and abs(float(half["kendall"]) - float(want["kendall"])) < 5e-3
+
+
 # ------------------------------------------------------------------ features/fusion.py helpers (a9-a11)
 def test_fusion_helpers_match_reference(cuda_ready, golden_dir):
     from avsum_b200.features import fusion

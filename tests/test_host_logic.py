@@ -104,6 +104,14 @@ def test_feature_dir_dataset_and_packed_batches(tmp_path):
         for k, i in enumerate(b.indices):
             s, n = int(b.row_start[k]), int(b.lengths[k])
             assert torch.equal(b.visual[s:s + n], ds[i][0]["visual"]) and torch.equal(b.scores[s:s + n], ds[i][1])
+    # opt-in 16-bit feature cache: same batches, features packed as IEEE half (scores untouched)
+    half = list(packed_batches(ds, max_frames=30, pin=False, feature_dtype="fp16"))
+    assert [b.indices for b in half] == [b.indices for b in batches]
+    for hb, fb in zip(half, batches):
+        assert hb.visual.dtype == torch.float16 and hb.audio.dtype == torch.float16 and hb.scores.dtype == fb.scores.dtype
+        assert torch.equal(hb.visual, fb.visual.to(torch.float16))
+    with pytest.raises(ValueError):
+        next(packed_batches(ds, feature_dtype="bf16"))
 
 
 def test_shot_descriptors_pack_like_the_per_call_path():
