@@ -2,8 +2,8 @@
 // (/root/reference/models/av_model.py:18-23, 39-40) on tcgen05.
 //
 // One thread-block cluster of 8 CTAs runs one (modality, direction) recurrence for a group of up
-// to NB videos.  CTA r owns hidden units [32r, 32r+32) = 128 gate columns, packed so that the four
-// gates (i,f,g,o) of a unit sit in four adjacent accumulator lanes (column p = 4*jj + gate).
+// to NB videos.  CTA r owns hidden units [32r, 32r+32) = 128 gate columns (global packing p = 4*jj + gate); inside
+// the CTA's accumulator the four gates (i,f,g,o) of a unit sit 8 TMEM lanes apart (lane 32 q + 8 gate + u).
 //
 // Per time step and CTA:
 //   gates^T[128 cols, NB videos] = W_hh_slice[128, 256] * h_prev[NB, 256]^T      (16 x tcgen05.mma, fp16 in, fp32 acc)
@@ -11,9 +11,12 @@
 //       128 lanes x 128 columns), so a step never re-streams the 64 KB slice through shared memory
 //     - h_prev: fp16, shared memory (no-swizzle K-major), rewritten every step by all 8 CTAs
 //     - accumulator: tensor memory, NB columns
-//   epilogue warps (4 per "part" of NB/4 videos): tcgen05.ld -> 4x4 quad shuffle transpose (every thread then
-//     owns all four gates of one (hidden unit, video)) -> + x W_ih^T (precomputed by the GEMM, fp32, one
-//     float4) -> cell update on the SFU with shared denominators (5 ex2 + 2 rcp per cell) in fp32 registers
+//   epilogue warps (4 per "part" of NB/4 videos): two tcgen05.ld of the 16-lane shapes (.16x128b / .16x256b), which
+//     hand thread t the accumulator rows t/4, t/4 + 8 (+ 16, + 24 for the second load) of column t%4: the W_hh rows
+//     are placed in TMEM so that those four lanes are the gates i, f, g, o of ONE hidden unit, i.e. every thread owns
+//     all four gates of one (hidden unit, video) straight out of the load (round 1 read one lane per thread and
+//     transposed 4x4 with two shuffle rounds, ~65 clk of every step's critical path) -> + x W_ih^T (precomputed by
+//     the GEMM, fp32, one float4) -> cell update on the SFU with shared denominators (5 ex2 + 2 rcp per cell)
 //     -> h staged as fp16 in the destination layout, then pushed into every peer CTA's next-step buffer per
 //     warp, right after a __syncwarp: lane l sends the 16-byte chunk of video l/8 to CTA l%8 with st.async,
 //     whose mbarrier complete_tx (release at cluster scope) counts the bytes on the receiver's barrier;
@@ -82,31 +85,56 @@ __device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, u
     return d;
 }
 
-template <int N>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]);
-template <>
-__device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, uint32_t (&r)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr)
-                 : "memory");
+// The four gate pre-activations of this thread's (hidden unit, video) pairs.  TMEM lane 32 q + 8 g + u holds gate g of
+// hidden unit 8 q + u; the .16x128b / .16x256b shapes give thread t (u = t / 4, c = t % 4) lanes u and u + 8 of a
+// 16-lane window -- gates (i, f) from the window at lane 32 q, gates (g, o) from the window at 32 q + 16 -- for
+// column c (NV = 4), columns 2c, 2c + 1 (NV = 8) or 2c, 2c + 1, 8 + 2c, 9 + 2c (NV = 16).
+template <int NV>
+__device__ __forceinline__ void tmem_ld_gates(uint32_t taddr, float (&gi)[NV / 4], float (&gf)[NV / 4], float (&gg)[NV / 4],
+                                              float (&go)[NV / 4]) {
+    const uint32_t hi = taddr + (16u << 16);
+    if constexpr (NV == 4) {
+        uint32_t a0, a1, b0, b1;
+        asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(taddr) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(hi) : "memory");
+        tmem_ld_wait();
+        gi[0] = __uint_as_float(a0); gf[0] = __uint_as_float(a1); gg[0] = __uint_as_float(b0); go[0] = __uint_as_float(b1);
+    } else if constexpr (NV == 8) {
+        uint32_t a[4], b[4];
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(taddr) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(hi) : "memory");
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            gi[k] = __uint_as_float(a[k]); gf[k] = __uint_as_float(a[2 + k]);
+            gg[k] = __uint_as_float(b[k]); go[k] = __uint_as_float(b[2 + k]);
+        }
+    } else {
+        static_assert(NV == 16, "video slots per part: 4, 8 or 16");
+        uint32_t a[8], b[8];
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7])
+                     : "r"(hi) : "memory");
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // k = 2 * (column block) + (column in the pair)
+            const int o = (k >> 1) * 4 + (k & 1);
+            gi[k] = __uint_as_float(a[o]); gf[k] = __uint_as_float(a[o + 2]);
+            gg[k] = __uint_as_float(b[o]); go[k] = __uint_as_float(b[o + 2]);
+        }
+    }
 }
-template <>
-__device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-template <>
-__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-        "[%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
+// video slot (inside the part) of this thread's k-th pair, c = lane % 4
+template <int NV>
+__device__ __forceinline__ int owned_video(int c, int k) {
+    if constexpr (NV == 4) return c;
+    else if constexpr (NV == 8) return 2 * c + k;
+    else return 2 * c + (k & 1) + 8 * (k >> 1);
 }
 
 // SFU primitives of the cell update: ex2.approx / rcp.approx are ~1-2 ulp (absolute error ~1e-7 on the gate
@@ -195,11 +223,13 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         // W_hh slice -> tensor memory, resident for the whole kernel.  A-operand layout of
         // kind::f16 with M = 128: lane = row (gate column), 32-bit column c holds k = 2c, 2c+1.
         const int q = warp & 3;                            // lane quarter
-        const int row = q * 32 + lane;
+        // TMEM lane 32 q + 8 g + u  <-  packed row 4 (8 q + u) + g  (gate g of hidden unit 8 q + u): the four gates
+        // of a unit sit 8 lanes apart, where the 16-lane tcgen05.ld shapes deliver them to one thread
+        const int prow = q * 32 + ((lane & 7) << 2) + (lane >> 3);
 #pragma unroll 1
         for (int cpart = warp >> 2; cpart < 4; cpart += PARTS) {   // 32-column (64 k) part of the row
             const float4* src = reinterpret_cast<const float4*>(
-                whh + (static_cast<size_t>(ld) * 4 * HC + r * COLS + row) * HC + cpart * 64);
+                whh + (static_cast<size_t>(ld) * 4 * HC + r * COLS + prow) * HC + cpart * 64);
             uint32_t pk[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -275,22 +305,19 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps
-        // TMEM lane p = 4*jj + gate holds one gate of hidden unit jj for NV videos (columns).  The four
-        // lanes of a quad exchange their values with a 4x4 shuffle transpose, after which lane g owns ALL
-        // four gates of unit jj for video v0 + 4k + g: the cell update runs once per (unit, video) with
-        // no redundant lanes, and the input projection arrives as one float4 per owned video.
+        // Thread (u = lane / 4, c = lane % 4) of quarter q owns hidden unit jj = 8 q + u and NP = NV / 4 videos
+        // (owned_video): the cell update runs once per (unit, video) with no redundant lanes, the gates come
+        // straight from the two 16-lane TMEM loads and the input projection arrives as one float4 per video.
         const int q = warp & 3;              // TMEM lane quarter
         const int part = warp >> 2;          // which quarter of the videos
-        const int p = q * 32 + lane;         // gate column inside the slice: 4*jj + gate
-        const int g = p & 3;                 // gate held in TMEM == video-in-block owned after the transpose
-        const int jj = p >> 2;
+        const int cq = lane & 3;             // column selector of the 16-lane load shapes
+        const int jj = q * 8 + (lane >> 2);  // hidden unit inside the CTA's slice
         const int v0 = part * NV;                        // first video slot of this part (index into s_len / s_row)
         const int lv0 = CHAINS == 1 ? v0 : 0;            // the same, relative to this chain's buffers / accumulator
         const float4* xg4 = reinterpret_cast<const float4*>(((ld >> 1) ? xg_a : xg_v) + dir * (4 * HC) + r * COLS + 4 * jj);
         constexpr int XG_LD4 = XG_LD / 4;
         const int out_col = ld * HC + r * UNITS;
         const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + lv0;
-        const bool par1 = (lane & 1) != 0, par2 = (lane & 2) != 0;
         // this thread's slot in the staged slice: [jj/8][video][jj%8] 16-bit values
         uint16_t* stage_mine = reinterpret_cast<uint16_t*>(stage16 + (jj >> 3) * S::H_LBO) + (jj & 7);
         float* const fcol = reinterpret_cast<float*>(fused_out) + out_col + jj;
@@ -315,7 +342,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             c_state[k] = 0.f;
-            vid_r[k] = v0 + 4 * k + g;
+            vid_r[k] = v0 + owned_video<NV>(cq, k);
             const int len = s_len[vid_r[k]];
             len_r[k] = len;
             row_r[k] = s_row[vid_r[k]] + (dir ? (len > 0 ? len - 1 : 0) : 0);
@@ -338,9 +365,8 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
                 tC = clk64();
                 tr_acc[1] += tC - tr_ts[0];                   // commit issued -> epilogue awake (MMA latency)
             }
-            uint32_t acc[NV];
-            tmem_ld_cols<NV>(taddr, acc);
-            tmem_ld_wait();
+            float gi[NP], gf[NP], gg[NP], go[NP];
+            tmem_ld_gates<NV>(taddr, gi, gf, gg, go);
             if (tracing && tid == 0) {
                 tD = clk64();
                 tr_acc[2] += tD - tC;                         // tcgen05.ld
@@ -348,18 +374,10 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
             float h_out[NP];
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                // ---- quad transpose: in a[j] = (gate g, video 4k + j)  ->  out t_j = (gate j, video 4k + g)
-                const float a0 = __uint_as_float(acc[4 * k]), a1 = __uint_as_float(acc[4 * k + 1]);
-                const float a2 = __uint_as_float(acc[4 * k + 2]), a3 = __uint_as_float(acc[4 * k + 3]);
-                const float r0 = __shfl_xor_sync(0xffffffffu, par1 ? a0 : a1, 1);
-                const float r1 = __shfl_xor_sync(0xffffffffu, par1 ? a2 : a3, 1);
-                const float n0 = par1 ? r0 : a0, n1 = par1 ? a1 : r0, n2 = par1 ? r1 : a2, n3 = par1 ? a3 : r1;
-                const float u0 = __shfl_xor_sync(0xffffffffu, par2 ? n0 : n2, 2);
-                const float u1 = __shfl_xor_sync(0xffffffffu, par2 ? n1 : n3, 2);
-                const float t_i = (par2 ? u0 : n0) + xv0[k].x;
-                const float t_f = (par2 ? u1 : n1) + xv0[k].y;
-                const float t_g = (par2 ? n2 : u0) + xv0[k].z;
-                const float t_o = (par2 ? n3 : u1) + xv0[k].w;
+                const float t_i = gi[k] + xv0[k].x;
+                const float t_f = gf[k] + xv0[k].y;
+                const float t_g = gg[k] + xv0[k].z;
+                const float t_o = go[k] + xv0[k].w;
                 // ---- LSTM cell on the SFU with shared denominators (5 ex2 + 2 rcp per cell):
                 //   sigmoid(x) = 1 / (1 + e^-x),  tanh(x) = (1 - e^-2x) / (1 + e^-2x)
                 //   c' = sig(f) c + sig(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ei)(1+eg)(1+ef)]
