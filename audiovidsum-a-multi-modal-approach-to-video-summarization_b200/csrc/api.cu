@@ -1787,12 +1787,20 @@ static avs_status bilstm_pair_impl(avs_model* m, const float* v_emb, const float
     const GemmW w_ih_v{m->ih_v_x, m->ih_v_t, m->ih_v_l}, w_ih_a{m->ih_a_x, m->ih_a_t, m->ih_a_l};
     GemmEpilogue e2;
     e2.ldc = 2 * G4;
+    // the two input projections are independent: the audio one runs on the branch stream (fork / join, capturable)
+    cudaStream_t sa = m->branch_stream[0];
+    AVS_CUDA(cudaEventRecord(m->ev_branch_in[0], st));
+    AVS_CUDA(cudaStreamWaitEvent(sa, m->ev_branch_in[0], 0));
     e2.bias = m->ih_v_b;
     e2.C = xg_v;
-    AVS_TRY(run_gemm(precision, xv, act, H, w_ih_v, 0, H, R, 2 * G4, H, e2, st));
+    avs_status sv = run_gemm(precision, xv, act, H, w_ih_v, 0, H, R, 2 * G4, H, e2, st);
     e2.bias = m->ih_a_b;
     e2.C = xg_a;
-    AVS_TRY(run_gemm(precision, xa, act, H, w_ih_a, 0, H, R, 2 * G4, H, e2, st));
+    avs_status sa_rc = run_gemm(precision, xa, act, H, w_ih_a, 0, H, R, 2 * G4, H, e2, sa);
+    cudaEventRecord(m->ev_branch_out[0], sa);
+    cudaStreamWaitEvent(st, m->ev_branch_out[0], 0);
+    AVS_TRY(sv);
+    AVS_TRY(sa_rc);
     const int slots = plan.n_groups * plan.nb;
     LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
     if (!simt) return lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, act, fused, DT_F32, 0, st, save_pre, save_c);

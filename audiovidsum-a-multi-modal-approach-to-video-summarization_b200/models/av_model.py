@@ -47,6 +47,7 @@ class AVBiLSTMModel(nn.Module):
         self._native_key = None
         self._native_lstm_key = None
         self._train_in_eval = False   # set to differentiate through an eval-mode (dropout-free) forward
+        self._side_stream = None      # training forward: the audio branch's stream
 
     # ------------------------------------------------------------------ native handle
     def _weights_key(self):
@@ -142,8 +143,18 @@ class AVBiLSTMModel(nn.Module):
         xv = visual.reshape(B * T, -1).to(torch.float32)
         xa = audio.reshape(B * T, -1).to(torch.float32)
         relu, drop = torch.relu, torch.nn.functional.dropout
+        # the audio branch (audio_fc) is independent of the visual one until the recurrences: it runs on a side stream
+        # (autograd runs each node's backward on the stream of its forward, so the two fc backward passes overlap too;
+        # fork / join by stream waits -- capturable in the CUDA graph of training.TrainStep)
+        cur = torch.cuda.current_stream(visual.device)
+        if self._side_stream is None or self._side_stream.device != visual.device:
+            self._side_stream = torch.cuda.Stream(device=visual.device)
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            a = drop(relu(T_.linear(xa, self.audio_fc[0].weight, self.audio_fc[0].bias)), self.audio_fc[2].p, self.training)
         v = drop(relu(T_.linear(xv, self.visual_fc[0].weight, self.visual_fc[0].bias)), self.visual_fc[2].p, self.training)
-        a = drop(relu(T_.linear(xa, self.audio_fc[0].weight, self.audio_fc[0].bias)), self.audio_fc[2].p, self.training)
+        cur.wait_stream(side)   # (every later use of the side stream starts by waiting for `cur`: no record_stream needed)
         lw = []
         for mod in (self.visual_bilstm, self.audio_bilstm):
             for suf in ("", "_reverse"):
