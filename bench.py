@@ -673,7 +673,10 @@ def run_train(args, rank, world, local_rank):
     model = AVBiLSTMModel(1024, 128, 512, attn_axis="literal_b1")
     model.load_state_dict(synth.seeded_state_dict())
     model = model.to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True)
+    # the reference's optimiser (train_av_model.py:68: AdamW, lr 1e-4) in torch's single-kernel form: the default
+    # (foreach) capturable AdamW launches ~100 tiny kernels per step for the per-parameter bias corrections
+    # (profiles/r02i_train_launches.csv: 83 + 18 launches, 0.6 ms serialised); same update rule
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True, **({} if args.foreach_adamw else {"fused": True}))
     n_params = sum(p.numel() for p in model.parameters())
     stepper = training.TrainStep(model, opt, torch.nn.functional.mse_loss, visual, audio, target,
                                  world_size=world, graph=not args.no_graph, warmup=max(args.warmup, 3))
@@ -717,6 +720,8 @@ def run_train(args, rank, world, local_rank):
                 "config": {"workload": WORKLOADS["train"], "videos_per_gpu": B, "frames_per_gpu": B * T,
                            "parameters": n_params, "gradient_bucket_mb": n_params * 4 / 1e6,
                            "cuda_graph": stepper.graphed, "allreduce": stepper.allreduce_mode,
+                           "optimizer": "torch.optim.AdamW(lr=1e-4, capturable=True, "
+                                        + ("foreach)" if args.foreach_adamw else "fused=True)"),
                            "parallelism": f"dp{world} by video", "l2": "activations + weights + optimiser state of a "
                            "step (~0.5 GB touched) exceed the 126 MB L2"},
                 "steps_per_s": 1e3 / ms,
@@ -726,7 +731,7 @@ def run_train(args, rank, world, local_rank):
                 "roofline": {"kernel": "whole step (~100 small kernels; BPTT chain is latency bound)", "bound": "tensor",
                              "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
                              "traffic": None},
-                "final_loss": float(loss), "last_e2e_loss": last,
+                "final_loss": float(loss.detach()), "last_e2e_loss": last,
                 "comm": {"backend": "nccl" if world > 1 else None, "nranks": world}}
         print(json.dumps(line), flush=True)
     finish(world, dist)
@@ -743,6 +748,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-attention-probe", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="--config train: launch the step eagerly")
+    ap.add_argument("--foreach-adamw", action="store_true", help="--config train: torch's default (foreach) AdamW")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
