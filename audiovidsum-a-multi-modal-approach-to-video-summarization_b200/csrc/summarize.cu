@@ -11,8 +11,10 @@
 //   dp_s[w]    = max(dp_{s-1}[w], dp_{s-1}[w - nf_s] + seg_mean_s), item kept only on strict gain
 //   back-trace from (S-1, capacity), capacity = floor(n_frames * num / den).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace avs {
 
@@ -455,6 +457,227 @@ __global__ void __launch_bounds__(NT) knapsack_fast_kernel(SummaryBatch b, const
     }
 }
 
+// ---------------------------------------------------------------------------- K7 + K8, long videos on a cluster
+// The long-video kernel above runs one video on ONE SM and is bound by instruction issue there (36 cells per thread
+// and item); a configs[3] batch has 8 videos for 148 SMs.  Here a cluster of KC CTAs shares a video: CTA k owns the
+// capacity cells [k * slice, (k + 1) * slice) (register-resident, published into a double-buffered shared row), and
+// cell w reads dp[w - wt] from the row of whichever CTA owns it -- its own (plain shared loads; warp-uniform test)
+// or a CTA to the left (ld.shared::cluster).  One cluster barrier per item orders "row s complete everywhere" before
+// its first read and "row s - 1 no longer read" before it is overwritten.  Every CTA pools the shots itself (cheap,
+// and it avoids a broadcast); CTA 0 walks the keep bits back and writes picks / bitmap.
+constexpr int KC = 4;                 // CTAs per video
+constexpr int KC_THREADS = 512;
+constexpr int KC_CPT = 12;            // cells per thread: slice <= 6,144 cells, capacity <= 24,575
+
+__device__ __forceinline__ long long ld_dsmem_s64(uint32_t cluster_addr) {
+    long long v;
+    asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(KC, 1, 1) __launch_bounds__(KC_THREADS)
+knapsack_cluster_kernel(SummaryBatch b, const float* __restrict__ scores, const int32_t* __restrict__ positions,
+                        long long* __restrict__ seg_mean_out, uint8_t* __restrict__ picks, uint8_t* __restrict__ summary,
+                        int slice, int items_cap, uint32_t* __restrict__ keep_bits) {
+    extern __shared__ long long csm[];
+    constexpr int NT = KC_THREADS;
+    const int v = blockIdx.x / KC;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tid = threadIdx.x;
+    const int nf = b.n_frames[v];
+    const int s0 = b.cps_start[v], S = b.cps_start[v + 1] - s0;
+    const int2* cps = reinterpret_cast<const int2*>(b.cps) + s0;
+    const long long cap_ll = (static_cast<long long>(nf) * b.prop_num) / b.prop_den;
+    const int cap = static_cast<int>(cap_ll < 0 ? 0 : cap_ll);
+    // keep rows as the planner lays them out for long videos (knapsack_keep_words): padded to whole 2,048-cell groups
+    const int kwords = (cap + 4 * KNAP_BIG_THREADS) / (4 * KNAP_BIG_THREADS) * (4 * KNAP_BIG_THREADS) / 32;
+    const int cpt = slice / NT;                       // cells per thread actually used (slice is a multiple of NT)
+    const int lo = static_cast<int>(rank) * slice;    // first cell of this CTA
+
+    long long* item_val = csm;                                        // [items_cap]
+    long long* row0 = item_val + items_cap;                           // [2][slice] double-buffered row slice
+    int* item_beg = reinterpret_cast<int*>(row0 + 2 * static_cast<size_t>(slice));
+    int* item_len = item_beg + items_cap;
+    // keep bits of the last KEEP_BATCH items, flushed to the global workspace in one coalesced burst: a global store
+    // per item would be outstanding at every cluster barrier, whose release semantics then wait for it (measured:
+    // 2.3 us per item with the stores in the loop)
+    constexpr int KEEP_BATCH = 16;
+    const int wpc = slice / 32;                                       // keep words of this CTA's slice per item
+    uint32_t* keep_sm = reinterpret_cast<uint32_t*>(item_len + items_cap);   // [KEEP_BATCH][wpc]
+    uint32_t* keep = keep_bits + b.keep_start[v];
+
+    for (int s = tid; s < S; s += NT) {
+        const int2 seg = cps[s];
+        item_beg[s] = seg.x;
+        item_len[s] = seg.y - seg.x + 1;
+        item_val[s] = 0;
+    }
+    __syncthreads();
+    {   // K7 (every CTA of the cluster computes the same per-shot sums)
+        const int row0v = b.row_start[v], T = b.lengths[v];
+        unsigned long long* acc = reinterpret_cast<unsigned long long*>(item_val);
+        for (int i = tid; i < T; i += NT) {
+            const long long q = quantize_score(scores[row0v + i]);
+            const int plo = positions[row0v + i];
+            const int phi = (i + 1 < T) ? positions[row0v + i + 1] : nf;
+            if (phi <= plo || q == 0) continue;
+            int a = 0, z = S;
+            while (a < z) {
+                const int mid = (a + z) >> 1;
+                if (item_beg[mid] + item_len[mid] - 1 < plo) a = mid + 1; else z = mid;
+            }
+            for (int s = a; s < S; ++s) {
+                const int sb = item_beg[s];
+                if (sb >= phi) break;
+                const int ov = min(phi, sb + item_len[s]) - max(plo, sb);
+                if (ov > 0) atomicAdd(acc + s, static_cast<unsigned long long>(q * ov));
+            }
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < S; s += NT) {
+        const int wt = item_len[s];
+        const unsigned long long sum = static_cast<unsigned long long>(item_val[s]);
+        const long long val = wt > 0 ? static_cast<long long>((2ull * sum + wt) / (2ull * wt)) : 0ll;
+        if (rank == 0 && seg_mean_out != nullptr) seg_mean_out[s0 + s] = val;
+        item_val[s] = val;
+    }
+    long long mine[KC_CPT];
+#pragma unroll
+    for (int c = 0; c < KC_CPT; ++c) {
+        mine[c] = 0;
+        if (c < cpt) {
+            row0[tid + c * NT] = 0;
+            row0[slice + tid + c * NT] = 0;
+        }
+    }
+    __syncthreads();
+    cluster_barrier();     // every CTA's rows exist (zeroed) before any remote read
+    // (a per-item barrier built from mbarriers -- one remote arrive per CTA pair -- measured the same as
+    // barrier.cluster here: 1.49 vs 1.40 ms for 8 videos; what costs is the remote halo reads, not the barrier)
+    const uint32_t row_sa = smem_u32(row0);
+    const bool lane0 = (tid & 31) == 0;
+    const int my_words = max(0, min(wpc, kwords - (lo >> 5)));     // words of this slice that exist in the keep rows
+    for (int s = 0; s < S; ++s) {
+        const int wt = item_len[s];
+        const long long val = item_val[s];
+        const long long* rd = row0 + static_cast<size_t>(s & 1) * slice;
+        long long* wr = row0 + static_cast<size_t>((s & 1) ^ 1) * slice;
+        const uint32_t rd_sa = row_sa + static_cast<uint32_t>(s & 1) * slice * 8;
+        uint32_t* krow = keep_sm + (s % KEEP_BATCH) * wpc + (tid >> 5);
+        const bool bump = wt == 0 && val > 0;
+#pragma unroll
+        for (int c = 0; c < KC_CPT; ++c) {
+            if (c < cpt) {   // uniform
+                const int wl = tid + c * NT;            // local cell
+                const int src = lo + wl - wt;           // global source cell
+                long long prev = 0;
+                if (src >= lo) {
+                    prev = rd[src - lo];                // own slice (all lanes, except in the first wt cells)
+                } else if (src >= 0) {
+                    const int owner = src / slice;      // halo: a CTA to the left
+                    prev = ld_dsmem_s64(mapa(rd_sa + static_cast<uint32_t>(src - owner * slice) * 8, owner));
+                }
+                const long long cand = (bump ? mine[c] : prev) + val;
+                const bool better = bump || (wt > 0 && src >= 0 && cand > mine[c]);
+                mine[c] = better ? cand : mine[c];
+                wr[wl] = mine[c];
+                const uint32_t bits = __ballot_sync(0xffffffffu, better);
+                if (lane0) krow[c * (NT / 32)] = bits;
+            }
+        }
+        // row s complete in every CTA before item s + 1 reads it; nobody still reads the buffer item s + 1 overwrites
+        cluster_barrier();
+        if ((s % KEEP_BATCH) == KEEP_BATCH - 1 || s == S - 1) {
+            // flush the batch (a video shorter than the batch's longest has narrower keep rows than KC slices: only
+            // my_words of them exist; cells past them are never read)
+            const int first = s - (s % KEEP_BATCH), n_it = s - first + 1;
+            for (int i = tid; i < n_it * my_words; i += NT) {
+                const int it = i / my_words, wd = i - it * my_words;
+                keep[static_cast<size_t>(first + it) * kwords + (lo >> 5) + wd] = keep_sm[it * wpc + wd];
+            }
+            __syncthreads();   // keep_sm is rewritten by the next item
+        }
+    }
+    __threadfence();
+    cluster_barrier();       // every CTA's last keep-bit flush is visible; last access to the peers' shared memory is over
+    if (rank != 0) return;
+    // ---- back-trace on CTA 0, keep rows staged through the (now free) row buffers in chunks
+    __threadfence();
+    uint32_t* stage = reinterpret_cast<uint32_t*>(row0);
+    const int chunk = max(1, static_cast<int>((2 * static_cast<size_t>(slice) * 8) / (static_cast<size_t>(kwords) * 4)));
+    __shared__ int w_cursor;
+    if (tid == 0) w_cursor = cap;
+    for (int hi = S; hi > 0; hi -= chunk) {
+        const int lo_s = max(0, hi - chunk);
+        __syncthreads();
+        const size_t n_words = static_cast<size_t>(hi - lo_s) * kwords;
+        const uint32_t* src = keep + static_cast<size_t>(lo_s) * kwords;
+#pragma unroll 8
+        for (size_t i = tid; i < n_words; i += NT) stage[i] = __ldcg(src + i);   // written by other SMs: read through L2
+        __syncthreads();
+        if (tid == 0) {
+            int w = w_cursor;
+            for (int s = hi - 1; s >= lo_s; --s) {
+                const int take = (stage[static_cast<size_t>(s - lo_s) * kwords + (w >> 5)] >> (w & 31)) & 1;
+                picks[s0 + s] = static_cast<uint8_t>(take);
+                if (take) w -= item_len[s];
+                else item_len[s] = -item_len[s];
+            }
+            w_cursor = w;
+        }
+    }
+    if (summary == nullptr) return;
+    __syncthreads();
+    uint8_t* out = summary + b.summary_start[v];
+    auto shot_of = [&](int f) {
+        int a = 0, z = S;
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (item_beg[mid] <= f) a = mid + 1; else z = mid;
+        }
+        return a - 1;
+    };
+    auto bit_at = [&](int f, int& s) -> uint32_t {
+        while (s + 1 < S && item_beg[s + 1] <= f) ++s;
+        if (s < 0) return 0u;
+        const int len = item_len[s];
+        return (len > 0 && f < item_beg[s] + len) ? 1u : 0u;
+    };
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(out);
+    const int head = min(nf, static_cast<int>((16 - (addr & 15)) & 15));
+    const int body = (nf - head) / 16;
+    for (int f = tid; f < head; f += NT) {
+        int s = shot_of(f);
+        out[f] = static_cast<uint8_t>(bit_at(f, s));
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(out + head);
+    for (int i = tid; i < body; i += NT) {
+        const int f0 = head + 16 * i;
+        int s = shot_of(f0);
+        uint32_t wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x |= bit_at(f0 + 4 * k + j, s) << (8 * j);
+            wv[k] = x;
+        }
+        o4[i] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    for (int f = head + body * 16 + tid; f < nf; f += NT) {
+        int s = shot_of(f);
+        out[f] = static_cast<uint8_t>(bit_at(f, s));
+    }
+}
+
 // ------------------------------------------------------------------- overlap F1
 __global__ void __launch_bounds__(256) temporal_f1_kernel(const int2* __restrict__ pred,
                                                           const int32_t* __restrict__ pred_start,
@@ -549,6 +772,30 @@ avs_status knapsack_select(const SummaryBatch& b, const unsigned long long* seg_
                 knapsack_fast_kernel<long long, KNAP_CPT, KNAP_THREADS, false><<<b.n, KNAP_THREADS, need, stream>>>(
                     b, scores, positions, seg_mean, picks, summary, rows, items, nullptr);
             }
+            AVS_LAUNCH_CHECK();
+            return AVS_OK;
+        }
+    }
+    // ---- long videos, few of them: a cluster of 4 CTAs per video (capacity range split, halo reads through DSMEM)
+    static const bool no_cluster = getenv("AVS_KNAPSACK_NO_CLUSTER") != nullptr;
+    if (scores != nullptr && keep_bits != nullptr && !no_cluster && b.n * KC <= device_sm_count() &&
+        b.max_cap + 1 <= KC * KC_CPT * KC_THREADS) {
+        const int slice = ((b.max_cap + KC) / KC + KC_THREADS - 1) / KC_THREADS * KC_THREADS;   // ceil((cap+1)/KC) -> x512
+        const int items = std::max(b.max_S, 1);
+        const size_t need = static_cast<size_t>(items) * 8 + 2 * static_cast<size_t>(slice) * 8 +
+                            static_cast<size_t>(items) * 8 + 16 * static_cast<size_t>(slice / 32) * 4 + 64;
+        // the keep rows are written with the long-video stride (knapsack_keep_words): all KC slices must fit in it
+        const int kwords = (b.max_cap + 4 * KNAP_BIG_THREADS) / (4 * KNAP_BIG_THREADS) * (4 * KNAP_BIG_THREADS) / 32;
+        if (need <= limit && KC * slice <= kwords * 32) {
+            static PerDeviceOnce cfg;
+            const int dev = current_device();
+            if (cfg.needed(dev)) {
+                AVS_CUDA(cudaFuncSetAttribute(knapsack_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(limit)));
+                cfg.mark(dev);
+            }
+            knapsack_cluster_kernel<<<b.n * KC, KC_THREADS, need, stream>>>(b, scores, positions, seg_mean, picks, summary,
+                                                                         slice, items, keep_bits);
             AVS_LAUNCH_CHECK();
             return AVS_OK;
         }

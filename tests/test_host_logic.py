@@ -155,3 +155,27 @@ def test_graphed_train_step_needs_cuda_and_a_capturable_optimiser():
     with pytest.raises(RuntimeError, match="CUDA"):
         training.GraphedTrainStep(lin, opt, torch.nn.functional.mse_loss, torch.zeros(1, 2, 4), torch.zeros(1, 2, 4),
                                   torch.zeros(1, 2))
+
+
+def test_bench_global_batch_spec_matches_the_synthetic_configs():
+    """bench.py generates only a rank's shard of the global batch; the (length, seed) spec every rank derives must
+    describe exactly the videos synth.config2 / config4 build (the CPU baseline and the parity check index by it)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("avs_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    one = bench.global_batch_spec(1, "infer")
+    vids = synth.config2()
+    assert [t for t, _ in one] == [v.T for v in vids] and sum(t for t, _ in one) == 21477
+    v7 = synth.make_video(*one[7][:1], 1024, 128, one[7][1])
+    assert np.array_equal(v7.cps, vids[7].cps) and bench.n_shots(*one[7]) == len(vids[7].cps)
+    two = bench.global_batch_spec(2, "infer")
+    assert two[:50] == one and len(two) == 100 and two[50][1] == 2234
+    long = bench.global_batch_spec(2, "long")
+    assert [t for t, _ in long] == [8192] * 16 and len({s for _, s in long}) == 16
+    # stage FLOP table: the pipelined stage is the sum of its parts
+    f = bench.stage_flops_per_frame("temporal", 400.0)
+    assert f["frontend_lstm_pipelined"] == f["frontend_gemms"] + f["lstm_recurrence"]
+    assert f["attention_core"] == 4 * 400.0 * 1024
