@@ -459,7 +459,14 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
     // The 8-slot kernel runs two independent chains of 4 videos per CTA; an isolated chain is faster (0.67 vs 0.76
     // us per step, tools/lstm_scaling.py).  A small batch therefore takes 4 videos per cluster -- the second chain of
     // every CTA stays empty -- as long as all clusters still get SMs of their own (16 videos -> 16 clusters).
-    const int per_cluster = (tensor_core && p.nb == 8 && B <= 16) ? 4 : p.nb;
+    // (8 videos x T = 8192, B200: 2 per cluster 4.95 ms, 4 per cluster 5.09 ms, 1 per cluster -- two CTAs per SM -- 5.18 ms)
+    int per_cluster = (tensor_core && p.nb == 8 && B <= 16) ? (B <= 8 ? 2 : 4) : p.nb;
+    if (tensor_core && p.nb == 8) {   // tuning aid: videos per cluster for small batches (1, 2, 4 or 8)
+        if (const char* e = getenv("AVS_LSTM_PER_CLUSTER")) {
+            const int want = atoi(e);
+            if ((want == 1 || want == 2 || want == 4 || want == 8) && ((B + want - 1) / want) * 4 <= 32) per_cluster = want;
+        }
+    }
     p.n_groups = (B + per_cluster - 1) / per_cluster;
     const int slots = p.n_groups * p.nb;
     p.host.assign(2 * slots + p.n_groups, 0);
