@@ -12,4 +12,6 @@ timeout 300 python bench.py --config long --steps 5 --warmup 3 --no-cpu-baseline
 timeout 300 python bench.py --config train --steps 20 --warmup 5 > $O/${P}_bench_train.json 2>> $O/${P}_bench.err
 timeout 200 python tools/bench_config3.py 2>/dev/null | tail -2 > $O/${P}_config3.log
 timeout 200 python tools/lstm_trace.py > $O/${P}_lstm_trace.log 2>&1
+timeout 100 python tools/prof_knapsack_long.py 8 8192 5 > $O/${P}_knapsack_long.log 2>&1
+(timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2) > $O/${P}_smoke.log
 tail -3 $O/${P}_pytest.log; cut -c1-400 $O/${P}_bench.json; tail -5 $O/${P}_bench.err; cut -c1-300 $O/${P}_bench_long.json; cut -c1-300 $O/${P}_bench_train.json; cat $O/${P}_config3.log
