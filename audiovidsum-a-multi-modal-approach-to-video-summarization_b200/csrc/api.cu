@@ -1323,6 +1323,24 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         }
     }
 
+    // ---- optional range check (AVS_CHECK_RANGE=1): the default mode keeps the activations behind the fc layers in
+    // fp16, whose casts SATURATE at 65504 instead of overflowing -- silent for un-normalised features with huge
+    // magnitudes.  With the switch on, a saturated / non-finite embedding fails the call loudly (one extra pass over
+    // 2 KB per frame and a synchronisation: a validation aid, not the default).
+    const bool check_range = getenv("AVS_CHECK_RANGE") != nullptr;
+    if (check_range && act == DT_F16) {
+        unsigned int* cnt = reinterpret_cast<unsigned int*>(seq_dev);   // reuses the (not yet written) descriptor slot
+        unsigned int host_cnt = 0;
+        AVS_CUDA(cudaMemsetAsync(cnt, 0, 4, st));
+        AVS_TRY(count_saturated_f16(v_emb, R * H, cnt, st));
+        AVS_TRY(count_saturated_f16(a_emb, R * H, cnt, st));
+        AVS_CUDA(cudaMemcpyAsync(&host_cnt, cnt, 4, cudaMemcpyDeviceToHost, st));
+        AVS_CUDA(cudaStreamSynchronize(st));
+        AVS_CHECK(host_cnt == 0, AVS_ERR_UNSUPPORTED,
+                  "%u fc activations saturate fp16 (|x| >= 65504) or are not finite: normalise the features or use "
+                  "AVS_PREC_BF16 (fp32 exponent range)", host_cnt);
+    }
+
     // ---- K2b: recurrences; writes [v_fwd | v_bwd | a_fwd | a_bwd] = torch.cat of av_model.py:43
     if (!pipelined) {
         const int slots = plan.n_groups * plan.nb;
@@ -1531,6 +1549,8 @@ static avs_status summarize_prepare(avs_model* m, Arena& A, int32_t n_videos, co
     sb.max_cap = max_cap;
     sb.max_S = 0;
     for (int v = 0; v < n; ++v) sb.max_S = std::max(sb.max_S, cps_start[v + 1] - cps_start[v]);
+    sb.max_wt = 0;
+    for (int i = 0; i < total_S; ++i) sb.max_wt = std::max(sb.max_wt, cps[2 * i + 1] - cps[2 * i] + 1);
     // K7 + K8 in one launch when every video's shots fit in shared memory (always, for TVSum/SumMe-sized inputs)
     P->fuse_pool = knapsack_can_fuse_pool(sb);
     P->total_S = total_S;

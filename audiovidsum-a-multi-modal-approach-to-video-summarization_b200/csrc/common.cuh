@@ -115,6 +115,8 @@ avs_status gemm_simt(const float* A, int64_t lda, const float* W, int64_t ldw, i
 // ---- elementwise helpers -----------------------------------------------------
 // dst = tf32_rn(src) (fp32 container) or bf16/f16 cast; n elements.
 avs_status convert_f32(const float* src, void* dst, int64_t n, int dst_dtype, int round_tf32, cudaStream_t stream);
+// *count_dev += number of fp16 elements that are saturated (|x| = 65504), infinite or NaN (AVS_CHECK_RANGE=1)
+avs_status count_saturated_f16(const void* x, int64_t n, unsigned int* count_dev, cudaStream_t stream);
 
 // ---- LSTM recurrence -----------------------------------------------------------
 struct LstmBatch {            // device arrays, one entry per slot (n_groups * NB slots)
@@ -186,6 +188,7 @@ struct SummaryBatch {   // device arrays, [n] unless noted
     int prop_num, prop_den;
     int max_cap;                 // max capacity over the batch
     int max_S;                   // max number of shots of one video
+    int max_wt = 0;              // longest shot (frames) of the batch
 };
 avs_status shot_pool(const float* scores, const int32_t* positions, const SummaryBatch& b, unsigned long long* seg_sum,
                      cudaStream_t stream);

@@ -112,6 +112,23 @@ avs_status gemm_simt(const float* A, int64_t lda, const float* W, int64_t ldw, i
     return AVS_OK;
 }
 
+// Range check of fp16 activations (AVS_CHECK_RANGE=1): counts the elements whose magnitude is at the saturation value
+// of the fp32 -> fp16 casts (65504) or that are not finite.
+__global__ void count_saturated_f16_kernel(const uint16_t* __restrict__ x, int64_t n, unsigned int* __restrict__ count) {
+    unsigned int local = 0;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        local += ((x[i] & 0x7FFFu) >= 0x7BFFu) ? 1u : 0u;   // |x| == 65504, inf or NaN
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+avs_status count_saturated_f16(const void* x, int64_t n, unsigned int* count_dev, cudaStream_t stream) {
+    if (n == 0) return AVS_OK;
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    count_saturated_f16_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(x), n, count_dev);
+    AVS_LAUNCH_CHECK();
+    return AVS_OK;
+}
+
 avs_status convert_f32(const float* src, void* dst, int64_t n, int dst_dtype, int round_tf32, cudaStream_t stream) {
     if (n == 0) return AVS_OK;
     AVS_CHECK(n % 4 == 0, AVS_ERR_INVALID, "convert: element count must be a multiple of 4");

@@ -247,6 +247,25 @@ def test_padded_batch_rows_are_packed_before_the_gemms(cuda_ready):
             assert torch.equal(alone.cpu(), ref[b, :n])
 
 
+def test_range_check_flags_saturating_features(cuda_ready):
+    """AVS_CHECK_RANGE=1: the fp16 activations of the default mode saturate at 65504 instead of overflowing; with the
+    switch on, features large enough to saturate the fc outputs fail the call loudly (and bf16, with its fp32
+    exponent range, still scores them), normal features pass unchanged."""
+    vid = synth.config1()
+    m = make_model(spread=True)
+    want = m(vid.visual[None].cuda(), vid.audio[None].cuda())
+    os.environ["AVS_CHECK_RANGE"] = "1"
+    try:
+        got = m(vid.visual[None].cuda(), vid.audio[None].cuda())
+        assert torch.equal(got, want)
+        with pytest.raises(_cabi.AvsUnsupported, match="saturate"):
+            m((vid.visual[None] * 3e6).cuda(), vid.audio[None].cuda())
+        mb = make_model(spread=True, precision="bf16")
+        assert bool(torch.isfinite(mb((vid.visual[None] * 3e6).cuda(), vid.audio[None].cuda())).all())
+    finally:
+        os.environ.pop("AVS_CHECK_RANGE", None)
+
+
 def test_training_forward_equals_eval_forward(cuda_ready):
     """One operand policy on both paths: the autograd forward (avs_linear per layer) and the inference forward
     (avs_forward) of the same weights agree to the tolerance of their operand formats (fp32 vs fp16 activations
