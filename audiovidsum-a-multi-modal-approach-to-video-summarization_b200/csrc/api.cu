@@ -1082,6 +1082,13 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     const size_t fsz = f16_in ? 2 : 4;
     const int in_dt = bf16 ? DT_BF16 : (f16_in ? DT_F16 : DT_F32);   // what the fc GEMMs read
     const size_t asz = dtype_size(act);
+    // gate pre-activations (input projections of the four recurrences): fp16 on the tensor-core paths -- the largest
+    // HBM item of the step (2 x 2048 values per frame, written by two GEMMs and read back by the recurrence), halved;
+    // fp16 in the bf16 mode too (pre-activations need the significand, and beyond +-65504 every gate is saturated
+    // anyway: the cast clamps).  AVS_XG_F32=1 keeps fp32 (A/B aid).
+    static const bool xg_f32 = getenv("AVS_XG_F32") != nullptr;
+    const int xg_dt = (simt || xg_f32) ? DT_F32 : DT_F16;
+    const size_t xsz = dtype_size(xg_dt);
 
     bool literal_rows = attn_axis == AVS_ATTN_LITERAL_B1 || (attn_axis == AVS_ATTN_LITERAL && n_videos == 1);
     if (attn_axis == AVS_ATTN_LITERAL && n_videos > 1) {
@@ -1097,7 +1104,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     const bool tc_attn = !simt && attn_axis == AVS_ATTN_TEMPORAL && E == m->heads * 256;
     const int qkv_dt = tc_attn ? act : DT_F32;
     const size_t uR = static_cast<size_t>(R);
-    const size_t bytes = uR * (Dv + Da) * fsz + (bf16 ? uR * (Dv + Da) * 2 : 0) + 2 * uR * H * asz + 2 * uR * 2 * G4 * 4 +
+    const size_t bytes = uR * (Dv + Da) * fsz + (bf16 ? uR * (Dv + Da) * 2 : 0) + 2 * uR * H * asz + 2 * uR * 2 * G4 * xsz +
                          3 * uR * E * asz + (literal_rows ? 0 : uR * 3 * E * dtype_size(qkv_dt)) + uR * 4 +
                          (plan.host.size() + 3 * static_cast<size_t>(n_seqs)) * 4 + 64 * 256;
     AVS_TRY(WS.reserve(bytes));
@@ -1108,8 +1115,8 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     uint16_t* in_a16 = bf16 ? WS.take<uint16_t>(uR * Da) : nullptr;
     char* v_emb = WS.take<char>(uR * H * asz);
     char* a_emb = WS.take<char>(uR * H * asz);
-    float* xg_v = WS.take<float>(uR * 2 * G4);
-    float* xg_a = WS.take<float>(uR * 2 * G4);
+    char* xg_v = WS.take<char>(uR * 2 * G4 * xsz);
+    char* xg_a = WS.take<char>(uR * 2 * G4 * xsz);
     char* fused = WS.take<char>(uR * E * asz);
     char* qkv = literal_rows ? nullptr : WS.take<char>(uR * 3 * E * dtype_size(qkv_dt));
     char* ctx = WS.take<char>(uR * E * asz);
@@ -1181,6 +1188,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 if (!bf16 && !f16_in) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
                 GemmEpilogue e2;
                 e2.ldc = 2 * G4;
+                e2.out_dtype = xg_dt;
                 e1.max_ctas = e2.max_ctas = busy ? std::max(sms - busy, 16) : 0;
                 const void* xv = feat_at(visual, r0, Dv, fsz);
                 const void* xa = feat_at(audio, r0, Da, fsz);
@@ -1201,10 +1209,10 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 e1.C = a_emb + r0 * H * asz;
                 AVS_TRY(run_gemm(precision, xa, in_dt, Da, w_fc_a, 0, Da, Rc, H, Da, e1, sa));
                 e2.bias = m->ih_v_b;
-                e2.C = xg_v + r0 * 2 * G4;
+                e2.C = xg_v + r0 * 2 * G4 * xsz;
                 AVS_TRY(run_gemm(precision, v_emb + r0 * H * asz, act, H, w_ih_v, 0, H, Rc, 2 * G4, H, e2, st));
                 e2.bias = m->ih_a_b;
-                e2.C = xg_a + r0 * 2 * G4;
+                e2.C = xg_a + r0 * 2 * G4 * xsz;
                 AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, sa));
                 AVS_CUDA(cudaEventRecord(m->ev_branch_out[0], sa));
                 AVS_CUDA(cudaStreamWaitEvent(st, m->ev_branch_out[0], 0));
@@ -1213,7 +1221,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 // ONE launch per segment (kernels on one stream would run one after the other); only single-group
                 // segments can be exclusive
                 const int excl = (g_hi - g_lo == 1 && g_lo < n_excl) ? 1 : 0;
-                AVS_TRY(lstm_recurrence_tc_groups(xg_v, xg_a, m->whh, lb, g_lo, g_hi, excl, act, fused, act, m->pipe_stream[k]));
+                AVS_TRY(lstm_recurrence_tc_groups(xg_v, xg_a, xg_dt, m->whh, lb, g_lo, g_hi, excl, act, fused, act, m->pipe_stream[k]));
                 busy += (g_hi - g_lo) * (excl ? 32 : 16);
                 AVS_CUDA(cudaEventRecord(m->ev_pipe_done[k], m->pipe_stream[k]));
             }
@@ -1281,6 +1289,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         if (!simt && !bf16 && !f16_in) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
         GemmEpilogue e2;
         e2.ldc = 2 * G4;
+        e2.out_dtype = xg_dt;
         if (sa != st) {
             // concurrent kernels: per-kernel event pairs would count the overlap twice, so the four GEMMs are
             // timed as ONE stage ("frontend_gemms": fork -> join on st)
@@ -1294,10 +1303,10 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
             e1.C = a_emb + r0 * H * asz;
             AVS_TRY(run_gemm(precision, xa, in_dt, Da, w_fc_a, 0, Da, Rc, H, Da, e1, sa));
             e2.bias = m->ih_v_b;
-            e2.C = xg_v + r0 * 2 * G4;
+            e2.C = xg_v + r0 * 2 * G4 * xsz;
             AVS_TRY(run_gemm(precision, v_emb + r0 * H * asz, act, H, w_ih_v, 0, H, Rc, 2 * G4, H, e2, st));
             e2.bias = m->ih_a_b;
-            e2.C = xg_a + r0 * 2 * G4;
+            e2.C = xg_a + r0 * 2 * G4 * xsz;
             AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, sa));
             AVS_CUDA(cudaEventRecord(m->ev_branch_out[gidx], sa));
             AVS_CUDA(cudaStreamWaitEvent(st, m->ev_branch_out[gidx], 0));
@@ -1314,10 +1323,10 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
             {
                 StageTimer tm(ST_IH_PROJ, st);
                 e2.bias = m->ih_v_b;
-                e2.C = xg_v + r0 * 2 * G4;
+                e2.C = xg_v + r0 * 2 * G4 * xsz;
                 AVS_TRY(run_gemm(precision, v_emb + r0 * H * asz, act, H, w_ih_v, 0, H, Rc, 2 * G4, H, e2, st));
                 e2.bias = m->ih_a_b;
-                e2.C = xg_a + r0 * 2 * G4;
+                e2.C = xg_a + r0 * 2 * G4 * xsz;
                 AVS_TRY(run_gemm(precision, a_emb + r0 * H * asz, act, H, w_ih_a, 0, H, Rc, 2 * G4, H, e2, st));
             }
         }
@@ -1350,8 +1359,10 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         if (covered < R)  // padded layout: rows no video owns must stay finite (0 * NaN would poison P*V)
             AVS_CUDA(cudaMemsetAsync(fused, 0, uR * E * asz, st));
         StageTimer tm(ST_LSTM, st);
-        if (simt) AVS_TRY(lstm_recurrence(xg_v, xg_a, m->whh, lb, reinterpret_cast<float*>(fused), 0, nullptr, 0, st));
-        else AVS_TRY(lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, act, fused, act, 0, st));
+        if (simt)
+            AVS_TRY(lstm_recurrence(reinterpret_cast<const float*>(xg_v), reinterpret_cast<const float*>(xg_a), m->whh, lb,
+                                    reinterpret_cast<float*>(fused), 0, nullptr, 0, st));
+        else AVS_TRY(lstm_recurrence_tc(xg_v, xg_a, xg_dt, m->whh, lb, act, fused, act, 0, st));
     }
 
     // ---- K3/K4: nn.MultiheadAttention  av_model.py:44
@@ -1830,7 +1841,7 @@ static avs_status bilstm_pair_impl(avs_model* m, const float* v_emb, const float
     AVS_TRY(sa_rc);
     const int slots = plan.n_groups * plan.nb;
     LstmBatch lb{plan_dev, plan_dev + slots, plan_dev + 2 * slots, plan.n_groups, plan.nb};
-    if (!simt) return lstm_recurrence_tc(xg_v, xg_a, m->whh, lb, act, fused, DT_F32, 0, st, save_pre, save_c);
+    if (!simt) return lstm_recurrence_tc(xg_v, xg_a, DT_F32, m->whh, lb, act, fused, DT_F32, 0, st, save_pre, save_c);
     AVS_CHECK(save_pre == nullptr, AVS_ERR_UNSUPPORTED, "the training forward needs a tensor-core precision");
     return lstm_recurrence(xg_v, xg_a, m->whh, lb, fused, 0, nullptr, 0, st);
 }

@@ -139,16 +139,17 @@ avs_status lstm_recurrence(const float* xg_v, const float* xg_a, const float* wh
 // 8 (two CTAs per SM), 16, 32 or 64.  fused output: fp32 (optionally tf32-rounded), fp16 or bf16 (out_dtype).
 // save_pre (float4 [rows, 4, 256]: i, f, g, o pre-activations) / save_c (float [rows, 4, 256]: new cell state) are
 // written when non-null (training forward; consumed by lstm_backward).
-avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
-                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream,
-                              void* save_pre = nullptr, float* save_c = nullptr);
+// xg_dtype: DT_F32 or DT_F16 (the element type of xg_v / xg_a; the inference path keeps them in fp16).
+avs_status lstm_recurrence_tc(const void* xg_v, const void* xg_a, int xg_dtype, const float* whh_packed,
+                              const LstmBatch& batch, int op_dtype, void* fused, int out_dtype, int round_tf32,
+                              cudaStream_t stream, void* save_pre = nullptr, float* save_c = nullptr);
 // The 8-slot variant (batch.nb == 8) for groups [g_lo, g_hi) only, on `stream`, with (exclusive != 0) or without an
 // SM-exclusive shared-memory request: the pipelined forward launches the groups one by one as their input
 // projections become available.  lstm_exclusive_groups: how many leading groups the one-launch policy would give
 // exclusive SMs for this group count.
-avs_status lstm_recurrence_tc_groups(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
-                                     int g_lo, int g_hi, int exclusive, int op_dtype, void* fused, int out_dtype,
-                                     cudaStream_t stream);
+avs_status lstm_recurrence_tc_groups(const void* xg_v, const void* xg_a, int xg_dtype, const float* whh_packed,
+                                     const LstmBatch& batch, int g_lo, int g_hi, int exclusive, int op_dtype, void* fused,
+                                     int out_dtype, cudaStream_t stream);
 int lstm_exclusive_groups(int n_groups);
 
 // BPTT through the four recurrences (CUDA-core fp32, cluster of 8 CTAs, DSMEM reduce-scatter of dh):

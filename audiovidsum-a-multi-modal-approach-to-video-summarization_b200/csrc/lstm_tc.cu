@@ -158,9 +158,24 @@ __device__ __forceinline__ long long clk64() {
     return t;
 }
 
-template <int NB, int PARTS, int CHAINS, bool TRACE>
+// The input projection of one (frame, hidden unit): the four gate pre-activations, fp32 (float4) or fp16 (uint2).
+// Inference keeps them in fp16 -- half of the largest HBM item of the step (2 x 2048 values per frame written by the
+// input-projection GEMMs and read back here); the rounding (2^-12 relative on a pre-activation) is the same size as
+// that of the fp16 h operand of the recurrent product.  The training forward keeps fp32.
+template <bool XG16> struct XgVec { using type = float4; };
+template <> struct XgVec<true> { using type = uint2; };
+__device__ __forceinline__ float4 xg_f4(const float4& v) { return v; }
+__device__ __forceinline__ float4 xg_f4(const uint2& v) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void xg_zero(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void xg_zero(uint2& v) { v = make_uint2(0u, 0u); }
+
+template <int NB, int PARTS, int CHAINS, bool TRACE, bool XG16>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PARTS * 128 + CHAINS * 32, PARTS == 2 ? 2 : 1)
-lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, const float* __restrict__ whh,
+lstm_tc_kernel(const void* __restrict__ xg_v, const void* __restrict__ xg_a, const float* __restrict__ whh,
                LstmBatch batch, int op_dtype, void* __restrict__ fused_out, int out_dtype, int round_tf32,
                float4* __restrict__ save_pre, float* __restrict__ save_c, int grp_off) {
     static_assert(CHAINS == 1 || CHAINS == PARTS, "a chain is either the whole CTA or one part");
@@ -314,7 +329,8 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         const int jj = q * 8 + (lane >> 2);  // hidden unit inside the CTA's slice
         const int v0 = part * NV;                        // first video slot of this part (index into s_len / s_row)
         const int lv0 = CHAINS == 1 ? v0 : 0;            // the same, relative to this chain's buffers / accumulator
-        const float4* xg4 = reinterpret_cast<const float4*>(((ld >> 1) ? xg_a : xg_v) + dir * (4 * HC) + r * COLS + 4 * jj);
+        using XgT = typename XgVec<XG16>::type;   // four gates of one hidden unit: 16 bytes (fp32) or 8 (fp16)
+        const XgT* xg4 = reinterpret_cast<const XgT*>((ld >> 1) ? xg_a : xg_v) + (dir * (4 * HC) + r * COLS + 4 * jj) / 4;
         constexpr int XG_LD4 = XG_LD / 4;
         const int out_col = ld * HC + r * UNITS;
         const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + lv0;
@@ -336,9 +352,10 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
         const uint32_t remote_bar = mapa(smem_u32(bar_h), peer);
 
         float c_state[NP];
-        float4 xv0[NP], xv1[NP];               // xv0: this step's input projection, xv1: next step's
+        XgT xv0[NP], xv1[NP];                  // xv0: this step's input projection, xv1: next step's
         int len_r[NP], row_r[NP], vid_r[NP];   // row_r: global row of the frame consumed at step s
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        XgT zero4;
+        xg_zero(zero4);
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             c_state[k] = 0.f;
@@ -352,7 +369,7 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
 
         for (int s = 0; s < maxlen; ++s) {
             // two-step-deep register prefetch of the input projections (DRAM latency >> one step)
-            float4 xv2[NP];
+            XgT xv2[NP];
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 xv2[k] = zero4;
@@ -374,10 +391,11 @@ lstm_tc_kernel(const float* __restrict__ xg_v, const float* __restrict__ xg_a, c
             float h_out[NP];
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                const float t_i = gi[k] + xv0[k].x;
-                const float t_f = gf[k] + xv0[k].y;
-                const float t_g = gg[k] + xv0[k].z;
-                const float t_o = go[k] + xv0[k].w;
+                const float4 xin = xg_f4(xv0[k]);
+                const float t_i = gi[k] + xin.x;
+                const float t_f = gf[k] + xin.y;
+                const float t_g = gg[k] + xin.z;
+                const float t_o = go[k] + xin.w;
                 // ---- LSTM cell on the SFU with shared denominators (5 ex2 + 2 rcp per cell):
                 //   sigmoid(x) = 1 / (1 + e^-x),  tanh(x) = (1 - e^-2x) / (1 + e^-2x)
                 //   c' = sig(f) c + sig(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ei)(1+eg)(1+ef)]
@@ -488,8 +506,8 @@ SplitCtx& split_ctx() {
     return c;
 }
 
-template <int NB, int PARTS, int CHAINS>
-avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, const LstmBatch& batch_in, int op_dtype,
+template <int NB, int PARTS, int CHAINS, bool XG16>
+avs_status launch_tc(const void* xg_v, const void* xg_a, const float* whh, const LstmBatch& batch_in, int op_dtype,
                      void* fused, int out_dtype, int round_tf32, float4* save_pre, float* save_c, cudaStream_t stream) {
     static const bool trace = getenv("AVS_LSTM_TRACE") != nullptr;
     static const bool no_split = getenv("AVS_LSTM_NO_SPLIT") != nullptr;
@@ -497,7 +515,7 @@ avs_status launch_tc(const float* xg_v, const float* xg_a, const float* whh, con
     batch.lane_map = 1;   // adjacent lanes address adjacent 16-byte chunks of ONE peer (measured: an isolated chain
                           // takes 0.67 instead of 0.71 us per step; no difference once chains share an SM)
     if (const char* e = getenv("AVS_LSTM_LANEMAP")) batch.lane_map = atoi(e);
-    auto kern = trace ? lstm_tc_kernel<NB, PARTS, CHAINS, NB == 16> : lstm_tc_kernel<NB, PARTS, CHAINS, false>;
+    auto kern = trace ? lstm_tc_kernel<NB, PARTS, CHAINS, NB == 16, XG16> : lstm_tc_kernel<NB, PARTS, CHAINS, false, XG16>;
     constexpr int SMEM = Smem<NB, CHAINS>::TOTAL;
     constexpr int SMEM_EXCLUSIVE = 200 * 1024;   // more than half an SM: no second CTA of either launch fits beside it
     static PerDeviceOnce configured;
@@ -549,22 +567,23 @@ int lstm_exclusive_groups(int n_groups) {
     return (n_groups >= 0 && n_groups <= 7) ? kExclusive[n_groups] : 0;
 }
 
-avs_status lstm_recurrence_tc_groups(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch_in,
-                                     int g_lo, int g_hi, int exclusive, int op_dtype, void* fused, int out_dtype,
-                                     cudaStream_t stream) {
+avs_status lstm_recurrence_tc_groups(const void* xg_v, const void* xg_a, int xg_dtype, const float* whh_packed,
+                                     const LstmBatch& batch_in, int g_lo, int g_hi, int exclusive, int op_dtype, void* fused,
+                                     int out_dtype, cudaStream_t stream) {
+    AVS_CHECK(xg_dtype == DT_F32 || xg_dtype == DT_F16, AVS_ERR_INVALID, "lstm_tc: input projections must be fp32 or fp16");
     AVS_CHECK(batch_in.nb == 8 && g_lo >= 0 && g_lo < g_hi && g_hi <= batch_in.n_groups, AVS_ERR_INVALID,
               "lstm_recurrence_tc_groups: bad group range [%d, %d) of %d (8-slot variant only)", g_lo, g_hi, batch_in.n_groups);
     AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
     LstmBatch batch = batch_in;
     batch.lane_map = 1;
-    auto kern = lstm_tc_kernel<16, 2, 2, false>;
+    auto kern = xg_dtype == DT_F16 ? lstm_tc_kernel<16, 2, 2, false, true> : lstm_tc_kernel<16, 2, 2, false, false>;
     constexpr int SMEM = Smem<16, 2>::TOTAL;
     constexpr int SMEM_EXCLUSIVE = 200 * 1024;
-    static PerDeviceOnce configured;
+    static PerDeviceOnce configured[2];
     const int dev = current_device();
-    if (configured.needed(dev)) {
+    if (configured[xg_dtype == DT_F16].needed(dev)) {
         AVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_EXCLUSIVE));
-        configured.mark(dev);
+        configured[xg_dtype == DT_F16].mark(dev);
     }
     kern<<<(g_hi - g_lo) * 4 * CL, 2 * 128 + 2 * 32, exclusive ? SMEM_EXCLUSIVE : SMEM, stream>>>(
         xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, 0, nullptr, nullptr, g_lo);
@@ -579,26 +598,39 @@ avs_status lstm_trace_read(unsigned long long* out8) {
     return AVS_OK;
 }
 
-avs_status lstm_recurrence_tc(const float* xg_v, const float* xg_a, const float* whh_packed, const LstmBatch& batch,
-                              int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream,
-                              void* save_pre, float* save_c) {
-    if (batch.n_groups == 0) return AVS_OK;
-    AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
+template <bool XG16>
+static avs_status recurrence_tc_dispatch(const void* xg_v, const void* xg_a, const float* whh_packed, const LstmBatch& batch,
+                                         int op_dtype, void* fused, int out_dtype, int round_tf32, cudaStream_t stream,
+                                         void* save_pre, float* save_c) {
+    float4* const pre = static_cast<float4*>(save_pre);
     switch (batch.nb) {   // video slots per cluster
         case 8:
             if (getenv("AVS_LSTM_ONE_CHAIN") != nullptr)   // experiment: 8 videos in ONE chain per CTA
-                return launch_tc<16, 2, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
-                                           static_cast<float4*>(save_pre), save_c, stream);
-            return launch_tc<16, 2, 2>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
-                                       static_cast<float4*>(save_pre), save_c, stream);
-        case 16: return launch_tc<16, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
-                                                static_cast<float4*>(save_pre), save_c, stream);
-        case 32: return launch_tc<32, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
-                                                static_cast<float4*>(save_pre), save_c, stream);
-        case 64: return launch_tc<64, 4, 1>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32,
-                                                static_cast<float4*>(save_pre), save_c, stream);
+                return launch_tc<16, 2, 1, XG16>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, pre,
+                                                 save_c, stream);
+            return launch_tc<16, 2, 2, XG16>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, pre,
+                                             save_c, stream);
+        case 16: return launch_tc<16, 4, 1, XG16>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, pre,
+                                                  save_c, stream);
+        case 32: return launch_tc<32, 4, 1, XG16>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, pre,
+                                                  save_c, stream);
+        case 64: return launch_tc<64, 4, 1, XG16>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, pre,
+                                                  save_c, stream);
         default: set_error("lstm_tc: unsupported videos-per-cluster %d", batch.nb); return AVS_ERR_INVALID;
     }
+}
+
+avs_status lstm_recurrence_tc(const void* xg_v, const void* xg_a, int xg_dtype, const float* whh_packed,
+                              const LstmBatch& batch, int op_dtype, void* fused, int out_dtype, int round_tf32,
+                              cudaStream_t stream, void* save_pre, float* save_c) {
+    if (batch.n_groups == 0) return AVS_OK;
+    AVS_CHECK(op_dtype == DT_F16 || op_dtype == DT_BF16, AVS_ERR_INVALID, "lstm_tc: operand dtype must be fp16 or bf16");
+    AVS_CHECK(xg_dtype == DT_F32 || xg_dtype == DT_F16, AVS_ERR_INVALID, "lstm_tc: input projections must be fp32 or fp16");
+    if (xg_dtype == DT_F16)
+        return recurrence_tc_dispatch<true>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream,
+                                            save_pre, save_c);
+    return recurrence_tc_dispatch<false>(xg_v, xg_a, whh_packed, batch, op_dtype, fused, out_dtype, round_tf32, stream,
+                                         save_pre, save_c);
 }
 
 }  // namespace avs
