@@ -543,6 +543,15 @@ avs_status avs_debug_lstm_trace(uint64_t* out8) {
     return lstm_trace_read(reinterpret_cast<unsigned long long*>(out8));
 }
 
+/* Debugging aid: with AVS_BPTT_TRACE=1 the tensor-core BPTT kernel accumulates clock64 deltas of its per-step chain on
+ * cluster 0 / CTA 0: [0] partials landed -> B operand staged, [1] 32 MMAs + commit issued, [2] -> epilogue awake,
+ * [3] tcgen05.ld, [4] shuffles + st.async issue, [6] partials sent -> next partials landed,
+ * [7] partials sent -> dh-independent math of the next step done, [8] steps. */
+avs_status avs_debug_bptt_trace(uint64_t* out10) {
+    AVS_CHECK(out10 != nullptr, AVS_ERR_INVALID, "null pointer");
+    return bptt_trace_read(reinterpret_cast<unsigned long long*>(out10));
+}
+
 /* Debugging aid: clock64 totals of the tensor-core GEMM pipeline on block 0 since the last read (AVS_GEMM_TRACE=1):
  * [0] MMA thread span, [1] MMA waiting for operands, [2] MMA waiting for a drained accumulator, [3] producer waiting
  * for a free stage, [4] epilogue warp waiting for an accumulator, [5] epilogue span, [6] tiles. */
@@ -1981,12 +1990,19 @@ avs_status avs_bilstm_pair_bwd(avs_model* m, const float* d_fused, const float* 
         if (lengths[b] > 0) order.push_back(b);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lengths[a] > lengths[b]; });
     const int B = static_cast<int>(order.size());
-    // Videos per cluster: as few as still fit the batch into ONE wave of clusters (4 recurrences x 8 CTAs per group,
-    // one CTA per SM: at most 4 groups on 148 SMs).  A CTA's work per step grows with its videos (128 FMAs per
-    // thread and video), so 8 videos as 4 groups of 2 on 128 SMs undo a step ~3x faster than 1 group of 8 on 32.
+    // Videos per cluster: as few as still fit the batch into ONE wave of clusters.  A group is 4 recurrences x 8 CTAs
+    // with one CTA per SM (the kernel keeps its W_hh^T slice in 256 of the SM's 512 tensor-memory columns), and
+    // clusters are placed inside one GPC: 12 such clusters are resident at once on B200, 16 are not (measured: with
+    // 8 videos as 4 groups of 2 the kernel took two waves, 580 us instead of 300) -- so at most 3 groups.  The
+    // exchange of a step is bound by the number of st.async messages an SM receives (64 per video of the
+    // cluster), which is why fewer videos per cluster are preferred when they fit.
     int nb = 8;
     for (int c : {1, 2, 4, 8})
-        if ((B + c - 1) / c <= 4) { nb = c; break; }
+        if ((B + c - 1) / c <= 3) { nb = c; break; }
+    if (const char* e = getenv("AVS_BPTT_NB")) {   // experiment switch
+        const int c = atoi(e);
+        if (c == 1 || c == 2 || c == 4 || c == 8) nb = c;
+    }
     const int n_groups = (B + nb - 1) / nb;
     const int slots = n_groups * nb;
     std::vector<int32_t> plan(2 * slots + n_groups + 2 * static_cast<size_t>(n_videos), 0);

@@ -158,6 +158,7 @@ avs_status lstm_backward(const float* d_fused, const void* save_pre, const float
                          const LstmBatch& batch, float* d_xg_v, float* d_xg_a, cudaStream_t stream);
 
 avs_status lstm_trace_read(unsigned long long* out8);   // AVS_LSTM_TRACE=1 debugging aid
+avs_status bptt_trace_read(unsigned long long* out10);  // AVS_BPTT_TRACE=1 debugging aid
 
 // ---- attention core -------------------------------------------------------------
 struct SeqDesc {  // device arrays [n_seqs]

@@ -75,16 +75,6 @@ struct Smem {
     static constexpr int TMEM_COLS = (W_TMEM_COLS + CHAINS * NB) <= 256 ? 256 : 512;
 };
 
-// K-major, no swizzle: start address, LBO = K-direction core-matrix stride, SBO = 8-row-group stride.
-__device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= static_cast<uint64_t>(1) << 46;  // version = 1 (Blackwell); layout_type 0 = SWIZZLE_NONE
-    return d;
-}
-
 // The four gate pre-activations of this thread's (hidden unit, video) pairs.  TMEM lane 32 q + 8 g + u holds gate g of
 // hidden unit 8 q + u; the .16x128b / .16x256b shapes give thread t (u = t / 4, c = t % 4) lanes u and u + 8 of a
 // 16-lane window -- gates (i, f) from the window at lane 32 q, gates (g, o) from the window at 32 q + 16 -- for

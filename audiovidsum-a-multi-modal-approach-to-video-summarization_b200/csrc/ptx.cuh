@@ -95,6 +95,18 @@ __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, const uin
                  "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster_addr)
                  : "memory");
 }
+// the 8-byte and 4-byte forms
+__device__ __forceinline__ void st_async_v2(uint32_t dst_cluster_addr, uint32_t a, uint32_t b, uint32_t mbar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(
+                     dst_cluster_addr),
+                 "r"(a), "r"(b), "r"(mbar_cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t dst_cluster_addr, uint32_t a, uint32_t mbar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
+                 "r"(a), "r"(mbar_cluster_addr)
+                 : "memory");
+}
 // mbarrier wait with acquire at CLUSTER scope: for consumers that read, with ordinary loads, data a peer CTA's
 // st.async delivered (pairs with the release of its complete_tx).  Costs a CCTL.IVALL per successful wait.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -166,6 +178,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
     return d;
 }
 
+// K-major, no swizzle ("interleaved"): core matrix = 8 rows x 16 bytes, contiguous (128 B); LBO = byte stride between
+// core matrices adjacent in K, SBO = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_noswz_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;  // version = 1 (Blackwell); layout_type 0 = SWIZZLE_NONE
+    return d;
+}
+
 enum : uint32_t { UMMA_FMT_F16 = 0, UMMA_FMT_BF16 = 1, UMMA_FMT_TF32 = 2 };
 
 // Instruction descriptor (upper 32 bits of CuTe's idescE): fp32 accumulate, A and B K-major.
@@ -227,6 +250,39 @@ __device__ __forceinline__ void umma_f16_ts_lohi(uint32_t tmem_d, uint32_t tmem_
         :
         : "r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// kind::tf32 with the A operand in tensor memory (lane = row, one 32-bit column per K element, K = 8 per
+// instruction) and the descriptor of B as two halves (see umma_f16_ts_lohi).
+__device__ __forceinline__ void umma_tf32_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 d;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// TMEM -> registers: this warp's 32 lanes x N consecutive 32-bit columns (N = 1, 2, 4 or 8).
+template <int N>
+__device__ __forceinline__ void tmem_ld_32xN(uint32_t taddr, uint32_t (&r)[N]) {
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8, "1, 2, 4 or 8 columns");
+    if constexpr (N == 1) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
+    } else if constexpr (N == 2) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+    } else if constexpr (N == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr) : "memory");
+    }
 }
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

@@ -261,6 +261,10 @@ void avs_profile_read(double* ms, int64_t* calls);
  * (h landed -> MMAs issued -> epilogue awake -> tcgen05.ld -> cell math -> fence+barrier -> copies issued ->
  * next h landed), out8[7] = number of steps. */
 avs_status avs_debug_lstm_trace(uint64_t* out8);
+/* The same for the tensor-core BPTT kernel of the training step (AVS_BPTT_TRACE): out10[0..4] = partials landed ->
+ * B operand staged -> MMAs issued -> epilogue awake -> tcgen05.ld -> st.async issued, [6] = partials sent -> next
+ * partials landed, [7] = partials sent -> next step's dh-independent math done, out10[8] = number of steps. */
+avs_status avs_debug_bptt_trace(uint64_t* out10);
 
 /* Page-locked host buffers for the host-space entry points (the features a loader packs).  write_combined != 0:
  * write-combined pages -- the CPU should only write them; device reads across PCIe then do not snoop CPU caches. */

@@ -21,7 +21,7 @@ def main():
     model = AVBiLSTMModel(1024, 128, 512, attn_axis="literal_b1")
     model.load_state_dict(synth.seeded_state_dict())
     model = model.cuda().train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True, fused=True)   # as bench.py --config train
     for _ in range(n):
         opt.zero_grad(set_to_none=True)
         loss = torch.nn.functional.mse_loss(model(visual, audio), target)
