@@ -679,7 +679,10 @@ def test_linear_backward_matches_autograd(cuda_ready, shape):
     assert _grad_err(xc.grad, x.grad) < 3e-3 and _grad_err(wc.grad, w.grad) < 3e-3 and _grad_err(bc.grad, b.grad) < 1e-5
 
 
-@pytest.mark.parametrize("lens", [[37], [5, 64, 1, 33], [20] * 11])
+# videos per cluster of the tcgen05 BPTT kernel: 1 ([37]), 2 (four ragged videos), 4 (11 videos, 3 groups; 8 x 320 = the
+# config-5 shape), 8 (13 ragged videos: the second group has empty slots)
+@pytest.mark.parametrize("lens", [[37], [5, 64, 1, 33], [20] * 11, [50, 3, 41, 17, 29, 8, 33, 21, 12, 45, 6, 38, 27],
+                                  [320] * 8])
 def test_bilstm_pair_backward_matches_torch_lstm(native, lens):
     """BPTT kernel + GEMMs vs torch.nn.LSTM autograd on the CPU (fp32): d_emb, dW_ih, dW_hh, db per recurrence."""
     from avsum_b200 import training
@@ -707,14 +710,23 @@ def test_bilstm_pair_backward_matches_torch_lstm(native, lens):
     fused = training.bilstm_pair(vc, ac, native, starts, lens, weights)
     assert float((fused.cpu() - torch.cat(outs).detach()).abs().max()) < 3e-3
     fused.backward(dfused.cuda())
-    assert _grad_err(vc.grad, v.grad) < 1e-2 and _grad_err(ac.grad, a.grad) < 1e-2
+    assert _grad_err(vc.grad, v.grad) < 2e-3 and _grad_err(ac.grad, a.grad) < 2e-3   # measured 3.5e-4 .. 4.7e-4
     i = 0
+    worst = 0.0
     for mod in (lv, la):
         for suf in ("", "_reverse"):
             for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
                 want = getattr(mod, f"{n}_l0{suf}").grad
-                assert _grad_err(weights[i].grad, want) < 1e-2, (n, suf, _grad_err(weights[i].grad, want))
+                assert _grad_err(weights[i].grad, want) < 2e-3, (n, suf, _grad_err(weights[i].grad, want))   # measured <= 6.7e-4
+                worst = max(worst, _grad_err(weights[i].grad, want))
                 i += 1
+    print(f"bptt parity lens={lens[:4]}..x{len(lens)}: d_emb {_grad_err(vc.grad, v.grad):.2e} / "
+          f"{_grad_err(ac.grad, a.grad):.2e}, worst weight gradient {worst:.2e} (max-norm relative)")
+    # the reduce-scatter of the partial dh adds the eight partials in a fixed order: a second pass gives the same bits
+    first = vc.grad.clone()
+    vc.grad = None
+    training.bilstm_pair(vc, ac, native, starts, lens, weights).backward(dfused.cuda())
+    assert torch.equal(vc.grad, first)
 
 
 def test_training_step_matches_reference_autograd(cuda_ready):

@@ -1,7 +1,7 @@
 """Per-kernel GPU times of the eager training step (config 5 shape) from the CUPTI activity records that
 torch.profiler collects: kernels keep running concurrently on their streams (unlike an ncu launch list, which
 serialises them), so the numbers add up to more than the step where side streams overlap.
-    python tools/train_kernel_times.py [n_steps]"""
+    python tools/train_kernel_times.py [n_steps [chrome_trace.json]]"""
 import os
 import sys
 
@@ -40,6 +40,8 @@ def main():
         for _ in range(n):
             step()
         torch.cuda.synchronize()
+    if len(sys.argv) > 2:   # chrome trace of the profiled steps (timeline of the streams)
+        prof.export_chrome_trace(sys.argv[2])
     rows = []
     for e in prof.key_averages():
         t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
