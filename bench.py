@@ -388,7 +388,8 @@ def attention_probe(model_sd, dev, peaks, world, dist, n_videos=8, T=8192, steps
             "frac_of_burst_bf16_peak": tf / peaks["tflops_burst"], "algorithmic_flop": flops,
             "full_forward_ms": fwd_ms, "full_forward_frames_per_s": n_videos * T / (fwd_ms * 1e-3),
             "stages_ms": {k: v[0] / steps for k, v in st.items() if v[1]},
-            "ncu": "profiles/r02_ncu_attention_T8192.csv (sm__pipe_tensor_cycles_active, dram__bytes of the same kernel)"}
+            "ncu": "profiles/r02p_ncu_full_summary.csv, row attention_tc_kernel (ncu --set full of tools/prof_long.py 8 8192 2: "
+                   "sm__pipe_tensor_cycles_active 65.0 %, dram__bytes 518.6 MB per launch)"}
 
 
 # ------------------------------------------------------------------------------------ our arm: inference configs
@@ -679,7 +680,8 @@ def run_train(args, rank, world, local_rank):
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, capturable=True, **({} if args.foreach_adamw else {"fused": True}))
     n_params = sum(p.numel() for p in model.parameters())
     stepper = training.TrainStep(model, opt, torch.nn.functional.mse_loss, visual, audio, target,
-                                 world_size=world, graph=not args.no_graph, warmup=max(args.warmup, 3))
+                                 world_size=world, graph=not args.no_graph, warmup=max(args.warmup, 3),
+                                 **({} if args.bucket_mb is None else {"bucket_mb": args.bucket_mb}))
 
     def barrier():
         if world > 1:
@@ -749,6 +751,8 @@ def main():
     ap.add_argument("--no-attention-probe", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="--config train: launch the step eagerly")
     ap.add_argument("--foreach-adamw", action="store_true", help="--config train: torch's default (foreach) AdamW")
+    ap.add_argument("--bucket-mb", type=float, default=None,
+                    help="--config train: gradient all-reduce bucket size in MB (default: training.TrainStep's)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
