@@ -28,7 +28,7 @@ EXPORTS = [
     "avs_last_error", "avs_version", "avs_device_ok", "avs_model_create", "avs_model_update",
     "avs_model_destroy", "avs_forward", "avs_summarize", "avs_linear", "avs_bilstm_pair",
     "avs_attention", "avs_temporal_f1", "avs_launch_count", "avs_profile", "avs_profile_stages",
-    "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace", "avs_debug_bptt_trace",
+    "avs_profile_stage_name", "avs_profile_read", "avs_debug_lstm_trace", "avs_debug_bptt_trace", "avs_model_range_status",
     "avs_eval_metrics", "avs_cdist", "avs_interpolate", "avs_dtw_path",
     "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
     "avs_debug_e2e_trace", "avs_forward_summarize_async", "avs_slot_wait",
@@ -141,6 +141,8 @@ def lib() -> C.CDLL:
     L.avs_linear_bwd.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     L.avs_debug_lstm_trace.restype = C.c_int
     L.avs_debug_lstm_trace.argtypes = [vp]
+    L.avs_model_range_status.restype = C.c_int
+    L.avs_model_range_status.argtypes = [vp, vp]
     L.avs_debug_bptt_trace.restype = C.c_int
     L.avs_debug_bptt_trace.argtypes = [vp]
     L.avs_debug_gemm_trace.restype = C.c_int

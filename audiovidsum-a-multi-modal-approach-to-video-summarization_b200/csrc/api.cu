@@ -226,6 +226,11 @@ struct avs_model {
     int device = 0;
     int Dv = 0, Da = 0, heads = 4;
     int feat_f16 = 0;   // avs_model_set_feature_format: the caller's visual / audio buffers hold IEEE fp16, not fp32
+    // fp16 range watch: one word of MAPPED pinned host memory that the fc GEMM epilogues set when an activation
+    // reaches the fp16 limit (the cast saturates silently).  Host-space calls read it after their final stream
+    // synchronisation (no copy); device-space callers ask avs_model_range_status after synchronising themselves.
+    unsigned int* range_flag = nullptr;       // host view
+    unsigned int* range_flag_dev = nullptr;   // device view of the same word
     // packed parameters (one slab); *_x = exact fp32, *_t = tf32-rounded copies
     char* slab = nullptr;
     float *fc_v_w_x, *fc_v_w_t, *fc_a_w_x, *fc_a_w_t, *fc_v_b, *fc_a_b;
@@ -657,6 +662,17 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
         *it.p = m->slab + off;
         off += align_up(it.bytes, 256);
     }
+    if (cudaHostAlloc(reinterpret_cast<void**>(&m->range_flag), sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess)
+        *m->range_flag = 0u;
+    else {
+        m->range_flag = nullptr;
+    }
+    if (m->range_flag == nullptr ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->range_flag_dev), m->range_flag, 0) != cudaSuccess) {
+        if (m->range_flag) cudaFreeHost(m->range_flag);
+        m->range_flag = m->range_flag_dev = nullptr;   // the watch is an aid: without the page the forward does not report
+        cudaGetLastError();
+    }
     // the packing kernels run on the handle's own stream: the caller guarantees that the parameters are complete
     // (include/avsum_b200.h), nothing else is ordered against the legacy default stream
     avs_status s = AVS_OK;
@@ -746,6 +762,7 @@ void avs_model_destroy(avs_model* m) {
     m->ws.release();
     m->staging.release();
     m->pack_ws.release();
+    if (m->range_flag) cudaFreeHost(m->range_flag);
     for (int i = 0; i < avs_model::SLOTS; ++i) {
         m->host_in[i].release();
         if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
@@ -777,6 +794,19 @@ void avs_model_destroy(avs_model* m) {
         if (e) cudaEventDestroy(e);
     if (m->slab) cudaFree(m->slab);
     delete m;
+}
+
+// Host side of the fp16 range watch: call after a stream synchronisation that covers the forward(s) in question.
+// Sticky until reported: with two batches in flight the report may come one call early.
+static avs_status range_report(avs_model* m) {
+    if (m == nullptr || m->range_flag == nullptr) return AVS_OK;
+    volatile unsigned int* f = m->range_flag;
+    if (*f == 0u) return AVS_OK;
+    *f = 0u;
+    set_error("fc activations reached the fp16 range limit (|x| >= 65504) in this or a concurrently running call and "
+              "were clamped there: the scores are not trustworthy.  Normalise the features or use AVS_PREC_BF16 (fp32 "
+              "exponent range)");
+    return AVS_ERR_UNSUPPORTED;
 }
 
 static avs_status forward_impl(avs_model* m, const float* visual, const float* audio, int64_t total_rows,
@@ -877,7 +907,10 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
                 copy_video_rows_kernel<float><<<grid, 256, 0, sp>>>(ps, scores, back_dev, n_videos, 1, 256);
                 AVS_LAUNCH_CHECK();
             }
-            if (host) AVS_CUDA(cudaStreamSynchronize(sp));
+            if (host) {
+                AVS_CUDA(cudaStreamSynchronize(sp));
+                AVS_TRY(range_report(m));
+            }
             return AVS_OK;
         }
     }
@@ -1048,7 +1081,7 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
     }
     AVS_CUDA(cudaMemcpyAsync(scores, sc_dev, uR * 4, cudaMemcpyDeviceToHost, st));
     AVS_CUDA(cudaStreamSynchronize(st));
-    return AVS_OK;
+    return range_report(m);
 }
 
 avs_status avs_forward(avs_model* m, const float* visual, const float* audio, int64_t total_rows, int32_t n_videos,
@@ -1107,6 +1140,11 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                       "layout with equal lengths; video %d breaks it", b);
     }
 
+    // fp16 range watch (see avs_model::range_flag): only when every row belongs to a video -- rows no video owns may
+    // hold anything (the contract is that they never reach a valid frame), and the GEMM epilogue cannot tell them apart
+    int64_t owned_rows = 0;
+    for (int b = 0; b < n_videos; ++b) owned_rows += lengths[b];
+    unsigned int* const sat_flag = (!simt && !bf16 && owned_rows == total_rows) ? m->range_flag_dev : nullptr;
     // ---- plan + workspace
     LstmPlan plan = plan_lstm(n_videos, row_start, lengths, !simt);
     const int n_seqs = literal_rows ? 0 : (attn_axis == AVS_ATTN_TEMPORAL ? n_videos : lengths[0]);
@@ -1193,6 +1231,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 GemmEpilogue e1;
                 e1.relu = 1;
                 e1.out_dtype = act;
+                e1.sat_flag = sat_flag;
                 e1.ldc = H;
                 if (!bf16 && !f16_in) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
                 GemmEpilogue e2;
@@ -1294,6 +1333,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         GemmEpilogue e1;
         e1.relu = 1;
         e1.out_dtype = act;
+        e1.sat_flag = sat_flag;
         e1.ldc = H;
         if (!simt && !bf16 && !f16_in) e1.acc_scale = 1.0f + 1.0f / 2048.0f;
         GemmEpilogue e2;
@@ -1444,6 +1484,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     if (space == AVS_HOST) {
         AVS_CUDA(cudaMemcpyAsync(scores, scores_dev, uR * 4, cudaMemcpyDeviceToHost, st));
         AVS_CUDA(cudaStreamSynchronize(st));
+        AVS_TRY(range_report(m));
     }
     return AVS_OK;
 }
@@ -1721,8 +1762,9 @@ static avs_status forward_summarize_impl(avs_model* m, const float* visual, cons
     if (async) {
         AVS_CUDA(cudaEventRecord(m->ev_slot[slot], st));
         m->slot_busy[slot] = true;
+        return AVS_OK;     // avs_slot_wait reports the range watch
     }
-    return AVS_OK;
+    return range_report(m);   // the stream is synchronised: the forward of this call has completed
 }
 
 avs_status avs_forward_summarize(avs_model* m, const float* visual, const float* audio, const int32_t* positions,
@@ -1748,6 +1790,21 @@ avs_status avs_forward_summarize_async(avs_model* m, const float* visual, const 
                                   summary, summary_start, AVS_HOST, cuda_stream, slot, true);
 }
 
+/* fp16 range watch for DEVICE-space callers (host-space calls report by themselves): *saturated = 1 when, since the last
+ * report, an fc activation of a forward on this handle reached the fp16 limit and was clamped.  Reads and clears the
+ * flag; the caller has synchronised the stream(s) of the forwards it asks about.  No reference counterpart (the
+ * reference computes in fp32). */
+avs_status avs_model_range_status(avs_model* m, int32_t* saturated) {
+    AVS_CHECK(m != nullptr && saturated != nullptr, AVS_ERR_INVALID, "avs_model_range_status: null pointer");
+    *saturated = 0;
+    if (m->range_flag != nullptr) {
+        volatile unsigned int* f = m->range_flag;
+        *saturated = *f != 0u ? 1 : 0;
+        *f = 0u;
+    }
+    return AVS_OK;
+}
+
 avs_status avs_slot_wait(avs_model* m, int slot) {
     AVS_CHECK(m != nullptr, AVS_ERR_INVALID, "model handle is null");
     AVS_CHECK(slot >= 0 && slot < avs_model::SLOTS, AVS_ERR_INVALID, "bad slot %d", slot);
@@ -1755,7 +1812,7 @@ avs_status avs_slot_wait(avs_model* m, int slot) {
     Guard g(m->device);
     AVS_CUDA(cudaEventSynchronize(m->ev_slot[slot]));
     m->slot_busy[slot] = false;
-    return AVS_OK;
+    return range_report(m);
 }
 
 avs_status avs_linear(const float* A, const float* W, const float* bias, int64_t M, int32_t N, int32_t K, int relu,

@@ -98,6 +98,9 @@ struct GemmEpilogue {
     const float* score_w2 = nullptr;
     const float* score_b2 = nullptr;   // device pointer to 1 float
     float* scores = nullptr;
+    // fp16 outputs only: *sat_flag = 1 when a value reached the fp16 range limit (|x| >= 65504) or was not finite
+    // (the cast saturates silently).  Points into mapped pinned host memory: the host reads it after a stream sync.
+    unsigned int* sat_flag = nullptr;
     // host-side launch hint: at most this many CTAs of the persistent grid (0 = one per SM).  Used when part of the
     // GPU is known to be occupied by concurrently running recurrence clusters: CTAs of a statically scheduled
     // persistent kernel that cannot be placed at once would delay their share of the tiles.

@@ -171,6 +171,11 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
             const bool bias_vec = (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
             const bool tr = g_gemm_trace_on && blockIdx.x == 0 && warp == 2 && lane == 0;   // (warp 2: q = 2, cg = 0)
             long long tr_wait = 0, tr_t0 = tr ? gclk() : 0;
+            // range watch of fp16 outputs (epi.sat_flag): the cast saturates at 65504 instead of overflowing, which is
+            // silent; the largest magnitude this thread produced is tracked in a register and reported ONCE, after the
+            // last tile, with a plain store into the (mapped, pinned) flag word.  (NaN does not count: fmaxf drops it,
+            // and a NaN feature shows up as a NaN score.)
+            float sat_big = 0.f;
             uint32_t lt = 0;
             for (int t = tile0; t < num_tiles; t += tile_step, ++lt) {
                 const int m0 = (t / tiles_n) * tile_rows + m_off, n0 = (t % tiles_n) * BN;
@@ -217,6 +222,7 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
                             load_bias32(epi.bias, nb + hf * 32, N, bias_vec, bv);
                             tmem_ld_wait();
                             uint32_t pk[16];
+                            float big = 0.f;   // largest magnitude of this thread's values (range watch, see below)
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 float x0 = fmaf(__uint_as_float(r[j]), epi.acc_scale, bv[j]), x1 = fmaf(__uint_as_float(r[j + 1]), epi.acc_scale, bv[j + 1]);
@@ -224,8 +230,10 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
                                     x0 = fmaxf(x0, 0.f);
                                     x1 = fmaxf(x1, 0.f);
                                 }
+                                big = fmaxf(big, fmaxf(fabsf(x0), fabsf(x1)));
                                 pk[j >> 1] = pack_lowp2(x0, x1, epi.out_dtype);
                             }
+                            sat_big = fmaxf(sat_big, big);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 st_shared_v4(dst + ((static_cast<uint32_t>(hf * 4 + j) ^ sw) << 4), pk[4 * j],
@@ -245,6 +253,9 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* tiles, uint32_t tmem_base
             }
             if (lane == 0) bulk_wait_group_read(0);   // shared memory must outlive the last stores' reads
             __syncwarp();
+            // (rows beyond M and columns beyond N are zero-filled by TMA and carry the bias only: they cannot trip it)
+            if (epi.sat_flag != nullptr && epi.out_dtype == DT_F16 && !(sat_big < 65504.f))
+                *reinterpret_cast<volatile unsigned int*>(epi.sat_flag) = 1u;
             if (tr) {
                 g_gemm_trace[4] += tr_wait;
                 g_gemm_trace[5] += gclk() - tr_t0;

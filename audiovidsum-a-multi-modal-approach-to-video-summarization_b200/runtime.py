@@ -195,6 +195,17 @@ class NativeModel:
         except Exception:
             pass
 
+    def range_status(self, synchronize: bool = True) -> bool:
+        """fp16 range watch for device-space forwards (host-space calls raise by themselves): True when an fc activation
+        of a forward on this handle reached the fp16 limit (65504) and was clamped since the last report -- un-normalised
+        features of huge magnitude; the reference computes in fp32.  Reading clears the flag.  ``synchronize`` waits for
+        the device first (the flag is written by the kernels of the forward)."""
+        if synchronize:
+            torch.cuda.synchronize(self.device)
+        sat = C.c_int32(0)
+        _cabi.check(self.lib.avs_model_range_status(self._handle, C.byref(sat)))
+        return bool(sat.value)
+
     def _features(self, visual: torch.Tensor, audio: torch.Tensor):
         """Feature buffers as the library will read them: both tensors float16 -> the opt-in 16-bit feature format
         (avs_model_set_feature_format, half the bytes per frame); anything else -> float32, as in the reference."""

@@ -159,6 +159,14 @@ avs_status avs_forward_summarize_async(avs_model* m, const float* visual, const 
                                        const int32_t* cps_start, int32_t prop_num, int32_t prop_den, float* scores,
                                        uint8_t* picks, int64_t* seg_mean, uint8_t* summary,
                                        const int64_t* summary_start, int slot, void* cuda_stream);
+/* fp16 range watch.  The default precision keeps the activations behind the fc layers in fp16, whose cast SATURATES at
+ * 65504 instead of overflowing -- silent for un-normalised features of huge magnitude (the reference computes in fp32).
+ * The fc GEMM epilogues therefore watch the magnitudes they write (dense batches: every row owned by a video) and set
+ * a flag; HOST-space calls (avs_forward, avs_forward_summarize, avs_slot_wait) fail with AVS_ERR_UNSUPPORTED when it is
+ * set.  DEVICE-space calls return before the work has run: their callers synchronise and ask here.  *saturated = 1
+ * when an activation was clamped since the last report; reading clears the flag. */
+avs_status avs_model_range_status(avs_model* m, int32_t* saturated);
+
 /* Block until the asynchronous step that used `slot` has completed (no-op for an idle slot). */
 avs_status avs_slot_wait(avs_model* m, int slot);
 

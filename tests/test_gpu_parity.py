@@ -1084,3 +1084,25 @@ def test_attention_core_is_repeatable_under_concurrent_load(cuda_ready):
         out = runtime.attention(qkv, 1024, 4, starts, ones, lens)
         assert torch.equal(out, ref), f"launch {i} differs from the first"
     torch.cuda.synchronize()
+
+
+def test_fp16_range_watch_reports_clamped_activations(native):
+    """The default precision keeps the fc activations in fp16, whose cast clamps at 65504: features of huge magnitude
+    must not produce silently wrong scores.  Host-space calls fail loudly, device-space callers ask range_status();
+    ordinary features and the bf16 mode (fp32 exponent range) do not trip it."""
+    g = torch.Generator().manual_seed(5)
+    R = 300
+    visual, audio = torch.randn(R, 1024, generator=g), torch.randn(R, 128, generator=g)
+    starts, lens = [0, 200], [200, 100]
+    native.forward_rows(visual.cuda(), audio.cuda(), starts, lens, "literal_b1", "tf32")
+    assert native.range_status() is False
+    huge = visual * 3e6                                   # |fc output| ~ 3e6 * sqrt(1024) * |w| >> 65504
+    native.forward_rows(huge.cuda(), audio.cuda(), starts, lens, "literal_b1", "tf32")
+    assert native.range_status() is True
+    assert native.range_status() is False                 # reading cleared it
+    with pytest.raises(RuntimeError, match="fp16 range limit"):
+        native.forward_rows(huge.pin_memory(), audio.pin_memory(), starts, lens, "literal_b1", "tf32")
+    out = native.forward_rows(visual.pin_memory(), audio.pin_memory(), starts, lens, "literal_b1", "tf32")   # recovered
+    assert torch.isfinite(out).all()
+    native.forward_rows(huge.cuda(), audio.cuda(), starts, lens, "literal_b1", "bf16")
+    assert native.range_status() is False
