@@ -1021,6 +1021,48 @@ def test_summarize_randomised_batches_bit_exact(native, prop):
             assert np.array_equal(ws, summary[sum_start[i]:sum_start[i + 1]]), (oversized, i)
 
 
+@pytest.mark.parametrize("n_vid,prop", [(3, (15, 100)), (9, (1, 2)), (20, (15, 100)), (30, (3, 7))])
+def test_summarize_long_videos_on_clusters_bit_exact(native, n_vid, prop):
+    """Batches whose largest capacity no longer fits one SM's fast path and that leave room for a cluster per video:
+    8 CTAs per video up to 18 videos, 4 CTAs up to 37 (csrc/summarize.cu knapsack_cluster_kernel).  Ragged on purpose:
+    capacities from a few cells to ~20,000, shots from one frame to longer than a CTA's slice, gaps between shots,
+    short videos next to long ones.  Picks / shot means / bitmap bit-exact against the oracle."""
+    rng = np.random.default_rng(1000 + n_vid)
+    vids, scores = [], []
+    for i in range(n_vid):
+        # capacity = nf * num // den: 20,000 cells for the first video (the batch's largest; the cluster kernel covers
+        # up to 24,575), a few cells or several thousand for the others
+        cap = 20000 if i == 0 else int(rng.choice([int(rng.integers(3, 300)), int(rng.integers(3000, 19000))]))
+        nf = cap * prop[1] // prop[0] + int(rng.integers(0, max(prop[1] // prop[0], 1)))
+        n_cuts = 2 * int(rng.integers(1, 200 if nf > 5000 else 20))
+        cuts = np.sort(rng.choice(nf + 1, size=min(nf + 1, n_cuts), replace=False))
+        shots = [(int(a), int(b) - 1) for a, b in zip(cuts[0::2], cuts[1::2]) if b > a] or [(0, nf - 1)]
+        if i == 1 and nf > 20000:
+            # one long shot: 900 frames, whose halo reaches far into the left neighbour's slice (the kernel handles shots
+            # up to 1,024 frames); in the 9-video case a third of the video, which sends the batch to the general path
+            end = nf // 3 if n_vid == 9 else 899
+            shots = [(0, end)] + [(a, b) for a, b in shots if a > end]
+        T = int(rng.integers(1, min(nf, 600) + 1))
+        pos = np.sort(rng.choice(nf, size=T, replace=False)).astype(np.int32)
+        sc = rng.random(T).astype(np.float32)
+        sc[rng.random(T) < 0.05] = 0.0
+        vids.append(synth.Video(torch.zeros(T, 1), torch.zeros(T, 1), nf, pos, np.asarray(shots, np.int32)))
+        scores.append(sc)
+    lens = [v.T for v in vids]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    picks, seg_mean, summary, cps_start, sum_start = native.summarize_rows(
+        torch.from_numpy(np.concatenate(scores)).cuda(),
+        torch.from_numpy(np.concatenate([v.positions for v in vids]).astype(np.int32)).cuda(), starts, lens,
+        [v.n_frames for v in vids], [v.cps for v in vids], prop)
+    torch.cuda.synchronize()
+    picks, seg_mean, summary = picks.cpu().numpy(), seg_mean.cpu().numpy(), summary.cpu().numpy()
+    for i, v in enumerate(vids):
+        wp, ws, wm = av_oracle.generate_summary(scores[i], v.cps, v.n_frames, v.positions, prop[0], prop[1])
+        assert np.array_equal(wm, seg_mean[cps_start[i]:cps_start[i + 1]]), i
+        assert np.array_equal(wp, picks[cps_start[i]:cps_start[i + 1]]), i
+        assert np.array_equal(ws, summary[sum_start[i]:sum_start[i + 1]]), i
+
+
 @pytest.mark.parametrize("n_videos", [20, 70, 150, 300])
 def test_forward_many_short_videos_all_lstm_variants(cuda_ready, n_videos):
     """Batches of 20 / 70 / 150 / 300 videos select the 16- / 32- / 64-slot recurrence kernels (and, beyond one
