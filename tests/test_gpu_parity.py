@@ -1034,12 +1034,15 @@ def test_summarize_long_videos_on_clusters_bit_exact(native, n_vid, prop):
         # up to 24,575), a few cells or several thousand for the others
         cap = 20000 if i == 0 else int(rng.choice([int(rng.integers(3, 300)), int(rng.integers(3000, 19000))]))
         nf = cap * prop[1] // prop[0] + int(rng.integers(0, max(prop[1] // prop[0], 1)))
-        n_cuts = 2 * int(rng.integers(1, 200 if nf > 5000 else 20))
-        cuts = np.sort(rng.choice(nf + 1, size=min(nf + 1, n_cuts), replace=False))
-        shots = [(int(a), int(b) - 1) for a, b in zip(cuts[0::2], cuts[1::2]) if b > a] or [(0, nf - 1)]
+        # shots of 1 .. 600 frames (TVSum / SumMe shots are 30 - 300) with random gaps, up to ~400 of them
+        shots, f, n_max = [], int(rng.integers(0, 50)), int(rng.integers(1, 400))
+        while f < nf and len(shots) < n_max:
+            end = min(f + int(rng.integers(1, 601)) - 1, nf - 1)
+            shots.append((f, end))
+            f = end + 1 + int(rng.integers(0, 200))
         if i == 1 and nf > 20000:
             # one long shot: 900 frames, whose halo reaches far into the left neighbour's slice (the kernel handles shots
-            # up to 1,024 frames); in the 9-video case a third of the video, which sends the batch to the general path
+            # up to 1,024 frames); in the 9-video case a third of the video, which sends the batch to the one-SM path
             end = nf // 3 if n_vid == 9 else 899
             shots = [(0, end)] + [(a, b) for a, b in shots if a > end]
         T = int(rng.integers(1, min(nf, 600) + 1))
@@ -1050,11 +1053,20 @@ def test_summarize_long_videos_on_clusters_bit_exact(native, n_vid, prop):
         scores.append(sc)
     lens = [v.T for v in vids]
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
-    picks, seg_mean, summary, cps_start, sum_start = native.summarize_rows(
-        torch.from_numpy(np.concatenate(scores)).cuda(),
-        torch.from_numpy(np.concatenate([v.positions for v in vids]).astype(np.int32)).cuda(), starts, lens,
-        [v.n_frames for v in vids], [v.cps for v in vids], prop)
-    torch.cuda.synchronize()
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:      # which kernel made the selection?
+        picks, seg_mean, summary, cps_start, sum_start = native.summarize_rows(
+            torch.from_numpy(np.concatenate(scores)).cuda(),
+            torch.from_numpy(np.concatenate([v.positions for v in vids]).astype(np.int32)).cuda(), starts, lens,
+            [v.n_frames for v in vids], [v.cps for v in vids], prop)
+        torch.cuda.synchronize()
+    kernels = " ".join(e.key for e in prof.key_averages())
+    if "knapsack" in kernels:          # (CUPTI records available)
+        want_kernel = {3: "knapsack_cluster_kernel<8>", 20: "knapsack_cluster_kernel<4>", 30: "knapsack_cluster_kernel<4>",
+                       9: "knapsack_fast_kernel"}[n_vid]
+        if n_vid == 9 and not any(v.n_frames > 20000 for v in vids[1:2]):
+            want_kernel = "knapsack_cluster_kernel<8>"       # (no long shot drawn: the cluster kernel takes the batch)
+        assert want_kernel in kernels, kernels
     picks, seg_mean, summary = picks.cpu().numpy(), seg_mean.cpu().numpy(), summary.cpu().numpy()
     for i, v in enumerate(vids):
         wp, ws, wm = av_oracle.generate_summary(scores[i], v.cps, v.n_frames, v.positions, prop[0], prop[1])
