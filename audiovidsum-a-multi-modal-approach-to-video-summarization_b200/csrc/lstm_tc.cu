@@ -134,6 +134,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -393,6 +398,16 @@ lstm_tc_kernel(const void* __restrict__ xg_v, const void* __restrict__ xg_a, con
                 // arguments clamped from below so that the products stay far inside fp32 (sigmoid(-25) = 1.4e-11).
                 // No upper clamp: beyond +25 (+12.5) the exponential is < 2^-24 and 1 + e rounds to 1 either way,
                 // down to the flushed zero -- same bits, one dependent instruction less per gate.
+#ifdef AVS_LSTM_TANH_APPROX
+                // EXPERIMENT (not the shipped build): one MUFU.TANH per activation -- sigmoid(x) =
+                // 0.5 tanh(x / 2) + 0.5 -- i.e. a dependent chain of two SFU operations per cell instead of four, at
+                // tanh.approx's ~2^-11 relative error (the formulation below is ~1e-7)
+                const float s_i = fmaf(tanh_approx(0.5f * t_i), 0.5f, 0.5f);
+                const float s_f = fmaf(tanh_approx(0.5f * t_f), 0.5f, 0.5f);
+                const float s_o = fmaf(tanh_approx(0.5f * t_o), 0.5f, 0.5f);
+                const float cn = fmaf(s_f, c_state[k], s_i * tanh_approx(t_g));
+                const float h = s_o * tanh_approx(cn);
+#else
                 const float ei = ex2_approx(fmaxf(t_i, -25.f) * -LOG2E);
                 const float ef = ex2_approx(fmaxf(t_f, -25.f) * -LOG2E);
                 const float eg = ex2_approx(fmaxf(t_g, -12.5f) * (-2.f * LOG2E));
@@ -402,6 +417,7 @@ lstm_tc_kernel(const void* __restrict__ xg_v, const void* __restrict__ xg_a, con
                 const float cn = fmaf(c_state[k], A, (1.f - eg) * opf) * rcp_approx(A * opf);
                 const float ec = ex2_approx(fmaxf(cn, -12.5f) * (-2.f * LOG2E));
                 const float h = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));
+#endif
                 const bool on = s < len_r[k];
                 c_state[k] = on ? cn : c_state[k];
                 h_out[k] = h;

@@ -113,6 +113,7 @@ def test_bilstm_pair_matches_torch_lstm(native, lens):
                                                C.c_void_p(fused.data_ptr()),
                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         torch.cuda.synchronize()
+        print(f"bilstm pair {prec} lens={lens}: max |h - torch| {float((fused.cpu() - want).abs().max()):.2e} (tolerance {tol})")
         assert float((fused.cpu() - want).abs().max()) < tol
 
 
@@ -360,6 +361,7 @@ def test_config2_full_batch_matches_cpu_port(cuda_ready, golden_dir):
         want = av_oracle_torch.run_videos(port, [(v.visual, v.audio) for v in vids],
                                           "literal" if axis == "literal_b1" else "temporal")
         worst = max(rel(a.numpy(), b.numpy()) for a, b in zip(got, want))
+        print(f"config 2, spread weights, {axis}: worst relative score error {worst:.2e} (tolerance 1e-3)")
         assert worst < 1e-3, (axis, worst)
 
 
