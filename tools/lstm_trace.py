@@ -16,9 +16,11 @@ import avsum_b200  # noqa: E402,F401
 from avsum_b200 import _cabi, synth  # noqa: E402
 from avsum_b200.models.av_model import AVBiLSTMModel  # noqa: E402
 
-NAMES = ["h landed -> 16 MMAs + commit issued", "commit issued -> epilogue awake (MMA latency)", "tcgen05.ld",
-         "transpose + cell math + stage write", "fence.proxy.async + 512-thread barrier", "bulk-copy issue",
-         "copies issued -> next h landed (DSMEM exchange, slowest peer)"]
+NAMES = ["h landed -> fence.proxy.async + 16 MMAs + commit issued", "commit issued -> epilogue awake (MMA latency)",
+         "tcgen05.ld (two 16-lane loads: all four gates of one unit per thread)",
+         "+ input projection, cell update on the SFU, h staged as fp16", "tcgen05 fence + __syncwarp",
+         "ld.shared of the staged chunk + st.async issue (one 16-byte message per lane)",
+         "messages issued -> next h landed (DSMEM exchange, slowest peer)"]
 
 
 def main():
