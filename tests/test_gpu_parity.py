@@ -464,6 +464,26 @@ def test_summarize_long_video_uses_global_dp_rows(native):
     assert picks.sum() > 0
 
 
+def test_summarize_capacity_beyond_every_on_chip_path(native):
+    """A capacity no on-chip variant covers (60,000 cells: the cluster kernel stops at 24,575, the one-SM register
+    kernel at 20,480): DP rows and keep bits in the global workspace.  Bit-exact against the oracle, next to a short
+    video in the same batch."""
+    rng = np.random.default_rng(77)
+    vids, scores = [], []
+    for nf, n_shots in ((400000, 300), (900, 12)):
+        shots, f = [], 0
+        while f < nf and len(shots) < n_shots:
+            end = min(f + int(rng.integers(1, 3000 if nf > 1000 else 120)) - 1, nf - 1)
+            shots.append((f, end))
+            f = end + 1 + int(rng.integers(0, 50))
+        T = min(nf, 500)
+        pos = np.sort(rng.choice(nf, size=T, replace=False)).astype(np.int32)
+        vids.append(synth.Video(torch.zeros(T, 1), torch.zeros(T, 1), nf, pos, np.asarray(shots, np.int32)))
+        scores.append(rng.random(T).astype(np.float32))
+    picks = _summarize_and_compare(native, vids, np.concatenate(scores), "cuda")
+    assert picks.sum() > 0
+
+
 def test_generate_summary_single_video_api(cuda_ready):
     from avsum_b200.evaluation.summary import generate_summary
     m = make_model()
