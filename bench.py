@@ -589,6 +589,18 @@ def run_infer(args, rank, world, local_rank):
     flops = stage_flops_per_frame(axis, mean_T)
     kernels = kernel_table(stage_ms, args.steps, flops, R, peaks, 8 * R + 16 * sum(len(c) for c in cps_list))
     roofline = roofline_of(kernels, ms_per_step, peaks, world)
+    # the whole step against both rooflines: algorithmic FLOP of the layers the step executes and the
+    # algorithmic bytes of its inputs / outputs (features read once, one score per frame, weights once per step)
+    step_flop = R * sum(flops[k] for k in ("fc_gemm", "lstm_input_gemm", "lstm_recurrence", "attn_in_proj_gemm",
+                                           "attention_core", "attn_out_proj_gemm", "score_head_gemm"))
+    step_bytes = R * ((1024 + 128) * 4 + 4) + 32_035_332
+    whole_step = {"algorithmic_tflop": step_flop / 1e12, "tflops": step_flop / (ms_per_step * 1e-3) / 1e12,
+                  "frac_of_tensor_peak": step_flop / (ms_per_step * 1e-3) / 1e12 / peaks["tflops"],
+                  "ideal_ms_at_tensor_peak": step_flop / (peaks["tflops"] * 1e12) * 1e3,
+                  "algorithmic_bytes": step_bytes, "ideal_ms_at_hbm_peak": step_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3,
+                  "note": "the step is bound by neither roofline: the recurrence is a chain of max(T) dependent "
+                          "steps (roofline.share_of_step of the time at a few percent of the tensor peak); the "
+                          "contractions around it run at kernels{}.frac_of_tensor_peak"}
 
     line = {
         "metric": METRIC, "value": frames_global / (ms_per_step * 1e-3), "unit": "frames/s", "n_gpus": world,
@@ -620,6 +632,7 @@ def run_infer(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": roofline,
         "kernels": kernels,
+        "whole_step": whole_step,
         "wall_s_timed_region": wall,
         "comm": {"backend": "nccl" if world > 1 else None, "nranks": world,
                  "collective": "all_gather_into_tensor of the keyshot picks, once per step" if world > 1 else None},
