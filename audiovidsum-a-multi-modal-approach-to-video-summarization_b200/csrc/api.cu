@@ -41,16 +41,20 @@ int device_sm_count() {
 // Enabled by avs_profile(1); events are resolved lazily in avs_profile_read so the hot path
 // never synchronises because of profiling.
 enum Stage : int { ST_CONVERT = 0, ST_FC, ST_IH_PROJ, ST_LSTM, ST_QKV_PROJ, ST_ATTENTION, ST_OUT_PROJ, ST_SCORER,
-                   ST_POOL, ST_KNAPSACK, ST_FRONT, ST_FRONT_LSTM, ST_COUNT };
+                   ST_POOL, ST_KNAPSACK, ST_FRONT, ST_FRONT_LSTM, ST_TAIL_EXPOSED, ST_COUNT };
 static const char* const kStageNames[ST_COUNT] = {"convert_tf32", "fc_gemm", "lstm_input_gemm", "lstm_recurrence",
                                                   "attn_in_proj_gemm", "attention_core", "attn_out_proj_gemm",
                                                   "score_head_gemm", "shot_pool", "knapsack_select",
-                                                  "frontend_gemms", "frontend_lstm_pipelined"};
+                                                  "frontend_gemms", "frontend_lstm_pipelined",
+                                                  "tail_behind_longest_recurrence"};
 struct Profiler {
     bool enabled = false;
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
-    struct Rec { int stage; cudaEvent_t a, b; };
+    // span != 0: the records of one span (same id) time concurrent pieces of ONE stage that start together; the stage
+    // lasts until the last of them ends (maximum, counted once)
+    struct Rec { int stage; cudaEvent_t a, b; long long span = 0; };
+    long long next_span = 1;
     std::vector<Rec> pending;
     double ms[ST_COUNT] = {};
     long long calls[ST_COUNT] = {};
@@ -63,14 +67,32 @@ struct Profiler {
         return pool[used++];
     }
     void resolve() {
+        long long cur_span = 0;
+        int span_stage = 0;
+        float span_ms = 0.f;
+        auto close_span = [&]() {
+            if (cur_span) {
+                ms[span_stage] += span_ms;
+                calls[span_stage] += 1;
+            }
+            cur_span = 0;
+            span_ms = 0.f;
+        };
         for (auto& r : pending) {
             cudaEventSynchronize(r.b);
             float t = 0.f;
-            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+            if (r.span != cur_span) close_span();
+            if (r.span) {   // records of a span are pushed back to back
+                cur_span = r.span;
+                span_stage = r.stage;
+                span_ms = std::max(span_ms, t);
+            } else {
                 ms[r.stage] += t;
                 calls[r.stage] += 1;
             }
         }
+        close_span();
         pending.clear();
         used = 0;
     }
@@ -90,7 +112,7 @@ struct StageTimer {
         if (a) {
             cudaEvent_t b = g_prof.get();
             cudaEventRecord(b, st);
-            g_prof.pending.push_back({stage, a, b});
+            g_prof.pending.push_back({stage, a, b, 0});
         }
     }
 };
@@ -277,7 +299,7 @@ struct avs_model {
     cudaEvent_t ev_branch_in[MAX_CHUNKS] = {}, ev_branch_out[MAX_CHUNKS] = {};
     // pipelined front: the recurrence of video group k starts (on its own high-priority stream) as soon as the input
     // projections of its rows exist, while the GEMMs of the following groups still run
-    static constexpr int PIPE_SEGS = 5;
+    static constexpr int PIPE_SEGS = 8;
     cudaStream_t pipe_stream[PIPE_SEGS] = {};
     cudaEvent_t ev_pipe_front[PIPE_SEGS] = {}, ev_pipe_done[PIPE_SEGS] = {};
 };
@@ -475,10 +497,14 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
     p.n_groups = (B + per_cluster - 1) / per_cluster;
     const int slots = p.n_groups * p.nb;
     p.host.assign(2 * slots + p.n_groups, 0);
+    // Uneven split: the extra videos go to the SHORTEST groups.  The longest group is the critical chain and the last
+    // to finish; the row-parallel work behind its recurrence (pipelined tail) is what the step still has to wait for,
+    // so it gets the fewest rows.  (AVS_PLAN_REM_FIRST=1: extras to the longest groups, the round-1 split; A/B aid.)
+    static const bool rem_first = getenv("AVS_PLAN_REM_FIRST") != nullptr;
     const int base = B / p.n_groups, rem = B % p.n_groups;
     int idx = 0;
     for (int g = 0; g < p.n_groups; ++g) {
-        const int cnt = base + (g < rem ? 1 : 0);
+        const int cnt = base + ((rem_first ? g < rem : g >= p.n_groups - rem) ? 1 : 0);
         p.host[2 * slots + g] = lengths[order[idx]];
         for (int i = 0; i < cnt; ++i, ++idx) {
             p.host[g * p.nb + i] = row_start[order[idx]];
@@ -486,6 +512,30 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
         }
     }
     return p;
+}
+
+// Row range [lo, hi) of every recurrence group when the groups tile the batch's rows in order (batches ordered longest
+// video first, the order packed_batches produces): group g then owns a contiguous block of rows and row-parallel work
+// can be issued per group.  False when a group's rows are not contiguous or the groups do not follow each other.
+bool group_row_ranges(const LstmPlan& plan, int64_t R, std::vector<int64_t>& glo, std::vector<int64_t>& ghi) {
+    const int G = plan.n_groups, nbp = plan.nb, slots = G * nbp;
+    glo.assign(G, 0);
+    ghi.assign(G, 0);
+    for (int gq = 0; gq < G; ++gq) {
+        int64_t lo = INT64_MAX, hi = 0, sum = 0;
+        for (int i = 0; i < nbp; ++i) {
+            const int64_t len = plan.host[slots + gq * nbp + i], rs0 = plan.host[gq * nbp + i];
+            if (len > 0) {
+                lo = std::min(lo, rs0);
+                hi = std::max(hi, rs0 + len);
+                sum += len;
+            }
+        }
+        if (!(sum > 0 && sum == hi - lo && lo == (gq ? ghi[gq - 1] : 0))) return false;
+        glo[gq] = lo;
+        ghi[gq] = hi;
+    }
+    return G > 0 && ghi[G - 1] == R;
 }
 
 // One weight matrix in every operand format the kernels consume.
@@ -1197,24 +1247,9 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     if (!simt && space == AVS_DEVICE && arena == nullptr && lstm_excl == 0 && plan.nb == 8 && plan.n_groups >= 3 &&
         getenv("AVS_PIPELINE") != nullptr && !(reinterpret_cast<uintptr_t>(visual) & 15) &&
         !(reinterpret_cast<uintptr_t>(audio) & 15)) {
-        const int G = plan.n_groups, nbp = plan.nb, slots = G * nbp;
-        std::vector<int64_t> glo(G), ghi(G);
-        bool ordered = true;
-        for (int gq = 0; gq < G && ordered; ++gq) {
-            int64_t lo = INT64_MAX, hi = 0, sum = 0;
-            for (int i = 0; i < nbp; ++i) {
-                const int64_t len = plan.host[slots + gq * nbp + i], rs0 = plan.host[gq * nbp + i];
-                if (len > 0) {
-                    lo = std::min(lo, rs0);
-                    hi = std::max(hi, rs0 + len);
-                    sum += len;
-                }
-            }
-            ordered = sum > 0 && sum == hi - lo && lo == (gq ? ghi[gq - 1] : 0);
-            glo[gq] = lo;
-            ghi[gq] = hi;
-        }
-        ordered = ordered && ghi[G - 1] == R;
+        const int G = plan.n_groups, nbp = plan.nb;
+        std::vector<int64_t> glo, ghi;
+        const bool ordered = group_row_ranges(plan, R, glo, ghi);
         if (ordered) {
             pipelined = true;
             const int n_seg = std::min(G, avs_model::PIPE_SEGS);   // groups 0 .. n_seg-2 alone, the rest together
@@ -1398,6 +1433,130 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                   "%u fc activations saturate fp16 (|x| >= 65504) or are not finite: normalise the features or use "
                   "AVS_PREC_BF16 (fp32 exponent range)", host_cnt);
     }
+
+    // ---- pipelined tail (device-resident batches ordered longest video first, sequence-length-1 attention): the
+    // recurrence of a group lasts max(T of the group) dependent steps, so the groups finish one after the other,
+    // shortest first, and the SMs of a finished group stay idle until the longest group is done (config 2: 128 of 148
+    // SMs hold recurrence CTAs, and the groups end between ~1/3 and all of the kernel's time).  Everything behind the
+    // recurrence is row-parallel (value projection, out_proj, score head: av_model.py:44-46 with sequence length 1),
+    // so each group's recurrence is launched on its own stream, followed on the same stream by the tail GEMMs of that
+    // group's rows: the tails of the shorter groups run on the SMs their recurrences have left while the longest
+    // chain is still going, and only the tail of the longest group (~1/4 of the rows) remains after it.  Row r of a
+    // GEMM is computed identically whatever the row range of the launch, so the scores are bit-identical to the
+    // one-launch schedule.  Per-stage profiling (avs_profile) then reports the recurrence stage as front-done -> the
+    // LAST group's recurrence done, and "tail_behind_longest_recurrence" = the longest group's recurrence done -> all
+    // streams joined; the individual tail GEMMs are only timed in the one-launch schedule (AVS_PIPE_TAIL=0).
+    const char* const pipe_tail_env = getenv("AVS_PIPE_TAIL");   // read per call: the tests toggle it
+    const int pipe_tail = pipe_tail_env ? atoi(pipe_tail_env) : 1;
+    bool tail_done = false;
+    if (!pipelined && pipe_tail && !simt && literal_rows && space == AVS_DEVICE && arena == nullptr && lstm_excl == 0 &&
+        plan.nb == 8 && plan.n_groups >= 3 && plan.n_groups <= avs_model::PIPE_SEGS && owned_rows == total_rows) {
+        std::vector<int64_t> glo, ghi;
+        if (group_row_ranges(plan, R, glo, ghi)) {
+            tail_done = true;
+            const int G = plan.n_groups, slots_all = G * plan.nb;
+            int n_excl = lstm_exclusive_groups(G);
+            if (const char* e = getenv("AVS_PIPE_EXCL")) n_excl = atoi(e);
+            const int n_long = getenv("AVS_PIPE_LONG") ? atoi(getenv("AVS_PIPE_LONG")) : 0;
+            const int long_kb = getenv("AVS_PIPE_LONG_KB") ? atoi(getenv("AVS_PIPE_LONG_KB")) : 120;
+            // groups 2.. each start behind one more short stagger kernel, so that the groups are placed in order of
+            // length (measured: 0.685 vs 0.695 ms per config-2 forward; AVS_PIPE_STAGGER_ONCE=1: one stagger for all)
+            const bool stagger_each = getenv("AVS_PIPE_STAGGER_ONCE") == nullptr;
+            const int sms = device_sm_count();
+            LstmBatch lb{plan_dev, plan_dev + slots_all, plan_dev + 2 * slots_all, G, plan.nb, 0};
+            // The longest group runs on the caller's stream itself: its recurrence follows the front without an event
+            // hop and its SM-exclusive CTAs are placed first (exclusive CTAs need EMPTY SMs; were the 192 shared CTAs
+            // of the other groups placed first, one on every SM, the longest chain would wait for the shortest group
+            // to finish -- measured: +150..260 us in a third of the steps).  The other groups start a few microseconds
+            // later, behind a stagger kernel; they have that much slack many times over.
+            AVS_CUDA(cudaEventRecord(m->ev_pipe_front[0], st));
+            AVS_CUDA(cudaStreamWaitEvent(m->pipe_stream[0], m->ev_pipe_front[0], 0));
+            AVS_TRY(launch_stagger(m->pipe_stream[0], 4000));
+            AVS_CUDA(cudaEventRecord(m->ev_pipe_front[1], m->pipe_stream[0]));
+            avs_status rc = AVS_OK;
+            int launched = 0;
+            cudaEvent_t prof_a = nullptr, prof_g0 = nullptr;
+            const long long prof_span = g_prof.enabled ? g_prof.next_span++ : 0;
+            if (g_prof.enabled) {
+                prof_a = g_prof.get();
+                cudaEventRecord(prof_a, st);
+            }
+            // AVS_PIPE_TRACE=1: timeline of the schedule on stderr (synchronises: a debugging aid)
+            static const bool ptrace = getenv("AVS_PIPE_TRACE") != nullptr;
+            static cudaEvent_t tev[1 + 2 * avs_model::PIPE_SEGS] = {};
+            if (ptrace) {
+                if (!tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+                cudaEventRecord(tev[0], st);
+            }
+            for (int k = 0; k < G && rc == AVS_OK; ++k) {
+                cudaStream_t ps = k ? m->pipe_stream[k] : st;
+                const int64_t r0 = glo[k], Rc = ghi[k] - r0;
+                if (k && stagger_each && k >= 2) {
+                    launch_stagger(m->pipe_stream[0], 1500);
+                    cudaEventRecord(m->ev_pipe_front[k], m->pipe_stream[0]);
+                }
+                if (k && cudaStreamWaitEvent(ps, m->ev_pipe_front[(stagger_each && k >= 2) ? k : 1], 0) != cudaSuccess) { rc = AVS_ERR_CUDA; break; }
+                ++launched;
+                const int smem_class = k < n_excl ? 1 : (k < n_excl + n_long ? long_kb * 1024 : 0);
+                rc = lstm_recurrence_tc_groups(xg_v, xg_a, xg_dt, m->whh, lb, k, k + 1, smem_class, act, fused, act, ps);
+                if (ptrace) cudaEventRecord(tev[1 + 2 * k], ps);
+                if (prof_a) {
+                    cudaEvent_t b = g_prof.get();
+                    cudaEventRecord(b, ps);
+                    g_prof.pending.push_back({ST_LSTM, prof_a, b, prof_span});
+                    if (k == 0) prof_g0 = b;
+                }
+                // SMs the longer groups' recurrences still hold when this group's tail runs (the groups behind it
+                // have finished): 32 for an exclusive group, up to 32 for a shared one (its 32 CTAs are spread)
+                const int free_sms = std::max(sms - 32 * k, 20);
+                GemmEpilogue e3;
+                e3.bias = m->in_b + 2 * E;
+                e3.C = ctx + r0 * E * asz;
+                e3.ldc = E;
+                e3.out_dtype = act;
+                e3.max_ctas = k ? free_sms : 0;
+                e3.prefer_pairs = 1;
+                if (rc == AVS_OK)
+                    rc = run_gemm(precision, fused + r0 * E * asz, act, E, w_in, 2ll * E * E, E, Rc, E, E, e3, ps);
+                GemmEpilogue e5 = e3;
+                e5.bias = m->out_b;
+                e5.C = attn_out + r0 * E * asz;
+                if (rc == AVS_OK) rc = run_gemm(precision, ctx + r0 * E * asz, act, E, w_out, 0, E, Rc, E, E, e5, ps);
+                GemmEpilogue e6;
+                e6.bias = m->sc0_b;
+                e6.relu = 1;
+                e6.score_w2 = m->sc2_w;
+                e6.score_b2 = m->sc2_b;
+                e6.scores = scores_dev + r0;
+                e6.max_ctas = k ? free_sms : 0;
+                if (rc == AVS_OK) rc = run_gemm(precision, attn_out + r0 * E * asz, act, E, w_sc0, 0, E, Rc, 64, E, e6, ps);
+                if (ptrace) cudaEventRecord(tev[2 + 2 * k], ps);
+                if (k) cudaEventRecord(m->ev_pipe_done[k], ps);
+            }
+            // join every forked stream, also after an error (pipe_stream[0] only ran the stagger kernel, which the
+            // other streams waited for)
+            for (int k = 1; k < launched; ++k) cudaStreamWaitEvent(st, m->ev_pipe_done[k], 0);
+            if (launched < 2) cudaStreamWaitEvent(st, m->ev_pipe_front[1], 0);
+            if (prof_g0) {
+                cudaEvent_t e = g_prof.get();
+                cudaEventRecord(e, st);
+                g_prof.pending.push_back({ST_TAIL_EXPOSED, prof_g0, e, 0});
+            }
+            if (rc != AVS_OK) return rc;
+            if (ptrace) {
+                cudaDeviceSynchronize();
+                fprintf(stderr, "[pipe tail] group: rows, recurrence done / tail done (us after the front)\n");
+                for (int k = 0; k < G; ++k) {
+                    float a = 0.f, b = 0.f;
+                    cudaEventElapsedTime(&a, tev[0], tev[1 + 2 * k]);
+                    cudaEventElapsedTime(&b, tev[0], tev[2 + 2 * k]);
+                    fprintf(stderr, "  g%d: %6lld rows, maxT %4d  %7.1f / %7.1f\n", k, static_cast<long long>(ghi[k] - glo[k]),
+                            plan.host[2 * slots_all + k], a * 1e3f, b * 1e3f);
+                }
+            }
+        }
+    }
+    if (tail_done) return AVS_OK;
 
     // ---- K2b: recurrences; writes [v_fwd | v_bwd | a_fwd | a_bwd] = torch.cat of av_model.py:43
     if (!pipelined) {

@@ -105,6 +105,10 @@ struct GemmEpilogue {
     // GPU is known to be occupied by concurrently running recurrence clusters: CTAs of a statically scheduled
     // persistent kernel that cannot be placed at once would delay their share of the tiles.
     int max_ctas = 0;
+    // host-side launch hint: take the CTA-pair kernel (256 x 256 tiles) even when the pair tiles do not fill the GPU --
+    // for GEMMs over a group's rows that run beside other work, where the 128 x 128 tiles' operand traffic (125 B/clk/SM
+    // against the 42.6 the L2 delivers) costs more than the unbalanced last round of wide tiles
+    int prefer_pairs = 0;
 };
 
 // tcgen05 / TMA path.  in_dtype: DT_F32 (kind::tf32), DT_F16 or DT_BF16 (kind::f16).
@@ -154,6 +158,10 @@ avs_status lstm_recurrence_tc_groups(const void* xg_v, const void* xg_a, int xg_
                                      const LstmBatch& batch, int g_lo, int g_hi, int exclusive, int op_dtype, void* fused,
                                      int out_dtype, cudaStream_t stream);
 int lstm_exclusive_groups(int n_groups);
+// Holds `stream` for ~ns nanoseconds (one sleeping thread).  Orders the PLACEMENT of kernels that become eligible at the
+// same moment on different streams: SM-exclusive recurrence CTAs need EMPTY SMs, so they must be placed before the
+// shared CTAs of the other groups spread over every SM (otherwise the longest chain waits for whole groups to finish).
+avs_status launch_stagger(cudaStream_t stream, unsigned int ns);
 
 // BPTT through the four recurrences (CUDA-core fp32, cluster of 8 CTAs, DSMEM reduce-scatter of dh):
 // d_fused [rows, 1024] -> d_xg_v / d_xg_a [rows, 2048] (gate gradients in the packed column order of xg).

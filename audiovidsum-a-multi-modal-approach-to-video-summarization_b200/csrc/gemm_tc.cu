@@ -741,7 +741,7 @@ avs_status gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, int i
     static const bool no_pairs = getenv("AVS_GEMM_1CTA") != nullptr;
     static const int pair_min = getenv("AVS_GEMM_PAIR_MIN") ? atoi(getenv("AVS_GEMM_PAIR_MIN")) : 2 * 74;   // test hook
     const int64_t pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / 256);
-    if (!no_pairs && N % 256 == 0 && epi.scores == nullptr && pair_tiles >= pair_min)
+    if (!no_pairs && N % 256 == 0 && epi.scores == nullptr && pair_tiles >= (epi.prefer_pairs ? 1 : pair_min))
         return gemm_tc2(A, lda, W, ldw, in_dtype, M, N, K, epi, stream);
 
     CUtensorMap tmA, tmB, tmC;

@@ -517,6 +517,31 @@ def run_infer(args, rank, world, local_rank):
     _cabi.profile(0)
     ms_local = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     ms_per_step = max_over_ranks([ms_local], dev, world, dist)[0]
+    # The timed step runs the pipelined tail (every group's value projection / out_proj / score head behind its own
+    # recurrence, on the SMs the shorter groups have left): its stage timers see the recurrence stage (front done ->
+    # last group's recurrence done) and the tail that remains behind the longest recurrence, not the individual tail
+    # GEMMs, which overlap the recurrences.  Those are timed in a second, untimed-for-the-metric pass over the same
+    # batch in the one-launch schedule (AVS_PIPE_TAIL=0: all recurrences, then each GEMM over all rows).
+    stage_seq, seq_ms = None, None
+    if stage_ms.get("tail_behind_longest_recurrence", (0.0, 0))[1] > 0:
+        os.environ["AVS_PIPE_TAIL"] = "0"
+        try:
+            for _ in range(3):
+                step_device()
+            torch.cuda.synchronize()
+            _cabi.profile(2)
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a, b in ev2:
+                flush.fill_(1)
+                a.record()
+                step_device()
+                b.record()
+            torch.cuda.synchronize()
+            stage_seq = _cabi.profile_read()
+            _cabi.profile(0)
+            seq_ms = sum(a.elapsed_time(b) for a, b in ev2) / args.steps
+        finally:
+            os.environ.pop("AVS_PIPE_TAIL", None)
     scores_timed = out_dev[0].cpu()
     picks_timed, cps_start_timed = out_dev[1].cpu().numpy(), out_dev[2]
 
@@ -597,6 +622,13 @@ def run_infer(args, rank, world, local_rank):
     mean_T = float(np.mean([t * t for t in lens]) / np.mean(lens))  # frame-weighted mean length
     flops = stage_flops_per_frame(axis, mean_T)
     kernels = kernel_table(stage_ms, args.steps, flops, R, peaks, 8 * R + 16 * sum(len(c) for c in cps_list))
+    if stage_seq is not None:
+        seq_tab = kernel_table(stage_seq, args.steps, flops, R, peaks, 8 * R + 16 * sum(len(c) for c in cps_list))
+        for name, rec in seq_tab.items():
+            if name not in kernels:
+                rec["schedule"] = "one-launch pass (AVS_PIPE_TAIL=0), overlapped with the recurrences in the timed step"
+                kernels[name] = rec
+        kernels["lstm_recurrence"]["one_launch_schedule_ms_per_step"] = seq_tab["lstm_recurrence"]["ms_per_step"]
     roofline = roofline_of(kernels, ms_per_step, peaks, world)
     # the whole step against both rooflines: algorithmic FLOP of the layers the step executes and the
     # algorithmic bytes of its inputs / outputs (features read once, one score per frame, weights once per step)
@@ -644,6 +676,10 @@ def run_infer(args, rank, world, local_rank):
         "kernels": kernels,
         "whole_step": whole_step,
         "wall_s_timed_region": wall,
+        "schedule": ({"timed_step": "pipelined tail: per recurrence group, recurrence -> value projection -> out_proj -> "
+                                    "score head on the group's own stream (bit-identical scores)",
+                      "one_launch_schedule_ms_per_step": seq_ms} if seq_ms is not None else
+                     {"timed_step": "one launch per stage over all rows"}),
         "comm": {"backend": "nccl" if world > 1 else None, "nranks": world,
                  "collective": "all_gather_into_tensor of the keyshot picks, once per step" if world > 1 else None},
     }
