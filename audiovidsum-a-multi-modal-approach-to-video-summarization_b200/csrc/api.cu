@@ -1449,7 +1449,8 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
     const char* const pipe_tail_env = getenv("AVS_PIPE_TAIL");   // read per call: the tests toggle it
     const int pipe_tail = pipe_tail_env ? atoi(pipe_tail_env) : 1;
     bool tail_done = false;
-    if (!pipelined && pipe_tail && !simt && literal_rows && space == AVS_DEVICE && arena == nullptr && lstm_excl == 0 &&
+    const bool tail_temporal = attn_axis == AVS_ATTN_TEMPORAL && tc_attn;
+    if (!pipelined && pipe_tail && !simt && (literal_rows || tail_temporal) && space == AVS_DEVICE && arena == nullptr && lstm_excl == 0 &&
         plan.nb == 8 && plan.n_groups >= 3 && plan.n_groups <= avs_model::PIPE_SEGS && owned_rows == total_rows) {
         std::vector<int64_t> glo, ghi;
         if (group_row_ranges(plan, R, glo, ghi)) {
@@ -1464,6 +1465,29 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
             const bool stagger_each = getenv("AVS_PIPE_STAGGER_ONCE") == nullptr;
             const int sms = device_sm_count();
             LstmBatch lb{plan_dev, plan_dev + slots_all, plan_dev + 2 * slots_all, G, plan.nb, 0};
+            // temporal attention: one descriptor table in PLAN order (group by group), so that the videos of a group
+            // are a contiguous range of it; the attention core of a group is one launch over that range
+            std::vector<int> seq_off(G + 1, 0);
+            if (tail_temporal) {
+                int n_sq = 0;
+                for (int i = 0; i < slots_all; ++i) n_sq += plan.host[slots_all + i] > 0;
+                std::vector<int32_t> sd(3 * static_cast<size_t>(n_sq));
+                int q = 0;
+                for (int k = 0; k < G; ++k) {
+                    seq_off[k] = q;
+                    for (int i = 0; i < plan.nb; ++i) {
+                        const int32_t len = plan.host[slots_all + k * plan.nb + i];
+                        if (len <= 0) continue;
+                        sd[q] = plan.host[k * plan.nb + i];
+                        sd[n_sq + q] = 1;
+                        sd[2 * n_sq + q] = len;
+                        ++q;
+                    }
+                }
+                seq_off[G] = q;
+                AVS_CHECK(n_sq <= std::max(n_seqs, 1), AVS_ERR_INVALID, "pipelined tail: descriptor table too small");
+                AVS_TRY(upload_small(seq_dev, sd.data(), sd.size() * 4, st));
+            }
             // The longest group runs on the caller's stream itself: its recurrence follows the front without an event
             // hop and its SM-exclusive CTAs are placed first (exclusive CTAs need EMPTY SMs; were the 192 shared CTAs
             // of the other groups placed first, one on every SM, the longest chain would wait for the shortest group
@@ -1516,8 +1540,20 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 e3.out_dtype = act;
                 e3.max_ctas = k ? free_sms : 0;
                 e3.prefer_pairs = 1;
-                if (rc == AVS_OK)
+                if (tail_temporal) {   // q | k | v projection of the group's rows, then the attention core of its videos
+                    GemmEpilogue eq = e3;
+                    eq.bias = m->in_b;
+                    eq.C = qkv + r0 * 3 * E * dtype_size(qkv_dt);
+                    eq.ldc = 3 * E;
+                    eq.out_dtype = qkv_dt;
+                    if (rc == AVS_OK) rc = run_gemm(precision, fused + r0 * E * asz, act, E, w_in, 0, E, Rc, 3 * E, E, eq, ps);
+                    const int n_sq = seq_off[G];
+                    SeqDesc sq{seq_dev + seq_off[k], seq_dev + n_sq + seq_off[k], seq_dev + 2 * n_sq + seq_off[k],
+                               seq_off[k + 1] - seq_off[k], plan.host[2 * slots_all + k]};
+                    if (rc == AVS_OK) rc = attention_tc(qkv, act, R, E, m->heads, sq, ctx, E, act, 0, ps);
+                } else if (rc == AVS_OK) {
                     rc = run_gemm(precision, fused + r0 * E * asz, act, E, w_in, 2ll * E * E, E, Rc, E, E, e3, ps);
+                }
                 GemmEpilogue e5 = e3;
                 e5.bias = m->out_b;
                 e5.C = attn_out + r0 * E * asz;

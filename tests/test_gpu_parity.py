@@ -1248,10 +1248,11 @@ def test_fp16_range_watch_reports_clamped_activations(native):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("axis", ["literal_b1", "temporal"])
 @pytest.mark.parametrize("n_videos", [17, 50, 64])
-def test_pipelined_tail_is_bit_identical(native, n_videos):
-    """Device-resident batches ordered longest video first run the row-parallel tail (value projection, out_proj,
-    score head) group by group behind each group's recurrence (AVS_PIPE_TAIL, on by default).  That only changes WHEN
+def test_pipelined_tail_is_bit_identical(native, n_videos, axis):
+    """Device-resident batches ordered longest video first run the tail (value projection -- or q | k | v projection and
+    the attention core over the group's videos --, out_proj, score head) group by group behind each group's recurrence (AVS_PIPE_TAIL, on by default).  That only changes WHEN
     and over which row range the GEMMs are launched: the scores must equal the one-launch schedule bit for bit, for 3
     to 8 recurrence groups, and an unordered batch (which falls back to the one-launch schedule) must agree per video."""
     rng = np.random.default_rng(n_videos)
@@ -1264,10 +1265,10 @@ def test_pipelined_tail_is_bit_identical(native, n_videos):
     ad = torch.cat([v.audio for v in vids]).cuda()
     try:
         os.environ["AVS_PIPE_TAIL"] = "0"
-        want = native.forward_rows(vd, ad, starts, lens, "literal_b1", "tf32").clone()
+        want = native.forward_rows(vd, ad, starts, lens, axis, "tf32").clone()
         os.environ["AVS_PIPE_TAIL"] = "1"
         for _ in range(3):
-            got = native.forward_rows(vd, ad, starts, lens, "literal_b1", "tf32")
+            got = native.forward_rows(vd, ad, starts, lens, axis, "tf32")
             torch.cuda.synchronize()
             assert torch.equal(got, want)
         # the same videos in a shuffled order: groups are no longer contiguous row blocks -> one-launch schedule
@@ -1276,7 +1277,7 @@ def test_pipelined_tail_is_bit_identical(native, n_videos):
         ad2 = torch.cat([vids[i].audio for i in perm]).cuda()
         lens2 = [lens[i] for i in perm]
         starts2 = np.concatenate([[0], np.cumsum(lens2)[:-1]]).astype(np.int32)
-        got2 = native.forward_rows(vd2, ad2, starts2, lens2, "literal_b1", "tf32")
+        got2 = native.forward_rows(vd2, ad2, starts2, lens2, axis, "tf32")
         torch.cuda.synchronize()
         for j, i in enumerate(perm):
             assert torch.equal(got2[starts2[j]:starts2[j] + lens2[j]], want[starts[i]:starts[i] + lens[i]])
