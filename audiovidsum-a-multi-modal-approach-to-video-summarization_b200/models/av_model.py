@@ -182,12 +182,18 @@ class AVBiLSTMModel(nn.Module):
         is "literal" (each video scored as the reference's B=1 call), else the model's.
         """
         axis = attn_axis or ("literal_b1" if self.attn_axis == "literal" else self.attn_axis)
-        lens = [int(v.shape[0]) for v, _ in videos]
+        # packed longest video first (the order data.dataset.packed_batches produces): the recurrence groups then own
+        # contiguous row blocks and the native call runs each group's tail behind its own recurrence
+        order = sorted(range(len(videos)), key=lambda i: -int(videos[i][0].shape[0]))
+        lens = [int(videos[i][0].shape[0]) for i in order]
         starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32) if lens else np.zeros(0, np.int32)
-        visual = torch.cat([v for v, _ in videos], dim=0)
-        audio = torch.cat([a for _, a in videos], dim=0)
+        visual = torch.cat([videos[i][0] for i in order], dim=0)
+        audio = torch.cat([videos[i][1] for i in order], dim=0)
         rows = self.native().forward_rows(visual, audio, starts, lens, axis, self.precision)
-        return list(torch.split(rows, lens))
+        out = [None] * len(videos)
+        for i, piece in zip(order, torch.split(rows, lens)):
+            out[i] = piece
+        return out
 
 
 # names used by BASELINE.json's north_star and by the reference's scripts/train.py:4

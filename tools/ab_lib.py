@@ -4,6 +4,7 @@ events inside the library) once per library, alternating, in fresh processes.
     python tools/ab_lib.py build/libavsum_b200_old.so [more.so ...] [n_videos ...]
 """
 import os, subprocess, sys
+os.environ.setdefault("AVS_PIPE_TAIL", "0")   # per-stage times / single launches: the one-launch schedule
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CHILD = r'''

@@ -3,6 +3,7 @@ Reports attention-only and full-forward numbers (CUDA events inside the library)
 attention core against the numpy oracle on one (video, head)."""
 import json
 import os
+os.environ.setdefault("AVS_PIPE_TAIL", "0")   # per-stage times / single launches: the one-launch schedule
 import sys
 
 import numpy as np

@@ -8,6 +8,7 @@ for a drained accumulator, the producer's wait for free stages and the epilogue'
 """
 import ctypes as C
 import os
+os.environ.setdefault("AVS_PIPE_TAIL", "0")   # per-stage times / single launches: the one-launch schedule
 import sys
 
 import numpy as np

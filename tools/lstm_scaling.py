@@ -1,6 +1,7 @@
 """LSTM recurrence time vs number of videos at (almost) fixed max length: is a step bound by its own dependency
 chain or by contention between the chains that share an SM?"""
 import os, sys
+os.environ.setdefault("AVS_PIPE_TAIL", "0")   # per-stage times / single launches: the one-launch schedule
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -4,6 +4,7 @@
 """
 import ctypes as C
 import os
+os.environ.setdefault("AVS_PIPE_TAIL", "0")   # per-stage times / single launches: the one-launch schedule
 import sys
 
 os.environ["AVS_LSTM_TRACE"] = "1"

@@ -4,6 +4,7 @@ the attention core's capture.
     python tools/prof_long.py [n_videos] [T] [n_forwards]
 """
 import os
+os.environ.setdefault("AVS_PIPE_TAIL", "0")   # per-stage times / single launches: the one-launch schedule
 import sys
 
 import torch
