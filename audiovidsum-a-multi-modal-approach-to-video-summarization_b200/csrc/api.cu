@@ -301,7 +301,7 @@ struct avs_model {
     // projections of its rows exist, while the GEMMs of the following groups still run
     static constexpr int PIPE_SEGS = 8;
     cudaStream_t pipe_stream[PIPE_SEGS] = {};
-    cudaEvent_t ev_pipe_front[PIPE_SEGS] = {}, ev_pipe_done[PIPE_SEGS] = {};
+    cudaEvent_t ev_pipe_front[PIPE_SEGS] = {}, ev_pipe_done[PIPE_SEGS] = {}, ev_pipe_rec[PIPE_SEGS] = {};
 };
 
 namespace {
@@ -752,6 +752,7 @@ avs_status avs_model_create(const avs_weights* w, int device, avs_model** out) {
             ce = cudaStreamCreateWithPriority(&m->pipe_stream[i], cudaStreamNonBlocking, prio_hi);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_pipe_front[i], cudaEventDisableTiming);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_pipe_done[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_pipe_rec[i], cudaEventDisableTiming);
         }
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&m->sum_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_sum_out, cudaEventDisableTiming);
@@ -828,6 +829,7 @@ void avs_model_destroy(avs_model* m) {
         if (m->pipe_stream[i]) cudaStreamDestroy(m->pipe_stream[i]);
         if (m->ev_pipe_front[i]) cudaEventDestroy(m->ev_pipe_front[i]);
         if (m->ev_pipe_done[i]) cudaEventDestroy(m->ev_pipe_done[i]);
+        if (m->ev_pipe_rec[i]) cudaEventDestroy(m->ev_pipe_rec[i]);
     }
     for (int i = 0; i < avs_model::MAX_CHUNKS; ++i) {
         if (m->branch_stream[i]) cudaStreamDestroy(m->branch_stream[i]);
@@ -1456,10 +1458,7 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
         if (group_row_ranges(plan, R, glo, ghi)) {
             tail_done = true;
             const int G = plan.n_groups, slots_all = G * plan.nb;
-            int n_excl = lstm_exclusive_groups(G);
-            if (const char* e = getenv("AVS_PIPE_EXCL")) n_excl = atoi(e);
-            const int n_long = getenv("AVS_PIPE_LONG") ? atoi(getenv("AVS_PIPE_LONG")) : 0;
-            const int long_kb = getenv("AVS_PIPE_LONG_KB") ? atoi(getenv("AVS_PIPE_LONG_KB")) : 120;
+            const int n_excl = lstm_exclusive_groups(G);
             // groups 2.. each start behind one more short stagger kernel, so that the groups are placed in order of
             // length (measured: 0.685 vs 0.695 ms per config-2 forward; AVS_PIPE_STAGGER_ONCE=1: one stagger for all)
             const bool stagger_each = getenv("AVS_PIPE_STAGGER_ONCE") == nullptr;
@@ -1512,17 +1511,17 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 if (!tev[0]) for (auto& e : tev) cudaEventCreate(&e);
                 cudaEventRecord(tev[0], st);
             }
+            // Phase 1: every group's recurrence on its own stream, placed in order of length.
             for (int k = 0; k < G && rc == AVS_OK; ++k) {
                 cudaStream_t ps = k ? m->pipe_stream[k] : st;
-                const int64_t r0 = glo[k], Rc = ghi[k] - r0;
-                if (k && stagger_each && k >= 2) {
+                if (stagger_each && k >= 2) {
                     launch_stagger(m->pipe_stream[0], 1500);
                     cudaEventRecord(m->ev_pipe_front[k], m->pipe_stream[0]);
                 }
                 if (k && cudaStreamWaitEvent(ps, m->ev_pipe_front[(stagger_each && k >= 2) ? k : 1], 0) != cudaSuccess) { rc = AVS_ERR_CUDA; break; }
                 ++launched;
-                const int smem_class = k < n_excl ? 1 : (k < n_excl + n_long ? long_kb * 1024 : 0);
-                rc = lstm_recurrence_tc_groups(xg_v, xg_a, xg_dt, m->whh, lb, k, k + 1, smem_class, act, fused, act, ps);
+                rc = lstm_recurrence_tc_groups(xg_v, xg_a, xg_dt, m->whh, lb, k, k + 1, k < n_excl ? 1 : 0, act, fused, act, ps);
+                cudaEventRecord(m->ev_pipe_rec[k], ps);
                 if (ptrace) cudaEventRecord(tev[1 + 2 * k], ps);
                 if (prof_a) {
                     cudaEvent_t b = g_prof.get();
@@ -1530,8 +1529,24 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                     g_prof.pending.push_back({ST_LSTM, prof_a, b, prof_span});
                     if (k == 0) prof_g0 = b;
                 }
-                // SMs the longer groups' recurrences still hold when this group's tail runs (the groups behind it
-                // have finished): 32 for an exclusive group, up to 32 for a shared one (its 32 CTAs are spread)
+            }
+            // Phase 2: the tails, one per SEGMENT of groups.  A segment is one group, except that groups expected to
+            // finish about when the longest one does share ITS tail: a step of a group on shared SMs takes ~1.16x a
+            // step on exclusive SMs (0.78 vs 0.67 us), so a group whose longest video has >= 0.86x the steps of the
+            // longest group's ends no earlier -- its own tail would run beside the longest group's, both on half a GPU
+            // with a partly filled last round of tiles each (measured, config 2: 69 + 57 us side by side).
+            static const bool no_merge = getenv("AVS_PIPE_NO_MERGE") != nullptr;
+            int seg_end0 = 1;   // groups [0, seg_end0) share the first tail
+            if (!no_merge && n_excl >= 1)
+                while (seg_end0 < G && seg_end0 >= n_excl &&
+                       plan.host[2 * slots_all + seg_end0] * 100ll >= plan.host[2 * slots_all] * 86ll) ++seg_end0;
+            for (int k = 0; k < launched && rc == AVS_OK; k = (k == 0 ? seg_end0 : k + 1)) {
+                const int k_hi = std::min(launched, k == 0 ? seg_end0 : k + 1);
+                cudaStream_t ps = k ? m->pipe_stream[k] : st;
+                for (int j = k + 1; j < k_hi; ++j) cudaStreamWaitEvent(ps, m->ev_pipe_rec[j], 0);
+                const int64_t r0 = glo[k], Rc = ghi[k_hi - 1] - r0;
+                // SMs the longer groups' recurrences still hold when this tail runs (the groups behind it have
+                // finished): 32 for an exclusive group, up to 32 for a shared one (its 32 CTAs are spread)
                 const int free_sms = std::max(sms - 32 * k, 20);
                 GemmEpilogue e3;
                 e3.bias = m->in_b + 2 * E;
@@ -1540,18 +1555,18 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 e3.out_dtype = act;
                 e3.max_ctas = k ? free_sms : 0;
                 e3.prefer_pairs = 1;
-                if (tail_temporal) {   // q | k | v projection of the group's rows, then the attention core of its videos
+                if (tail_temporal) {   // q | k | v projection of the segment's rows, then the attention core of its videos
                     GemmEpilogue eq = e3;
                     eq.bias = m->in_b;
                     eq.C = qkv + r0 * 3 * E * dtype_size(qkv_dt);
                     eq.ldc = 3 * E;
                     eq.out_dtype = qkv_dt;
-                    if (rc == AVS_OK) rc = run_gemm(precision, fused + r0 * E * asz, act, E, w_in, 0, E, Rc, 3 * E, E, eq, ps);
+                    rc = run_gemm(precision, fused + r0 * E * asz, act, E, w_in, 0, E, Rc, 3 * E, E, eq, ps);
                     const int n_sq = seq_off[G];
                     SeqDesc sq{seq_dev + seq_off[k], seq_dev + n_sq + seq_off[k], seq_dev + 2 * n_sq + seq_off[k],
-                               seq_off[k + 1] - seq_off[k], plan.host[2 * slots_all + k]};
+                               seq_off[k_hi] - seq_off[k], plan.host[2 * slots_all + k]};
                     if (rc == AVS_OK) rc = attention_tc(qkv, act, R, E, m->heads, sq, ctx, E, act, 0, ps);
-                } else if (rc == AVS_OK) {
+                } else {
                     rc = run_gemm(precision, fused + r0 * E * asz, act, E, w_in, 2ll * E * E, E, Rc, E, E, e3, ps);
                 }
                 GemmEpilogue e5 = e3;
@@ -1566,9 +1581,10 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                 e6.scores = scores_dev + r0;
                 e6.max_ctas = k ? free_sms : 0;
                 if (rc == AVS_OK) rc = run_gemm(precision, attn_out + r0 * E * asz, act, E, w_sc0, 0, E, Rc, 64, E, e6, ps);
-                if (ptrace) cudaEventRecord(tev[2 + 2 * k], ps);
-                if (k) cudaEventRecord(m->ev_pipe_done[k], ps);
+                if (ptrace)
+                    for (int j = k; j < k_hi; ++j) cudaEventRecord(tev[2 + 2 * j], ps);
             }
+            for (int k = 1; k < launched; ++k) cudaEventRecord(m->ev_pipe_done[k], m->pipe_stream[k]);
             // join every forked stream, also after an error (pipe_stream[0] only ran the stagger kernel, which the
             // other streams waited for)
             for (int k = 1; k < launched; ++k) cudaStreamWaitEvent(st, m->ev_pipe_done[k], 0);

@@ -1,20 +1,15 @@
 #!/bin/bash
-# sweep of the pipelined-tail placement knobs (config 2, device-resident forward)
+# A/B of the pipelined-tail variants (config 2, device-resident forward): tools/ab_pipe_sweep.sh
 O=gpurun_out/ab_pipe_sweep.log
 : > $O
-run() { echo "== $*" >> $O; env "$@" python tools/ab_pipe_tail.py 30 literal_b1 1 2>&1 | grep -v sorted >> $O; }
-run AVS_PIPE_TAIL=0
+run() { echo "== $*" >> $O; env "$@" python tools/ab_pipe_tail.py 30 ${AXIS:-literal_b1} 1 2>&1 | grep -v sorted >> $O; }
+run AVS_PIPE_NO_MERGE=1
 run AVS_X=1
-run AVS_PIPE_EXCL=2
-run AVS_PIPE_EXCL=2 AVS_PIPE_STAGGER_EACH=1
-run AVS_PIPE_LONG=1
-run AVS_PIPE_LONG=2
-run AVS_PIPE_LONG=3
-run AVS_PIPE_LONG=3 AVS_PIPE_STAGGER_EACH=1
-run AVS_PIPE_STAGGER_EACH=1
-run AVS_PIPE_EXCL=0 AVS_PIPE_LONG=4
-echo "== trace EXCL=2 STAGGER_EACH" >> $O
-AVS_PIPE_TRACE=1 AVS_PIPE_EXCL=2 AVS_PIPE_STAGGER_EACH=1 python tools/ab_pipe_tail.py 2 literal_b1 1 2>&1 | tail -12 >> $O
-echo "== trace LONG=3" >> $O
-AVS_PIPE_TRACE=1 AVS_PIPE_LONG=3 python tools/ab_pipe_tail.py 2 literal_b1 1 2>&1 | tail -12 >> $O
+run AVS_PIPE_NO_MERGE=1
+run AVS_X=1
+AXIS=temporal run AVS_PIPE_NO_MERGE=1
+AXIS=temporal run AVS_X=1
+echo "== trace" >> $O
+AVS_PIPE_TRACE=1 python tools/ab_pipe_tail.py 2 literal_b1 1 2>&1 | tail -10 >> $O
+python -m pytest tests -m gpu -x -q -k "pipelined_tail" 2>&1 | tail -2 >> $O
 cat $O
