@@ -912,7 +912,12 @@ static avs_status forward_entry(avs_model* m, const float* visual, const float* 
             std::vector<int32_t> prs(n_videos), desc(3 * static_cast<size_t>(n_videos));
             int64_t at = 0;
             int max_len = 0;
-            for (int b = 0; b < n_videos; ++b) {
+            // packed longest video first (the order of the recurrence groups): every group then owns one contiguous
+            // block of packed rows, which is what the pipelined tail of the forward needs
+            std::vector<int> pack_order(n_videos);
+            for (int b = 0; b < n_videos; ++b) pack_order[b] = b;
+            std::stable_sort(pack_order.begin(), pack_order.end(), [&](int x, int y) { return lengths[x] > lengths[y]; });
+            for (int b : pack_order) {
                 prs[b] = static_cast<int32_t>(at);
                 desc[b] = row_start[b];
                 desc[n_videos + b] = prs[b];
