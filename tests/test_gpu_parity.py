@@ -1266,11 +1266,21 @@ def test_pipelined_tail_is_bit_identical(native, n_videos, axis):
     try:
         os.environ["AVS_PIPE_TAIL"] = "0"
         want = native.forward_rows(vd, ad, starts, lens, axis, "tf32").clone()
-        os.environ["AVS_PIPE_TAIL"] = "1"
+        os.environ["AVS_PIPE_TAIL"] = "2"   # forced (1 = the default: only when the groups' lengths differ or the batch is long)
         for _ in range(3):
             got = native.forward_rows(vd, ad, starts, lens, axis, "tf32")
             torch.cuda.synchronize()
             assert torch.equal(got, want)
+        # equally long videos (the default schedule leaves these alone): forced, 12 videos = 3 groups of 4
+        eq_lens = [200] * 12
+        eq_starts = (np.arange(12) * 200).astype(np.int32)
+        os.environ["AVS_PIPE_TAIL"] = "0"
+        want_eq = native.forward_rows(vd[:2400], ad[:2400], eq_starts, eq_lens, axis, "tf32").clone()
+        os.environ["AVS_PIPE_TAIL"] = "2"
+        got_eq = native.forward_rows(vd[:2400], ad[:2400], eq_starts, eq_lens, axis, "tf32")
+        torch.cuda.synchronize()
+        assert torch.equal(got_eq, want_eq)
+        os.environ["AVS_PIPE_TAIL"] = "1"
         # the same videos in a shuffled order: groups are no longer contiguous row blocks -> one-launch schedule
         perm = rng.permutation(n_videos)
         vd2 = torch.cat([vids[i].visual for i in perm]).cuda()
