@@ -1551,8 +1551,12 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
             if (!no_merge && n_excl >= 1)
                 while (seg_end0 < G && seg_end0 >= n_excl &&
                        plan.host[2 * slots_all + seg_end0] * 100ll >= plan.host[2 * slots_all] * 86ll) ++seg_end0;
-            for (int k = 0; k < launched && rc == AVS_OK; k = (k == 0 ? seg_end0 : k + 1)) {
-                const int k_hi = std::min(launched, k == 0 ? seg_end0 : k + 1);
+            std::vector<std::pair<int, int>> segs;   // [first group, end group) of every tail
+            for (int k = 0; k < launched; k = segs.back().second) {
+                segs.push_back({k, std::min(launched, k == 0 ? seg_end0 : k + 1)});
+            }
+            for (size_t si = 0; si < segs.size() && rc == AVS_OK; ++si) {
+                const int k = segs[si].first, k_hi = segs[si].second;
                 cudaStream_t ps = k ? m->pipe_stream[k] : st;
                 for (int j = k + 1; j < k_hi; ++j) cudaStreamWaitEvent(ps, m->ev_pipe_rec[j], 0);
                 const int64_t r0 = glo[k], Rc = ghi[k_hi - 1] - r0;
