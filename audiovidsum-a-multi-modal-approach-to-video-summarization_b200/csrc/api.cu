@@ -1441,13 +1441,13 @@ static avs_status forward_impl(avs_model* m, const float* visual, const float* a
                   "AVS_PREC_BF16 (fp32 exponent range)", host_cnt);
     }
 
-    // ---- pipelined tail (device-resident batches ordered longest video first, sequence-length-1 attention): the
-    // recurrence of a group lasts max(T of the group) dependent steps, so the groups finish one after the other,
+    // ---- pipelined tail (device-resident batches ordered longest video first; sequence-length-1 or temporal
+    // attention -- both work per video): the recurrence of a group lasts max(T of the group) dependent steps, so the groups finish one after the other,
     // shortest first, and the SMs of a finished group stay idle until the longest group is done (config 2: 128 of 148
     // SMs hold recurrence CTAs, and the groups end between ~1/3 and all of the kernel's time).  Everything behind the
-    // recurrence is row-parallel (value projection, out_proj, score head: av_model.py:44-46 with sequence length 1),
-    // so each group's recurrence is launched on its own stream, followed on the same stream by the tail GEMMs of that
-    // group's rows: the tails of the shorter groups run on the SMs their recurrences have left while the longest
+    // recurrence is parallel over rows or videos (value projection -- or q | k | v projection + attention core --,
+    // out_proj, score head: av_model.py:44-46), so each group's recurrence is launched on its own stream, followed on the
+    // same stream by the tail of that group's rows: the tails of the shorter groups run on the SMs their recurrences have left while the longest
     // chain is still going, and only the tail of the longest group (~1/4 of the rows) remains after it.  Row r of a
     // GEMM is computed identically whatever the row range of the launch, so the scores are bit-identical to the
     // one-launch schedule.  Per-stage profiling (avs_profile) then reports the recurrence stage as front-done -> the

@@ -692,8 +692,9 @@ def run_infer(args, rank, world, local_rank):
         "kernels": kernels,
         "whole_step": whole_step,
         "wall_s_timed_region": wall,
-        "schedule": ({"timed_step": "pipelined tail: per recurrence group, recurrence -> value projection -> out_proj -> "
-                                    "score head on the group's own stream (bit-identical scores)",
+        "schedule": ({"timed_step": "pipelined tail: per recurrence group, recurrence -> attention (value projection, or "
+                                    "q|k|v projection + attention core over the group's videos) -> out_proj -> score head "
+                                    "on the group's own stream (scores bit-identical to the one-launch schedule)",
                       "one_launch_schedule_ms_per_step": seq_ms} if seq_ms is not None else
                      {"timed_step": "one launch per stage over all rows"}),
         "comm": {"backend": "nccl" if world > 1 else None, "nranks": world,
