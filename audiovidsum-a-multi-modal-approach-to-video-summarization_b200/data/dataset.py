@@ -118,14 +118,20 @@ class DeviceDataset:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         items = [dataset[i] for i in range(len(dataset))]
         self.lengths = np.asarray([int(f["visual"].shape[0]) for f, _ in items], dtype=np.int32)
-        self.row_start = np.concatenate([[0], np.cumsum(self.lengths)[:-1]]).astype(np.int32) if len(items) else \
-            np.zeros(0, np.int32)
+        # rows are laid out longest video first (each recurrence group then owns one block of rows: the native forward
+        # runs a group's tail behind its own recurrence); row_start / lengths stay indexed by dataset position
+        layout = sorted(range(len(items)), key=lambda i: -int(self.lengths[i]))
+        self.row_start = np.zeros(len(items), dtype=np.int32)
+        at = 0
+        for i in layout:
+            self.row_start[i] = at
+            at += int(self.lengths[i])
         if items:
-            self.visual = torch.cat([torch.as_tensor(f["visual"]).to(fdt) for f, _ in items]).to(dev)
-            self.audio = torch.cat([torch.as_tensor(f["audio"]).to(fdt) for f, _ in items]).to(dev)
+            self.visual = torch.cat([torch.as_tensor(items[i][0]["visual"]).to(fdt) for i in layout]).to(dev)
+            self.audio = torch.cat([torch.as_tensor(items[i][0]["audio"]).to(fdt) for i in layout]).to(dev)
             tgt = [torch.as_tensor(t).reshape(-1) for _, t in items]
             tdt = torch.float64 if any(t.dtype == torch.float64 for t in tgt) else torch.float32
-            self.scores = torch.cat([t.to(tdt) for t in tgt]).to(dev)
+            self.scores = torch.cat([tgt[i].to(tdt) for i in layout]).to(dev)
         else:
             self.visual = self.audio = self.scores = torch.zeros(0, device=dev)
         for n, (_, t) in zip(self.lengths, items):

@@ -47,6 +47,11 @@ def summarize_videos(model, videos, proportion=0.15, attn_axis: Optional[str] = 
     the two native calls -- or tensors already on the model's GPU.
     """
     nat = model.native()
+    # packed longest video first (the order data.dataset.packed_batches produces): the native call then pipelines
+    # host-space batches by video group and runs each recurrence group's tail behind its own recurrence; the results
+    # are handed back in the caller's order
+    caller_order = sorted(range(len(videos)), key=lambda i: -int(videos[i].visual.shape[0]))
+    videos = [videos[i] for i in caller_order]
     lens = [int(v.visual.shape[0]) for v in videos]
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
     visual = torch.cat([v.visual for v in videos], dim=0)
@@ -64,10 +69,10 @@ def summarize_videos(model, videos, proportion=0.15, attn_axis: Optional[str] = 
             visual, audio, positions, starts, lens, [v.n_frames for v in videos], [v.cps for v in videos], proportion,
             axis, model.precision)
     picks_h, mean_h, sum_h, scores_h = picks.cpu().numpy(), seg_mean.cpu().numpy(), summary.cpu().numpy(), scores.cpu()
-    out = []
+    out = [None] * len(videos)
     for i in range(len(videos)):
-        out.append(VideoSummary(scores_h[starts[i]:starts[i] + lens[i]], picks_h[cps_start[i]:cps_start[i + 1]],
-                                mean_h[cps_start[i]:cps_start[i + 1]], sum_h[sum_start[i]:sum_start[i + 1]]))
+        out[caller_order[i]] = VideoSummary(scores_h[starts[i]:starts[i] + lens[i]], picks_h[cps_start[i]:cps_start[i + 1]],
+                                            mean_h[cps_start[i]:cps_start[i + 1]], sum_h[sum_start[i]:sum_start[i + 1]])
     return out
 
 

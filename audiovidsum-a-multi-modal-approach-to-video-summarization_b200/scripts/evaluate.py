@@ -38,14 +38,22 @@ def evaluate(model, dataset, return_per_video: bool = False):
     for n, t in zip(lens, targets):
         if int(t.numel()) != n:
             raise ValueError("every video needs one target score per frame")
-    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    # rows are laid out longest video first (each recurrence group then owns one block of rows and the native call
+    # runs its tail behind its own recurrence); the descriptors -- and so the per-video metrics -- stay in dataset order
+    layout = sorted(range(len(lens)), key=lambda i: -lens[i])
+    starts = np.zeros(len(lens), dtype=np.int32)
+    at = 0
+    for i in layout:
+        starts[i] = at
+        at += lens[i]
     dev = next(model.parameters()).device
     with torch.no_grad():
         axis = "literal_b1" if model.attn_axis == "literal" else model.attn_axis
-        pred = model.native().forward_rows(torch.cat(visuals).to(dev), torch.cat(audios).to(dev), starts, lens, axis,
+        pred = model.native().forward_rows(torch.cat([visuals[i] for i in layout]).to(dev),
+                                           torch.cat([audios[i] for i in layout]).to(dev), starts, lens, axis,
                                            model.precision)
     tgt_dtype = torch.float64 if any(t.dtype == torch.float64 for t in targets) else torch.float32
-    target = torch.cat([t.to(tgt_dtype) for t in targets]).to(dev)
+    target = torch.cat([targets[i].to(tgt_dtype) for i in layout]).to(dev)
     return _metrics(pred, target, starts, lens, tgt_dtype, return_per_video)
 
 
