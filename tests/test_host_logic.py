@@ -179,3 +179,141 @@ def test_bench_global_batch_spec_matches_the_synthetic_configs():
     f = bench.stage_flops_per_frame("temporal", 400.0)
     assert f["frontend_lstm_pipelined"] == f["frontend_gemms"] + f["lstm_recurrence"]
     assert f["attention_core"] == 4 * 400.0 * 1024
+
+
+# ---- row layout of the callers (longest video first) against a stand-in for the native handle ---------------------
+# The callers below reorder the rows of a batch (so that every recurrence group owns one block of rows) while the
+# per-video descriptors and results stay in the caller's order.  That bookkeeping is host logic; it is checked here
+# with a stand-in for NativeModel whose "scores" are a row-local function of the features, so any mix-up between the
+# row layout and the descriptors shows.  (The GPU tests check the same callers against the oracle.)
+
+class _StubNative:
+    def __init__(self):
+        self.calls = []
+
+    @staticmethod
+    def _row_scores(visual, audio):
+        return (visual[:, 0].double() * 0.25 + audio[:, 0].double() * 0.5 + 0.125).float()
+
+    def forward_rows(self, visual, audio, row_start, lengths, attn_axis="literal", precision="tf32", out=None):
+        rs, ln = np.asarray(row_start, np.int64), np.asarray(lengths, np.int64)
+        # the descriptors must tile the rows exactly once, whatever the order of the videos
+        cover = np.zeros(visual.shape[0], np.int32)
+        for s, n in zip(rs, ln):
+            cover[s:s + n] += 1
+        assert np.all(cover == 1)
+        self.calls.append((rs.copy(), ln.copy(), attn_axis))
+        return self._row_scores(visual, audio)
+
+    def score_and_summarize_rows(self, visual, audio, positions, row_start, lengths, n_frames, cps_list,
+                                 proportion=0.15, attn_axis="literal_b1", precision="tf32"):
+        scores = self.forward_rows(visual, audio, row_start, lengths, attn_axis, precision)
+        rs, ln = np.asarray(row_start, np.int64), np.asarray(lengths, np.int64)
+        cps_start = np.concatenate([[0], np.cumsum([len(c) for c in cps_list])]).astype(np.int64)
+        sum_start = np.concatenate([[0], np.cumsum(n_frames)]).astype(np.int64)
+        picks = torch.zeros(int(cps_start[-1]), dtype=torch.uint8)
+        seg_mean = torch.zeros(int(cps_start[-1]), dtype=torch.int64)
+        summary = torch.zeros(int(sum_start[-1]), dtype=torch.uint8)
+        pos = positions.numpy()
+        for k in range(len(ln)):
+            tag = int(round(float(scores[rs[k]]) * 1e4))                 # a value only this video's rows produce
+            assert pos[rs[k]] == 0 and pos[rs[k] + ln[k] - 1] == (ln[k] - 1) * synth.SAMPLE_STRIDE
+            seg_mean[cps_start[k]:cps_start[k + 1]] = tag
+            picks[cps_start[k]:cps_start[k + 1]] = tag % 2
+            summary[sum_start[k]:sum_start[k + 1]] = tag % 251
+        return scores, picks, seg_mean, summary, cps_start, sum_start
+
+
+class _StubModel:
+    attn_axis = "literal"
+    precision = "tf32"
+
+    def __init__(self):
+        self.nat = _StubNative()
+
+    def native(self):
+        return self.nat
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter([torch.zeros(1)])
+
+
+def _mixed_videos(lengths, seed0=77):
+    return [synth.make_video(t, 16, 4, seed0 + i) for i, t in enumerate(lengths)]
+
+
+def test_summarize_videos_returns_results_in_the_callers_order():
+    from avsum_b200.evaluation.summary import summarize_videos
+    lengths = [9, 31, 9, 17, 40, 3, 17]                                  # unsorted, with ties
+    vids = _mixed_videos(lengths)
+    model = _StubModel()
+    res = summarize_videos(model, vids)
+    rs, ln, axis = model.nat.calls[0]
+    assert axis == "literal_b1" and list(ln) == sorted(lengths, reverse=True)      # packed longest first
+    assert list(rs) == list(np.concatenate([[0], np.cumsum(ln)[:-1]]))
+    for v, r in zip(vids, res):
+        want = _StubNative._row_scores(v.visual, v.audio)
+        assert torch.equal(torch.as_tensor(r.scores), want)
+        tag = int(round(float(want[0]) * 1e4))
+        assert r.picks.shape == (len(v.cps),) and np.all(r.seg_mean == tag) and np.all(r.picks == tag % 2)
+        assert r.summary.shape == (v.n_frames,) and np.all(r.summary == tag % 251)
+
+
+def test_score_videos_returns_scores_in_the_callers_order():
+    lengths = [5, 12, 5, 30, 1]
+    vids = _mixed_videos(lengths, seed0=5)
+    model = AVBiLSTMModel(16, 4, 512)
+    stub = _StubNative()
+    model.native = lambda for_training=False: stub
+    out = model.score_videos([(v.visual, v.audio) for v in vids])
+    assert list(stub.calls[0][1]) == sorted(lengths, reverse=True)
+    for v, s in zip(vids, out):
+        assert torch.equal(s, _StubNative._row_scores(v.visual, v.audio))
+
+
+def test_evaluate_lays_rows_out_longest_first_and_keeps_dataset_order(monkeypatch):
+    """scripts.evaluate.evaluate and data.dataset.DeviceDataset: rows longest video first, descriptors (and so the
+    per-video metrics) in dataset order; the means equal the reference loop's (scripts/evaluate.py:12-42) on the
+    same per-video scores."""
+    from oracle import av_oracle
+    from avsum_b200 import runtime
+    from avsum_b200.data.dataset import DeviceDataset
+    from avsum_b200.scripts.evaluate import evaluate
+    lengths = [23, 64, 23, 9, 51]
+    vids = _mixed_videos(lengths, seed0=900)
+    rng = np.random.default_rng(3)
+    dataset = [({"visual": v.visual, "audio": v.audio}, torch.as_tensor(rng.random(v.T).astype(np.float32)))
+               for v in vids]
+
+    def metrics_on_host(pred, target, row_start, lengths_):
+        rows = []
+        for s, n in zip(np.asarray(row_start), np.asarray(lengths_)):
+            p, t = pred[s:s + n].numpy(), target[s:s + n].numpy()
+            rows.append(list(av_oracle.eval_metrics(p, t)) + [float(np.mean(p))])
+        return np.asarray(rows, np.float64), np.zeros((len(rows), 8), np.int64)
+
+    monkeypatch.setattr(runtime, "eval_metrics_rows", metrics_on_host)
+    want = [av_oracle.eval_metrics(_StubNative._row_scores(f["visual"], f["audio"]).numpy(), t.numpy())
+            for f, t in dataset]
+    model = _StubModel()
+    out, per_video, _ = evaluate(model, dataset, return_per_video=True)
+    rs, ln, _axis = model.nat.calls[0]
+    assert list(ln) == lengths                                           # descriptors stay in dataset order
+    assert list(rs[np.argsort(-ln, kind="stable")]) == list(np.concatenate([[0], np.cumsum(sorted(lengths, reverse=True))[:-1]]))
+    assert np.array_equal(per_video[:, :3], np.asarray(want))
+    assert out["f1"] == np.mean([w[0] for w in want]) and out["spearman"] == np.mean([w[1] for w in want])
+    assert out["kendall"] == np.mean(np.asarray([w[2] for w in want], np.float32))
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)        # DeviceDataset refuses without CUDA
+    dd = DeviceDataset(dataset, device="cpu")
+    assert len(dd) == len(dataset) and list(dd.lengths) == lengths
+    for i, (f, t) in enumerate(dataset):                                  # items come back in dataset order
+        assert torch.equal(dd[i][0]["visual"], f["visual"]) and torch.equal(dd[i][0]["audio"], f["audio"])
+        assert torch.equal(dd[i][1], t)
+    assert dd.visual.shape[0] == sum(lengths) and torch.equal(dd.visual[:64], dataset[1][0]["visual"])   # longest first
+    model2 = _StubModel()
+    out2, per_video2, _ = evaluate(model2, dd, return_per_video=True)
+    assert np.array_equal(per_video2, per_video) and out2 == out
