@@ -33,7 +33,7 @@ EXPORTS = [
     "avs_bilstm_pair_train", "avs_bilstm_pair_bwd", "avs_linear_bwd", "avs_forward_summarize",
     "avs_debug_e2e_trace", "avs_forward_summarize_async", "avs_slot_wait",
     "avs_debug_gemm_trace", "avs_model_update_async", "avs_host_alloc", "avs_host_free",
-    "avs_model_set_feature_format",
+    "avs_model_set_feature_format", "avs_debug_plan",
 ]
 
 
@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
     L.avs_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t, C.c_int]
     L.avs_host_free.restype = C.c_int
     L.avs_host_free.argtypes = [vp]
+    L.avs_debug_plan.restype = C.c_int
+    L.avs_debug_plan.argtypes = [i32, vp, vp, i64, vp, vp, vp, i32]
     L.avs_model_destroy.restype = None
     L.avs_model_destroy.argtypes = [vp]
     L.avs_forward.restype = C.c_int
@@ -177,6 +179,25 @@ def np_ptr(a):
     """void* of a C-contiguous numpy array (host descriptor arrays)."""
     assert a.flags["C_CONTIGUOUS"]
     return C.c_void_p(a.ctypes.data)
+
+
+def recurrence_plan(row_start, lengths, total_rows=None):
+    """avs_debug_plan: the recurrence groups avs_forward cuts a batch into (host logic, no GPU needed).
+    Returns a dict: group_of [n] (-1 for empty videos), n_groups, slots_per_group, rows_ordered_by_group (what the
+    per-group schedule needs), groups_end_apart, group_rows [n_groups, 2] or None."""
+    import numpy as np
+    rs = np.ascontiguousarray(row_start, dtype=np.int32)
+    ln = np.ascontiguousarray(lengths, dtype=np.int32)
+    n = int(rs.size)
+    total = int((rs.astype(np.int64) + ln).max()) if total_rows is None and n else int(total_rows or 0)
+    group_of = np.full(max(n, 1), -1, dtype=np.int32)
+    info = np.zeros(4, dtype=np.int32)
+    rows = np.zeros((64, 2), dtype=np.int64)
+    check(lib().avs_debug_plan(n, np_ptr(rs), np_ptr(ln), total, np_ptr(group_of), np_ptr(info), np_ptr(rows), 64))
+    g = int(info[0])
+    return {"group_of": group_of[:n].copy(), "n_groups": g, "slots_per_group": int(info[1]),
+            "rows_ordered_by_group": bool(info[2]), "groups_end_apart": bool(info[3]),
+            "group_rows": rows[:g].copy() if info[2] and g <= 64 else None}
 
 
 def launch_count() -> int:

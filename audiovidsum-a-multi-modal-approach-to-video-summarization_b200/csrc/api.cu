@@ -459,6 +459,7 @@ avs_status validate_videos(int64_t total_rows, int32_t n, const int32_t* row_sta
 // Length-sorted grouping of videos into LSTM clusters.
 struct LstmPlan {
     std::vector<int32_t> host;  // [slot_row_start | slot_len | group_maxlen]
+    std::vector<int32_t> video; // [slot] -> index of the video in the caller's descriptors, -1 = empty slot
     int nb = 1, n_groups = 0;
 };
 LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, bool tensor_core) {
@@ -497,6 +498,7 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
     p.n_groups = (B + per_cluster - 1) / per_cluster;
     const int slots = p.n_groups * p.nb;
     p.host.assign(2 * slots + p.n_groups, 0);
+    p.video.assign(slots, -1);
     // Uneven split: the extra videos go to the SHORTEST groups.  The longest group is the critical chain and the last
     // to finish; the row-parallel work behind its recurrence (pipelined tail) is what the step still has to wait for,
     // so it gets the fewest rows.  (AVS_PLAN_REM_FIRST=1: extras to the longest groups, the round-1 split; A/B aid.)
@@ -509,6 +511,7 @@ LstmPlan plan_lstm(int32_t n, const int32_t* row_start, const int32_t* lengths, 
         for (int i = 0; i < cnt; ++i, ++idx) {
             p.host[g * p.nb + i] = row_start[order[idx]];
             p.host[slots + g * p.nb + i] = lengths[order[idx]];
+            p.video[g * p.nb + i] = order[idx];
         }
     }
     return p;
@@ -596,6 +599,36 @@ void avs_profile_read(double* ms, int64_t* calls) {
 avs_status avs_debug_lstm_trace(uint64_t* out8) {
     AVS_CHECK(out8 != nullptr, AVS_ERR_INVALID, "null pointer");
     return lstm_trace_read(reinterpret_cast<unsigned long long*>(out8));
+}
+
+/* Host logic only (no GPU work, callable without a device): the recurrence plan avs_forward derives from a batch's
+ * descriptors.  group_of[n_videos] = recurrence group of every video (-1: empty video); info[0] = groups, info[1] =
+ * slots per group, info[2] = 1 when the groups tile the rows in order (what the per-group schedule needs: rows laid out
+ * longest video first), info[3] = 1 when the groups end at different times (shortest group's longest video <= 0.9 x
+ * the longest group's); group_rows[2 g], [2 g + 1] = row range of group g when info[2] (max_groups entries at most). */
+avs_status avs_debug_plan(int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int64_t total_rows,
+                          int32_t* group_of, int32_t* info, int64_t* group_rows, int32_t max_groups) {
+    AVS_CHECK(info != nullptr && (n_videos == 0 || group_of != nullptr), AVS_ERR_INVALID, "null pointer");
+    int max_len = 0;
+    AVS_TRY(validate_videos(total_rows, n_videos, row_start, lengths, &max_len));
+    const LstmPlan plan = plan_lstm(n_videos, row_start, lengths, true);
+    for (int b = 0; b < n_videos; ++b) group_of[b] = -1;
+    for (int g = 0; g < plan.n_groups; ++g)
+        for (int i = 0; i < plan.nb; ++i)
+            if (plan.video[g * plan.nb + i] >= 0) group_of[plan.video[g * plan.nb + i]] = g;
+    std::vector<int64_t> glo, ghi;
+    const bool ordered = plan.n_groups > 0 && group_row_ranges(plan, total_rows, glo, ghi);
+    const int slots = plan.n_groups * plan.nb;
+    info[0] = plan.n_groups;
+    info[1] = plan.nb;
+    info[2] = ordered ? 1 : 0;
+    info[3] = (plan.n_groups > 0 && plan.host[2 * slots + plan.n_groups - 1] * 10ll <= plan.host[2 * slots] * 9ll) ? 1 : 0;
+    if (ordered && group_rows)
+        for (int g = 0; g < plan.n_groups && g < max_groups; ++g) {
+            group_rows[2 * g] = glo[g];
+            group_rows[2 * g + 1] = ghi[g];
+        }
+    return AVS_OK;
 }
 
 /* Debugging aid: with AVS_BPTT_TRACE=1 the tensor-core BPTT kernel accumulates clock64 deltas of its per-step chain on

@@ -292,6 +292,17 @@ avs_status avs_debug_gemm_trace(uint64_t* out8);
  * out20[18] = pooling + knapsack finished, out20[19] = last D2H copy finished. */
 avs_status avs_debug_e2e_trace(double* out20);
 
+/* Host logic only (no GPU work; callable on a machine without a device): the recurrence plan avs_forward derives from
+ * a batch's descriptors -- videos sorted by length (stable) and cut into groups of one recurrence cluster set each.
+ * group_of[n_videos] = group of every video (-1: empty video); info[0] = number of groups, info[1] = slots per group,
+ * info[2] = 1 when the groups tile the rows in order (rows laid out longest video first: what the per-group
+ * schedule of DESIGN.md section 4 needs; otherwise the forward runs one launch per stage over all rows),
+ * info[3] = 1 when the groups end at different times (the shortest group's longest video <= 0.9 x the longest
+ * group's); group_rows[2 g], [2 g + 1] = row range of group g when info[2] (at most max_groups pairs; may be NULL).
+ * Used by the CPU tests of the callers' row layout (evaluate, summarize_videos, packed_batches, DeviceDataset). */
+avs_status avs_debug_plan(int32_t n_videos, const int32_t* row_start, const int32_t* lengths, int64_t total_rows,
+                          int32_t* group_of, int32_t* info, int64_t* group_rows, int32_t max_groups);
+
 #ifdef __cplusplus
 }
 #endif

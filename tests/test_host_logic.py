@@ -317,3 +317,76 @@ def test_evaluate_lays_rows_out_longest_first_and_keeps_dataset_order(monkeypatc
     model2 = _StubModel()
     out2, per_video2, _ = evaluate(model2, dd, return_per_video=True)
     assert np.array_equal(per_video2, per_video) and out2 == out
+
+
+# ---- the recurrence plan of the native library (avs_debug_plan: host logic of avs_forward, no GPU work) -------------
+
+def _layout_longest_first(lengths):
+    """row_start in the callers' layout: rows longest video first, descriptors in the caller's order."""
+    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
+    rs, at = np.zeros(len(lengths), np.int32), 0
+    for i in order:
+        rs[i] = at
+        at += lengths[i]
+    return rs
+
+
+def test_recurrence_plan_of_config2_takes_the_per_group_schedule(native_lib):
+    """config 2 = 7 groups of 8 slots, the extra video of the uneven split in the SHORTEST group,
+    groups tiling the rows in order when the rows are laid out longest video first -- in the callers' order of the
+    descriptors (evaluate / DeviceDataset) as well as in sorted order (packed_batches)."""
+    from avsum_b200 import _cabi
+    lengths = [v.T for v in synth.config2()]
+    plan = _cabi.recurrence_plan(_layout_longest_first(lengths), lengths)
+    assert plan["n_groups"] == 7 and plan["slots_per_group"] == 8
+    assert plan["rows_ordered_by_group"] and plan["groups_end_apart"]
+    sizes = np.bincount(plan["group_of"], minlength=7)
+    assert list(sizes) == [7, 7, 7, 7, 7, 7, 8] and sizes.sum() == 50
+    by_len = sorted(range(50), key=lambda i: -lengths[i])
+    assert list(plan["group_of"][by_len]) == sorted(plan["group_of"])               # groups follow the length order
+    rows = plan["group_rows"]
+    assert rows[0, 0] == 0 and rows[-1, 1] == 21_477 and np.all(rows[1:, 0] == rows[:-1, 1])
+    assert rows[0, 1] == sum(sorted(lengths, reverse=True)[:7]) == 4_522            # the 72 CTA-pair tiles of DESIGN 4
+    # the same videos packed in the caller's (unsorted) order: same groups, but no group owns a block of rows
+    unsorted = _cabi.recurrence_plan(np.concatenate([[0], np.cumsum(lengths)[:-1]]), lengths)
+    assert np.array_equal(unsorted["group_of"], plan["group_of"]) and not unsorted["rows_ordered_by_group"]
+    assert unsorted["group_rows"] is None
+
+
+def test_recurrence_plan_edge_cases(native_lib):
+    from avsum_b200 import _cabi
+    # ties across a group boundary: the native sort is stable like the callers', so the layout still tiles
+    lengths = [300] * 20 + [100] * 5
+    plan = _cabi.recurrence_plan(_layout_longest_first(lengths), lengths)
+    assert plan["n_groups"] == 4 and plan["rows_ordered_by_group"]
+    assert not _cabi.recurrence_plan(_layout_longest_first([320] * 24), [320] * 24)["groups_end_apart"]
+    # empty videos take no slot; padded layouts (rows no video owns) never tile
+    lengths = [40, 0, 25, 0, 31]
+    plan = _cabi.recurrence_plan(_layout_longest_first(lengths), lengths)
+    assert plan["n_groups"] == 2                                  # <= 8 videos: two per cluster ...
+    assert list(plan["group_of"]) == [0, -1, 1, -1, 1]            # ... the extra video in the SHORTEST group
+    padded = _cabi.recurrence_plan([0, 50, 100], [40, 25, 31], total_rows=150)
+    assert not padded["rows_ordered_by_group"]
+    # small batches: 4 videos per cluster up to 16 videos, 8 for 17 - 64, wider clusters (one wave of 16) beyond
+    assert _cabi.recurrence_plan(np.arange(16) * 10, [10] * 16)["n_groups"] == 4
+    assert _cabi.recurrence_plan(np.arange(17) * 10, [10] * 17)["slots_per_group"] == 8
+    assert _cabi.recurrence_plan(np.arange(64) * 10, [10] * 64)["slots_per_group"] == 8
+    assert _cabi.recurrence_plan(np.arange(65) * 10, [10] * 65)["slots_per_group"] == 32
+    empty = _cabi.recurrence_plan([], [])
+    assert empty["n_groups"] == 0 and not empty["rows_ordered_by_group"]
+    with pytest.raises(ValueError, match="outside"):
+        _cabi.recurrence_plan([0, 5], [10, 10], total_rows=12)
+
+
+def test_callers_layout_matches_the_native_plan(native_lib):
+    """What summarize_videos / evaluate hand to the native call is a layout the per-group schedule accepts."""
+    from avsum_b200 import _cabi
+    from avsum_b200.evaluation.summary import summarize_videos
+    rng = np.random.default_rng(11)
+    lengths = [int(t) for t in rng.integers(20, 90, 30)]
+    vids = _mixed_videos(lengths, seed0=3000)
+    model = _StubModel()
+    summarize_videos(model, vids)
+    rs, ln, _ = model.nat.calls[0]
+    plan = _cabi.recurrence_plan(rs, ln)
+    assert plan["rows_ordered_by_group"] and plan["n_groups"] == 4 and plan["slots_per_group"] == 8
