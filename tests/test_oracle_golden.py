@@ -152,3 +152,69 @@ def test_generate_summary_budget_and_bitmap():
     # degenerate inputs
     picks, summary, _ = av_oracle.generate_summary(np.zeros(0, np.float32), np.zeros((0, 2), np.int32), 0, np.zeros(0, np.int32))
     assert picks.size == 0 and summary.size == 0
+
+
+_LIVE = r'''
+import os, sys, types
+sys.dont_write_bytecode = True
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(1, "/root/reference")
+import numpy as np, torch
+stub = types.ModuleType("fastdtw"); stub.fastdtw = lambda *a, **k: None
+sys.modules.setdefault("fastdtw", stub)
+from models.av_model import AVBiLSTMModel            # the reference itself
+from models.attention import MultiHeadSelfAttention
+import avsum_b200
+from oracle import av_oracle, av_oracle_torch
+worst = 0.0
+for case, (B, T, vd, ad, seed) in enumerate([(1, 57, 1024, 128, 11), (3, 23, 1024, 128, 12), (2, 9, 4096, 296, 13)]):
+    torch.manual_seed(100 + seed)
+    ref = AVBiLSTMModel(vd, ad, 512).eval()
+    with torch.no_grad():
+        ref.scorer[2].weight.mul_(50.0)
+        ref.attention.in_proj_weight[:2048].mul_(20.0 if case else 1.0)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    gen = torch.Generator().manual_seed(seed)
+    visual, audio = torch.randn(B, T, vd, generator=gen), torch.randn(B, T, ad, generator=gen)
+    port = av_oracle_torch.RefPortModel(vd, ad, 512).eval(); port.load_state_dict(sd)
+    with torch.no_grad():
+        want_lit = ref(visual, audio)
+        # temporal reading: the same module on the transposed tensor (SURVEY 3.2)
+        v_emb, a_emb = ref.visual_fc(visual), ref.audio_fc(audio)
+        fused = torch.cat([ref.visual_bilstm(v_emb)[0], ref.audio_bilstm(a_emb)[0]], dim=-1)
+        attn, _ = ref.attention(fused.transpose(0, 1), fused.transpose(0, 1), fused.transpose(0, 1))
+        want_tmp = ref.scorer(attn.transpose(0, 1)).squeeze()
+        assert torch.equal(port(visual, audio, "literal"), want_lit), "torch port differs from the reference (literal)"
+        assert torch.equal(port(visual, audio, "temporal"), want_tmp), "torch port differs from the reference (temporal)"
+    sd_np = {k: v.numpy() for k, v in sd.items()}
+    for axis, want in (("literal", want_lit), ("temporal", want_tmp)):
+        got = av_oracle.forward(sd_np, visual.numpy(), audio.numpy(), 4, axis)
+        assert got.shape == tuple(want.shape)
+        worst = max(worst, float(np.max(np.abs(got - want.numpy()))))
+torch.manual_seed(7)
+m = MultiHeadSelfAttention(1024, 4).eval()
+with torch.no_grad():
+    m.query.weight.mul_(12.0)
+x = torch.randn(2, 150, 1024, generator=torch.Generator().manual_seed(8))
+with torch.no_grad():
+    want = m(x).numpy()
+got = av_oracle.mhsa_forward({k: v.numpy() for k, v in m.state_dict().items()}, x.numpy(), 4)
+worst = max(worst, float(np.max(np.abs(got - want))))
+print("LIVE_OK %.3e" % worst)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference tree only exists in the build container")
+def test_oracles_match_the_imported_reference_on_fresh_inputs():
+    """Beyond the committed goldens: wherever /root/reference is present (the build container, never the GPU box) the
+    reference itself is imported in a child process and run on inputs / weights no fixture holds -- a new seed per
+    case, batch sizes 1 - 3, default 4096 / 296 dims, sharpened attention logits.  The torch port must be bit-identical
+    (literal and temporal axis), the numpy restatement within TOL, MultiHeadSelfAttention over three key blocks too."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-c", _LIVE, root], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("LIVE_OK")][-1]
+    assert float(line.split()[1]) < TOL
