@@ -1076,13 +1076,24 @@ def test_summarize_long_videos_on_clusters_bit_exact(native, n_vid, prop):
     lens = [v.T for v in vids]
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:      # which kernel made the selection?
-        picks, seg_mean, summary, cps_start, sum_start = native.summarize_rows(
+
+    def run():
+        out = native.summarize_rows(
             torch.from_numpy(np.concatenate(scores)).cuda(),
             torch.from_numpy(np.concatenate([v.positions for v in vids]).astype(np.int32)).cuda(), starts, lens,
             [v.n_frames for v in vids], [v.cps for v in vids], prop)
         torch.cuda.synchronize()
-    kernels = " ".join(e.key for e in prof.key_averages())
+        return out
+
+    res, kernels = None, ""
+    try:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:      # which kernel made the selection?
+            res = run()
+        kernels = " ".join(e.key for e in prof.key_averages())
+    except Exception:       # no CUPTI (another subscriber holds it): the parity check below does not depend on it
+        if res is None:
+            res = run()
+    picks, seg_mean, summary, cps_start, sum_start = res
     if "knapsack" in kernels:          # (CUPTI records available)
         want_kernel = {3: "knapsack_cluster_kernel<8>", 20: "knapsack_cluster_kernel<4>", 30: "knapsack_cluster_kernel<4>",
                        9: "knapsack_fast_kernel"}[n_vid]
